@@ -1,0 +1,558 @@
+/*
+ * ude_oracle_impl.h -- precision-generic body of the oracle (included twice by
+ * ude_oracle.c with REAL=double/SUF=_f64 and REAL=float/SUF=_f32).
+ * TEST INFRASTRUCTURE ONLY -- see ude_oracle.h for scope and citations.
+ */
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+#define FN(name) CAT(name, SUF)
+
+/* ---------------------------------------------------------------- chain ---- */
+/* Dense layer l: h <- act(W h + b), W is out x in stored column-major followed
+ * by b -- the layout Lux ComponentVector (scenario_1.jl:113), DiffEqFlux
+ * initial_params (seir_exposure.jl:115) and Flux.destructure
+ * (Fisher-KPP-CNN.jl:106) produce. */
+static inline REAL FN(act_fwd)(int act, REAL a)
+{
+    switch (act) {
+    case UDE_ACT_TANH: return R_TANH(a);
+    case UDE_ACT_RBF: return R_EXP(-(a * a));      /* rbf(x) = exp(-x^2), scenario_1.jl:59 */
+    default: return a;
+    }
+}
+/* derivative of the activation given pre-activation a and output h */
+static inline REAL FN(act_der)(int act, REAL a, REAL h)
+{
+    switch (act) {
+    case UDE_ACT_TANH: return (REAL)1 - h * h;
+    case UDE_ACT_RBF: return (REAL)-2 * a * h;
+    default: return (REAL)1;
+    }
+}
+
+/* forward keeping every layer's pre-activation (pre) and output (hs); hs[0] = input */
+static void FN(chain_forward_store)(const ude_model *m, const REAL *th, const REAL *x,
+                                    REAL hs[][UDE_MAX_WIDTH], REAL pre[][UDE_MAX_WIDTH])
+{
+    for (int i = 0; i < m->widths[0]; ++i) hs[0][i] = x[i];
+    const REAL *p = th;
+    for (int l = 0; l < m->n_layers; ++l) {
+        const int nin = m->widths[l], nout = m->widths[l + 1];
+        const REAL *W = p, *b = p + (size_t)nin * nout;
+        for (int j = 0; j < nout; ++j) {
+            REAL a = b[j];
+            for (int i = 0; i < nin; ++i) a += W[(size_t)i * nout + j] * hs[l][i];
+            pre[l][j] = a;
+            hs[l + 1][j] = FN(act_fwd)(m->acts[l], a);
+        }
+        p += (size_t)nin * nout + nout;
+    }
+}
+
+void FN(ude_mlp_forward)(const ude_model *m, const REAL *th, const REAL *x, REAL *y)
+{
+    REAL hs[UDE_MAX_LAYERS + 1][UDE_MAX_WIDTH], pre[UDE_MAX_LAYERS][UDE_MAX_WIDTH];
+    FN(chain_forward_store)(m, th, x, hs, pre);
+    for (int j = 0; j < m->widths[m->n_layers]; ++j) y[j] = hs[m->n_layers][j];
+}
+
+/* reverse sweep: given dy (cotangent of the chain output) return dx and add w * dtheta */
+static void FN(chain_vjp)(const ude_model *m, const REAL *th, REAL hs[][UDE_MAX_WIDTH],
+                          REAL pre[][UDE_MAX_WIDTH], const REAL *dy, REAL *dx, REAL *gth, REAL w)
+{
+    size_t off[UDE_MAX_LAYERS];
+    size_t o = 0;
+    for (int l = 0; l < m->n_layers; ++l) {
+        off[l] = o;
+        o += (size_t)m->widths[l] * m->widths[l + 1] + m->widths[l + 1];
+    }
+    REAL g[UDE_MAX_WIDTH], gin[UDE_MAX_WIDTH];
+    for (int j = 0; j < m->widths[m->n_layers]; ++j) g[j] = dy[j];
+    for (int l = m->n_layers - 1; l >= 0; --l) {
+        const int nin = m->widths[l], nout = m->widths[l + 1];
+        const REAL *W = th + off[l];
+        REAL *gW = gth ? gth + off[l] : NULL;
+        REAL *gb = gth ? gW + (size_t)nin * nout : NULL;
+        for (int j = 0; j < nout; ++j) g[j] *= FN(act_der)(m->acts[l], pre[l][j], hs[l + 1][j]);
+        for (int i = 0; i < nin; ++i) {
+            REAL s = 0;
+            for (int j = 0; j < nout; ++j) {
+                s += W[(size_t)i * nout + j] * g[j];
+                if (gW) gW[(size_t)i * nout + j] += w * g[j] * hs[l][i];
+            }
+            gin[i] = s;
+        }
+        if (gb) for (int j = 0; j < nout; ++j) gb[j] += w * g[j];
+        for (int i = 0; i < nin; ++i) g[i] = gin[i];
+    }
+    for (int i = 0; i < m->widths[0]; ++i) dx[i] = g[i];
+}
+
+static size_t FN(chain_len)(const ude_model *m)
+{
+    size_t o = 0;
+    for (int l = 0; l < m->n_layers; ++l)
+        o += (size_t)m->widths[l] * m->widths[l + 1] + m->widths[l + 1];
+    return o;
+}
+
+/* ------------------------------------------------------------------ RHS ---- */
+void FN(ude_rhs)(const ude_model *m, const REAL *th, const REAL *u, REAL *du)
+{
+    const REAL *thc = th + m->n_prefix;
+    REAL hs[UDE_MAX_LAYERS + 1][UDE_MAX_WIDTH], pre[UDE_MAX_LAYERS][UDE_MAX_WIDTH];
+    const int L = m->n_layers;
+    switch (m->model) {
+    case UDE_MODEL_LV: {
+        /* du1 = a1*u1 + NN1(u); du2 = -a2*u2 + NN2(u)   (scenario_1.jl:69-73)
+         * a1,a2 fixed (p_[1], p_[4]) | a2 = theta[0] (scenario_2.jl:90-95)
+         * | a1,a2 = theta[0:2] (hudson_bay.jl:85-91) */
+        REAL a1 = (REAL)m->consts[0], a2 = (REAL)m->consts[1];
+        if (m->n_prefix == 1) a2 = th[0];
+        if (m->n_prefix == 2) { a1 = th[0]; a2 = th[1]; }
+        FN(chain_forward_store)(m, thc, u, hs, pre);
+        du[0] = a1 * u[0] + hs[L][0];
+        du[1] = -a2 * u[1] + hs[L][1];
+        break;
+    }
+    case UDE_MODEL_SEIR: {
+        /* seir_exposure.jl:117-130; consts = F, b0, alpha, kappa, mu, sigma, gamma, d, lambda (:33) */
+        const REAL F = (REAL)m->consts[0], b0 = (REAL)m->consts[1], mu = (REAL)m->consts[4],
+                   sg = (REAL)m->consts[5], gm = (REAL)m->consts[6], dd = (REAL)m->consts[7],
+                   lm = (REAL)m->consts[8];
+        const REAL S = u[0], E = u[1], I = u[2], R = u[3], N = u[4], D = u[5];
+        REAL x[3] = { S / N, I, D / N };
+        FN(chain_forward_store)(m, thc, x, hs, pre);
+        const REAL z = hs[L][0];
+        du[0] = -b0 * S * F / N - z - mu * S;
+        du[1] = b0 * S * F / N + z - (sg + mu) * E;
+        du[2] = sg * E - (gm + mu) * I;
+        du[3] = gm * I - mu * R;
+        du[4] = -mu * N;
+        du[5] = dd * gm * I - lm * D;
+        du[6] = sg * E;
+        break;
+    }
+    case UDE_MODEL_FKPP: {
+        /* Fisher-KPP-CNN.jl:111-126: pointwise reaction net + D0 * 3-tap periodic stencil;
+         * theta suffix = [w1, w2, w3, conv bias (unused), D0] (:106-109) */
+        const REAL *sx = thc + FN(chain_len)(m);
+        const REAL w1 = sx[0], w2 = sx[1], w3 = sx[2], D0 = sx[4];
+        const int n = m->d;
+        for (int i = 0; i < n; ++i) {
+            const REAL um = u[(i + n - 1) % n], up = u[(i + 1) % n];
+            FN(chain_forward_store)(m, thc, &u[i], hs, pre);
+            du[i] = hs[L][0] + D0 * (w1 * um + w2 * u[i] + w3 * up);
+        }
+        break;
+    }
+    default: /* UDE_MODEL_NODE: du = NN(u) */
+        FN(chain_forward_store)(m, thc, u, hs, pre);
+        for (int k = 0; k < m->d; ++k) du[k] = hs[L][k];
+    }
+}
+
+/* dlam = J_u^T lam; gth += w * J_theta^T lam  (what ReverseDiffVJP provides,
+ * seir_exposure.jl:71) */
+void FN(ude_rhs_vjp)(const ude_model *m, const REAL *th, const REAL *u, const REAL *lam,
+                     REAL *dlam, REAL *gth, REAL w)
+{
+    const REAL *thc = th + m->n_prefix;
+    REAL *gthc = gth ? gth + m->n_prefix : NULL;
+    REAL hs[UDE_MAX_LAYERS + 1][UDE_MAX_WIDTH], pre[UDE_MAX_LAYERS][UDE_MAX_WIDTH];
+    REAL dx[UDE_MAX_WIDTH];
+    switch (m->model) {
+    case UDE_MODEL_LV: {
+        REAL a1 = (REAL)m->consts[0], a2 = (REAL)m->consts[1];
+        if (m->n_prefix == 1) a2 = th[0];
+        if (m->n_prefix == 2) { a1 = th[0]; a2 = th[1]; }
+        FN(chain_forward_store)(m, thc, u, hs, pre);
+        FN(chain_vjp)(m, thc, hs, pre, lam, dx, gthc, w);
+        dlam[0] = a1 * lam[0] + dx[0];
+        dlam[1] = -a2 * lam[1] + dx[1];
+        if (gth && m->n_prefix == 1) gth[0] += w * (-u[1] * lam[1]);
+        if (gth && m->n_prefix == 2) { gth[0] += w * (u[0] * lam[0]); gth[1] += w * (-u[1] * lam[1]); }
+        break;
+    }
+    case UDE_MODEL_SEIR: {
+        const REAL F = (REAL)m->consts[0], b0 = (REAL)m->consts[1], mu = (REAL)m->consts[4],
+                   sg = (REAL)m->consts[5], gm = (REAL)m->consts[6], dd = (REAL)m->consts[7],
+                   lm = (REAL)m->consts[8];
+        const REAL S = u[0], I = u[2], N = u[4], D = u[5];
+        (void)I;
+        REAL x[3] = { S / N, u[2], D / N };
+        FN(chain_forward_store)(m, thc, x, hs, pre);
+        REAL dz = lam[1] - lam[0];               /* z enters dS with -, dE with + */
+        FN(chain_vjp)(m, thc, hs, pre, &dz, dx, gthc, w);
+        const REAL c = b0 * F / N;               /* d(b0*S*F/N)/dS */
+        const REAL cN = -b0 * S * F / (N * N);   /* d(b0*S*F/N)/dN */
+        /* columns of J: contributions to dlam[k] = sum_r lam[r] * d f_r / d u_k */
+        dlam[0] = lam[0] * (-c - mu) + lam[1] * c + dx[0] / N;
+        dlam[1] = lam[1] * (-(sg + mu)) + lam[2] * sg + lam[6] * sg;
+        dlam[2] = lam[2] * (-(gm + mu)) + lam[3] * gm + lam[5] * dd * gm + dx[1];
+        dlam[3] = lam[3] * (-mu);
+        dlam[4] = lam[0] * (-cN) + lam[1] * cN + lam[4] * (-mu)
+                  - dx[0] * S / (N * N) - dx[2] * D / (N * N);
+        dlam[5] = lam[5] * (-lm) + dx[2] / N;
+        dlam[6] = 0;
+        break;
+    }
+    case UDE_MODEL_FKPP: {
+        const size_t cl = FN(chain_len)(m);
+        const REAL *sx = thc + cl;
+        REAL *gsx = gthc ? gthc + cl : NULL;
+        const REAL w1 = sx[0], w2 = sx[1], w3 = sx[2], D0 = sx[4];
+        const int n = m->d;
+        for (int i = 0; i < n; ++i) dlam[i] = 0;
+        for (int i = 0; i < n; ++i) {
+            const int im = (i + n - 1) % n, ip = (i + 1) % n;
+            FN(chain_forward_store)(m, thc, &u[i], hs, pre);
+            FN(chain_vjp)(m, thc, hs, pre, &lam[i], dx, gthc, w);
+            dlam[i] += dx[0] + D0 * w2 * lam[i];
+            dlam[im] += D0 * w1 * lam[i];
+            dlam[ip] += D0 * w3 * lam[i];
+            if (gsx) {
+                gsx[0] += w * D0 * u[im] * lam[i];
+                gsx[1] += w * D0 * u[i] * lam[i];
+                gsx[2] += w * D0 * u[ip] * lam[i];
+                gsx[4] += w * (w1 * u[im] + w2 * u[i] + w3 * u[ip]) * lam[i];
+            }
+        }
+        break;
+    }
+    default:
+        FN(chain_forward_store)(m, thc, u, hs, pre);
+        FN(chain_vjp)(m, thc, hs, pre, lam, dx, gthc, w);
+        for (int k = 0; k < m->d; ++k) dlam[k] = dx[k];
+    }
+}
+
+/* ---------------------------------------------------------- RK stepping ---- */
+/* one explicit RK step with the generic tableau; ks[s][d] receives the stage derivatives.
+ * Tsit5: stage 7 argument IS u_new (row 7 = b, FSAL); Vern7: u_new from b. */
+static void FN(rk_step)(const ude_model *m, const REAL *th, const ude_tableau *tb, const REAL *u,
+                        REAL dt, const REAL *k1_in, REAL *ks, REAL *unew, REAL *err)
+{
+    const int d = m->d, s = tb->s;
+    REAL g[UDE_MAX_STATE];
+    if (k1_in) for (int k = 0; k < d; ++k) ks[k] = k1_in[k];
+    else FN(ude_rhs)(m, th, u, ks);
+    for (int i = 1; i < s; ++i) {
+        for (int k = 0; k < d; ++k) {
+            REAL acc = 0;
+            for (int j = 0; j < i; ++j) {
+                const REAL a = (REAL)tb->A[i][j];
+                if (a != 0) acc += a * ks[(size_t)j * d + k];
+            }
+            g[k] = u[k] + dt * acc;
+        }
+        if (tb->fsal && i == s - 1) for (int k = 0; k < d; ++k) unew[k] = g[k];
+        FN(ude_rhs)(m, th, g, ks + (size_t)i * d);
+    }
+    if (!tb->fsal) {
+        for (int k = 0; k < d; ++k) {
+            REAL acc = 0;
+            for (int j = 0; j < s; ++j) {
+                const REAL b = (REAL)tb->b[j];
+                if (b != 0) acc += b * ks[(size_t)j * d + k];
+            }
+            unew[k] = u[k] + dt * acc;
+        }
+    }
+    if (err) {
+        for (int k = 0; k < d; ++k) {
+            REAL acc = 0;
+            for (int j = 0; j < s; ++j) {
+                const REAL b = (REAL)tb->bt[j];
+                if (b != 0) acc += b * ks[(size_t)j * d + k];
+            }
+            err[k] = dt * acc;
+        }
+    }
+}
+
+static int FN(all_finite)(const REAL *x, int n)
+{
+    for (int i = 0; i < n; ++i) if (!isfinite((double)x[i])) return 0;
+    return 1;
+}
+
+int FN(ude_solve_fixed)(const ude_model *m, const REAL *th, const REAL *u0, REAL dt, int n_steps,
+                        int solver, int save_every, REAL *out, REAL *dense)
+{
+    const ude_tableau *tb = ude_get_tableau(solver);
+    const int d = m->d, s = tb->s;
+    REAL u[UDE_MAX_STATE], un[UDE_MAX_STATE];
+    REAL ks[UDE_MAX_STAGES * UDE_MAX_STATE], kf[UDE_MAX_STATE];
+    int have_fsal = 0, isave = 0;
+    for (int k = 0; k < d; ++k) u[k] = u0[k];
+    for (int k = 0; k < d; ++k) out[(size_t)isave * d + k] = u[k];
+    ++isave;
+    for (int n = 0; n < n_steps; ++n) {
+        FN(rk_step)(m, th, tb, u, dt, have_fsal ? kf : NULL, ks, un, NULL);
+        if (dense) memcpy(dense + (size_t)n * s * d, ks, sizeof(REAL) * (size_t)s * d);
+        if (tb->fsal) { memcpy(kf, ks + (size_t)(s - 1) * d, sizeof(REAL) * d); have_fsal = 1; }
+        for (int k = 0; k < d; ++k) u[k] = un[k];
+        if ((n + 1) % save_every == 0) {
+            for (int k = 0; k < d; ++k) out[(size_t)isave * d + k] = u[k];
+            ++isave;
+        }
+        if (!FN(all_finite)(u, d)) return -1;
+    }
+    return 0;
+}
+
+/* Tsit5 free 4th-order interpolant weights b_i(Theta), i = 1..7 (Tsitouras 2011;
+ * the r_ij block of OrdinaryDiffEq's Tsit5ConstantCache) */
+static void FN(tsit5_bTheta)(REAL Th, REAL *bw)
+{
+    const double *r = ude_tsit5_r;   /* r11 r12 r13 r14 | r22 r23 r24 | ... | r72 r73 r74 */
+    const REAL T2 = Th * Th;
+    bw[0] = Th * ((REAL)r[0] + Th * ((REAL)r[1] + Th * ((REAL)r[2] + Th * (REAL)r[3])));
+    for (int i = 1; i < 7; ++i) {
+        const double *ri = r + 4 + 3 * (i - 1);
+        bw[i] = T2 * ((REAL)ri[0] + Th * ((REAL)ri[1] + Th * (REAL)ri[2]));
+    }
+}
+
+/* RMS error norm of OrdinaryDiffEq (ODE_DEFAULT_NORM) on err/(abstol + reltol*max(|u|,|unew|)) */
+static REAL FN(eest)(const REAL *err, const REAL *u, const REAL *un, int d, REAL abstol, REAL reltol)
+{
+    REAL acc = 0;
+    for (int k = 0; k < d; ++k) {
+        const REAL a = R_FABS(u[k]), b = R_FABS(un[k]);
+        const REAL sc = abstol + reltol * (a > b ? a : b);
+        const REAL e = err[k] / sc;
+        acc += e * e;
+    }
+    return R_SQRT(acc / (REAL)d);
+}
+
+int FN(ude_solve_adaptive)(const ude_model *m, const REAL *th, const REAL *u0, const REAL *saveat,
+                           int n_save, REAL abstol, REAL reltol, int solver, REAL *out,
+                           int *n_rejected)
+{
+    const ude_tableau *tb = ude_get_tableau(solver);
+    const int d = m->d, s = tb->s, order = tb->order;
+    const REAL t0 = saveat[0], t1 = saveat[n_save - 1];
+    /* OrdinaryDiffEq defaults: gamma=9/10, qmin=1/5, qmax=10, beta2=2/(5*order), beta1=7/(10*order),
+     * qsteady in [1, 1.2], qoldinit=1e-4 */
+    const REAL gamma = (REAL)0.9, qmin = (REAL)0.2, qmax = (REAL)10;
+    const REAL beta2 = (REAL)2 / ((REAL)5 * order), beta1 = (REAL)7 / ((REAL)10 * order);
+    REAL qold = (REAL)1e-4;
+    REAL u[UDE_MAX_STATE], un[UDE_MAX_STATE], err[UDE_MAX_STATE], f0[UDE_MAX_STATE], f1[UDE_MAX_STATE];
+    REAL ks[UDE_MAX_STAGES * UDE_MAX_STATE], kf[UDE_MAX_STATE];
+    for (int k = 0; k < d; ++k) u[k] = u0[k];
+    for (int k = 0; k < d; ++k) out[k] = u[k];
+    int isave = 1, nacc = 0, nrej = 0;
+    /* initial dt: Hairer-Norsett-Wanner heuristic as in OrdinaryDiffEq's ode_determine_initdt */
+    REAL dt;
+    {
+        FN(ude_rhs)(m, th, u, f0);
+        REAL d0 = 0, d1 = 0, d2 = 0;
+        for (int k = 0; k < d; ++k) {
+            const REAL sk = abstol + reltol * R_FABS(u[k]);
+            d0 += (u[k] / sk) * (u[k] / sk);
+            d1 += (f0[k] / sk) * (f0[k] / sk);
+        }
+        d0 = R_SQRT(d0 / d); d1 = R_SQRT(d1 / d);
+        REAL dt0 = (d0 < (REAL)1e-5 || d1 < (REAL)1e-5) ? (REAL)1e-6 : (REAL)0.01 * d0 / d1;
+        if (dt0 > t1 - t0) dt0 = t1 - t0;
+        for (int k = 0; k < d; ++k) un[k] = u[k] + dt0 * f0[k];
+        FN(ude_rhs)(m, th, un, f1);
+        for (int k = 0; k < d; ++k) {
+            const REAL sk = abstol + reltol * R_FABS(u[k]);
+            const REAL e = (f1[k] - f0[k]) / sk;
+            d2 += e * e;
+        }
+        d2 = R_SQRT(d2 / d) / dt0;
+        const REAL dm = d1 > d2 ? d1 : d2;
+        REAL dt1 = dm <= (REAL)1e-15 ? (dt0 * (REAL)1e-3 > (REAL)1e-6 ? dt0 * (REAL)1e-3 : (REAL)1e-6)
+                                     : R_POW((REAL)10, -((REAL)2 + R_LOG10(dm)) / (REAL)order);
+        dt = (REAL)100 * dt0 < dt1 ? (REAL)100 * dt0 : dt1;
+        if (dt > t1 - t0) dt = t1 - t0;
+    }
+    memcpy(kf, f0, sizeof(REAL) * d);
+    int have_fsal = tb->fsal;
+    REAL t = t0;
+    const int use_interp = (solver == UDE_TSIT5);
+    int guard = 0;
+    while (isave < n_save && guard++ < 10000000) {
+        REAL tend = use_interp ? t1 : saveat[isave];
+        REAL h = dt;
+        int clipped = 0;
+        if (t + h >= tend - (REAL)1e-12 * R_FABS(tend)) { h = tend - t; clipped = 1; }
+        FN(rk_step)(m, th, tb, u, h, have_fsal ? kf : NULL, ks, un, err);
+        const REAL EEst = FN(eest)(err, u, un, d, abstol, reltol);
+        if (!isfinite((double)EEst)) { if (n_rejected) *n_rejected = nrej; return -1; }
+        const REAL q11 = R_POW(EEst, beta1);
+        REAL q = q11 / R_POW(qold, beta2);
+        q = q / gamma;
+        if (q < (REAL)1 / qmax) q = (REAL)1 / qmax;
+        if (q > (REAL)1 / qmin) q = (REAL)1 / qmin;
+        if (EEst <= (REAL)1) {
+            ++nacc;
+            const REAL tn = t + h;
+            if (use_interp) {
+                while (isave < n_save && saveat[isave] <= tn + (REAL)1e-12 * R_FABS(tn)) {
+                    REAL Th = (saveat[isave] - t) / h, bw[7];
+                    if (Th > 1) Th = 1;
+                    FN(tsit5_bTheta)(Th, bw);
+                    for (int k = 0; k < d; ++k) {
+                        REAL acc = 0;
+                        for (int i = 0; i < 7; ++i) acc += bw[i] * ks[(size_t)i * d + k];
+                        out[(size_t)isave * d + k] = u[k] + h * acc;
+                    }
+                    ++isave;
+                }
+            } else if (clipped) {
+                for (int k = 0; k < d; ++k) out[(size_t)isave * d + k] = un[k];
+                ++isave;
+            }
+            qold = EEst > (REAL)1e-4 ? EEst : (REAL)1e-4;
+            if (q >= (REAL)1 && q <= (REAL)1.2) q = 1;     /* qsteady band: keep dt */
+            if (!clipped || h >= dt) dt = h / q; /* a clipped (shortened) step does not shrink the proposal */
+            else { const REAL prop = h / q; if (prop > dt) dt = prop; }
+            t = tn;
+            for (int k = 0; k < d; ++k) u[k] = un[k];
+            if (tb->fsal) { memcpy(kf, ks + (size_t)(s - 1) * d, sizeof(REAL) * d); have_fsal = 1; }
+        } else {
+            ++nrej;
+            REAL qr = q11 / gamma;
+            if (qr > (REAL)1 / qmin) qr = (REAL)1 / qmin;
+            dt = h / qr;
+            /* k1 of the rejected step is still f(u): reuse it */
+            memcpy(kf, ks, sizeof(REAL) * d);
+            have_fsal = 1;
+        }
+    }
+    if (n_rejected) *n_rejected = nrej;
+    return isave == n_save ? nacc : -1;
+}
+
+/* ------------------------------------------------ interpolating adjoint ---- */
+/* InterpolatingAdjoint (seir_exposure.jl:71,140; Fisher-KPP-CNN.jl:136): the
+ * augmented state [lambda; mu] is integrated from T back to t0 with the same
+ * Runge-Kutta method and step; u(t) at the backward stage times comes from the
+ * forward solution's dense output (Tsit5 4th-order interpolant over the stored
+ * k_1..k_7 of the step containing t); at every save time the loss cotangent
+ * dL/du(t_i) is added to lambda (discrete callback), which also invalidates
+ * FSAL, so k_1 is re-evaluated after each jump.  mu' = -lambda^T df/dtheta never
+ * feeds back, so its quadrature is accumulated straight into grad_theta. */
+void FN(ude_adjoint_fixed)(const ude_model *m, const REAL *th, const REAL *out, const REAL *dense,
+                           REAL dt, int n_steps, int save_every, const REAL *dLdout,
+                           REAL *grad_theta, REAL *grad_u0)
+{
+    const ude_tableau *tb = ude_get_tableau(UDE_TSIT5);
+    const int d = m->d, s = 7;
+    REAL lam[UDE_MAX_STATE], g[UDE_MAX_STATE], uu[UDE_MAX_STATE], un[UDE_MAX_STATE];
+    REAL kl[7 * UDE_MAX_STATE];
+    const int n_save = n_steps / save_every + 1;
+    for (int k = 0; k < d; ++k) lam[k] = dLdout[(size_t)(n_save - 1) * d + k];
+    /* reconstruct u_n at every step start from the saved states + dense output */
+    REAL *ustart = (REAL *)malloc(sizeof(REAL) * (size_t)(n_steps + 1) * d);
+    for (int k = 0; k < d; ++k) ustart[k] = out[k];
+    for (int n = 0; n < n_steps; ++n) {
+        const REAL *ks = dense + (size_t)n * s * d;
+        if ((n + 1) % save_every == 0) {
+            for (int k = 0; k < d; ++k) ustart[(size_t)(n + 1) * d + k] = out[(size_t)((n + 1) / save_every) * d + k];
+        } else {
+            for (int k = 0; k < d; ++k) {
+                REAL acc = 0;
+                for (int j = 0; j < 6; ++j) acc += (REAL)tb->A[6][j] * ks[(size_t)j * d + k];
+                ustart[(size_t)(n + 1) * d + k] = ustart[(size_t)n * d + k] + dt * acc;
+            }
+        }
+    }
+    for (int n = n_steps - 1; n >= 0; --n) {
+        const REAL *ks = dense + (size_t)n * s * d;
+        const REAL *u_n = ustart + (size_t)n * d;
+        /* backward step from t_{n+1} to t_n; stage i at t_{n+1} - c_i dt, Theta_i = 1 - c_i */
+        for (int i = 0; i < 6; ++i) {          /* k_7 only feeds FSAL/error: not needed */
+            const REAL Th = (REAL)1 - (REAL)tb->c[i];
+            REAL bw[7];
+            FN(tsit5_bTheta)(Th, bw);
+            for (int k = 0; k < d; ++k) {
+                REAL acc = 0;
+                for (int j = 0; j < 7; ++j) acc += bw[j] * ks[(size_t)j * d + k];
+                uu[k] = u_n[k] + dt * acc;
+            }
+            for (int k = 0; k < d; ++k) {
+                REAL acc = 0;
+                for (int j = 0; j < i; ++j) {
+                    const REAL a = (REAL)tb->A[i][j];
+                    if (a != 0) acc += a * kl[(size_t)j * d + k];
+                }
+                g[k] = lam[k] + dt * acc;
+            }
+            /* kl_i = J_u^T g ; grad_theta += dt*b_i * J_theta^T g */
+            FN(ude_rhs_vjp)(m, th, uu, g, kl + (size_t)i * d, grad_theta, dt * (REAL)tb->A[6][i]);
+        }
+        for (int k = 0; k < d; ++k) {
+            REAL acc = 0;
+            for (int j = 0; j < 6; ++j) acc += (REAL)tb->A[6][j] * kl[(size_t)j * d + k];
+            un[k] = lam[k] + dt * acc;
+        }
+        for (int k = 0; k < d; ++k) lam[k] = un[k];
+        if (n % save_every == 0)
+            for (int k = 0; k < d; ++k) lam[k] += dLdout[(size_t)(n / save_every) * d + k];
+    }
+    for (int k = 0; k < d; ++k) grad_u0[k] = lam[k];
+    free(ustart);
+}
+
+double FN(ude_ensemble_loss_grad)(const ude_model *m, const REAL *th, const REAL *u0, const REAL *y,
+                                  const REAL *wmask, size_t N, REAL dt, int n_steps, int save_every,
+                                  REAL *out, REAL *grad_theta, REAL *grad_u0, int n_threads)
+{
+    const int d = m->d;
+    const int n_save = n_steps / save_every + 1;
+    const size_t P = ude_num_params(m);
+    double loss = 0;
+    if (n_threads < 1) n_threads = 1;
+    REAL *gpart = (REAL *)calloc((size_t)n_threads * P, sizeof(REAL));
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads) reduction(+ : loss)
+#endif
+    {
+#ifdef _OPENMP
+        const int tid = omp_get_thread_num();
+#else
+        const int tid = 0;
+#endif
+        REAL *gt = gpart + (size_t)tid * P;
+        REAL *o = (REAL *)malloc(sizeof(REAL) * (size_t)n_save * d);
+        REAL *dl = (REAL *)malloc(sizeof(REAL) * (size_t)n_save * d);
+        REAL *dense = (REAL *)malloc(sizeof(REAL) * (size_t)n_steps * 7 * d);
+        REAL u[UDE_MAX_STATE], gu[UDE_MAX_STATE];
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (long long n = 0; n < (long long)N; ++n) {
+            for (int k = 0; k < d; ++k) u[k] = u0[(size_t)k * N + n];
+            FN(ude_solve_fixed)(m, th, u, dt, n_steps, UDE_TSIT5, save_every, o, dense);
+            for (int i = 0; i < n_save; ++i)
+                for (int k = 0; k < d; ++k) {
+                    const size_t idx = ((size_t)i * d + k) * N + n;
+                    const REAL r = o[(size_t)i * d + k] - y[idx];
+                    loss += (double)(wmask[k] * r * r);
+                    dl[(size_t)i * d + k] = (REAL)2 * wmask[k] * r;
+                    if (out) out[idx] = o[(size_t)i * d + k];
+                }
+            FN(ude_adjoint_fixed)(m, th, o, dense, dt, n_steps, save_every, dl, gt, gu);
+            if (grad_u0) for (int k = 0; k < d; ++k) grad_u0[(size_t)k * N + n] = gu[k];
+        }
+        free(o); free(dl); free(dense);
+    }
+    for (size_t p = 0; p < P; ++p) {
+        double acc = 0;
+        for (int t = 0; t < n_threads; ++t) acc += (double)gpart[(size_t)t * P + p];
+        grad_theta[p] = (REAL)acc;
+    }
+    free(gpart);
+    return loss;
+}
+
+#undef FN
+#undef CAT
+#undef CAT_
