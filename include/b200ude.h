@@ -1,0 +1,173 @@
+/*
+ * b200ude.h -- C ABI of the B200-native UDE training path.
+ *
+ * This is the drop-in boundary for ONE hot path of
+ * ChrisRackauckas/universal_differential_equations: the forward solve of a
+ * universal differential equation (known physics + embedded dense chain) for an
+ * ensemble of trajectories and its interpolating-adjoint gradient.  The
+ * reference has no FFI of its own: the seam is Julia dispatch on
+ *     concrete_solve(prob::ODEProblem, Tsit5()/Vern7(), u0, p; saveat, abstol,
+ *                    reltol, sensealg = InterpolatingAdjoint(autojacvec = ReverseDiffVJP()))
+ *         SEIR_exposure/seir_exposure.jl:137-141, FisherKPP/Fisher-KPP-CNN.jl:136,
+ *         LotkaVolterra/scenario_1.jl:82-88
+ * and its reverse rule (DiffEqSensitivity._concrete_solve_adjoint), driven by
+ *     DiffEqFlux.sciml_train(loss, theta, opt; cb, maxiters)
+ *         seir_exposure.jl:160-161, Fisher-KPP-CNN.jl:236-238.
+ * A Julia shim defines those methods on top of the entry
+ * points below with `ccall`; the Python mirror in
+ * universal_differential_equations_b200/sciml.py binds the same symbols with
+ * ctypes and is what the tests and bench.py exercise.
+ *
+ * Conventions
+ *  - every function returns int32_t: 0 = OK, <0 usage error, >0 CUDA runtime error
+ *    (message via b200ude_last_error); nothing throws or longjmps across the ABI.
+ *  - all arrays are plain pointers + sizes; the caller owns every array it passes;
+ *    the handle owns theta's device copy, the stored forward solution and scratch.
+ *  - ensemble layouts are trajectory-fastest (structure of arrays):
+ *        u0 [d][N]      out / data / dL_dout [n_save][d][N]      grad_u0 [d][N]
+ *    i.e. a Julia Array of size (N, d) / (N, d, n_save).
+ *  - theta is the reference's own flat layout: [n_prefix trainable physics scalars |
+ *    per dense layer: vec(W) column-major (W is out x in), then b | n_suffix scalars]
+ *    (Lux ComponentVector scenario_1.jl:113, DiffEqFlux initial_params
+ *    seir_exposure.jl:115, Flux.destructure Fisher-KPP-CNN.jl:106).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls taking a
+ *    stream are asynchronous with respect to the host unless stated otherwise.
+ *  - a handle is not thread-safe; use one handle per host thread and device.
+ */
+#ifndef B200UDE_H
+#define B200UDE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200UDE_ABI_VERSION 1
+
+/* dtype */
+#define B200UDE_F32 0
+#define B200UDE_F64 1 /* reserved; kernels are fp32 in this version */
+
+/* model kinds: the UDE right-hand sides of the reference */
+#define B200UDE_MODEL_LV 0   /* du1 = a1*u1 + NN1(u), du2 = -a2*u2 + NN2(u)   scenario_1.jl:69-73,
+                                a2 trainable (n_prefix=1) scenario_2.jl:90-95, a1,a2 trainable (n_prefix=2)
+                                hudson_bay.jl:85-91; consts = {p_[1], p_[4]} */
+#define B200UDE_MODEL_SEIR 1 /* 7-state exposure UDE, NN([S/N, I, D/N])      seir_exposure.jl:117-130;
+                                consts = F,beta0,alpha,kappa,mu,sigma,gamma,d,lambda (:33) */
+#define B200UDE_MODEL_FKPP 2 /* pointwise reaction net + D0 * 3-tap periodic stencil, n_suffix = 5
+                                Fisher-KPP-CNN.jl:111-126, scenario_3.jl:103-114 */
+#define B200UDE_MODEL_NODE 3 /* du = NN(u) */
+
+/* activations of the dense chain */
+#define B200UDE_ACT_IDENTITY 0
+#define B200UDE_ACT_TANH 1
+#define B200UDE_ACT_RBF 2 /* exp(-x^2), scenario_1.jl:59 */
+
+/* solver (OrdinaryDiffEq algorithm the reference passes to solve/concrete_solve) */
+#define B200UDE_TSIT5 0
+#define B200UDE_VERN7 1
+
+/* sensealg */
+#define B200UDE_INTERPOLATING_ADJOINT 0
+
+/* memory space of a pointer argument */
+#define B200UDE_HOST 0
+#define B200UDE_DEVICE 1
+
+/* flags */
+#define B200UDE_FLAG_APPROX_TANH 1u /* tanh.approx.f32 (2^-11 rel. error) instead of the ex2/rcp form */
+
+/* per-trajectory status words written by b200ude_forward */
+#define B200UDE_TRAJ_OK 0
+#define B200UDE_TRAJ_NONFINITE 1
+
+/* error codes */
+#define B200UDE_OK 0
+#define B200UDE_EINVAL (-1)       /* bad descriptor / argument */
+#define B200UDE_EUNSUPPORTED (-2) /* configuration has no sm_100a kernel in this build */
+#define B200UDE_ESTATE (-3)       /* call order violated (e.g. adjoint before forward) */
+#define B200UDE_ENOMEM (-4)
+#define B200UDE_ENODEVICE (-5)    /* no CUDA device / not an sm_100 part */
+
+#define B200UDE_MAX_LAYERS 6
+
+typedef struct b200ude_handle b200ude_handle;
+
+typedef struct b200ude_desc {
+    uint32_t struct_size; /* = sizeof(b200ude_desc); checked */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t dtype;        /* B200UDE_F32 */
+    int32_t model;        /* B200UDE_MODEL_* */
+    int32_t state_dim;    /* d */
+    int32_t n_layers;     /* dense layers of the embedded chain */
+    int32_t widths[B200UDE_MAX_LAYERS + 1]; /* widths[0] = chain input, widths[n_layers] = chain output */
+    int32_t acts[B200UDE_MAX_LAYERS];
+    int32_t n_prefix;     /* trainable physics scalars before the chain in theta */
+    int32_t n_suffix;     /* trainable scalars after the chain in theta */
+    int32_t n_consts;
+    double consts[16];    /* fixed physics constants */
+    int32_t solver;       /* B200UDE_TSIT5 | B200UDE_VERN7 */
+    int32_t sensealg;     /* B200UDE_INTERPOLATING_ADJOINT */
+    double t0;            /* tspan[1] */
+    double dt;            /* fixed step (adaptive = false); saveat = t0 + i*save_every*dt */
+    int32_t n_steps;      /* number of steps; tspan[2] = t0 + n_steps*dt */
+    int32_t save_every;   /* save the state every this many steps (and at t0) */
+    double abstol, reltol; /* reserved for adaptive stepping; ignored when dt > 0 */
+    int32_t n_loss_weights; /* 0 => all ones; else = state_dim */
+    double loss_weights[16]; /* per-component weight of the fused L2 loss (seir_exposure.jl:146 uses rows 2:4) */
+    uint64_t max_trajectories; /* capacity: scratch is sized for this many trajectories */
+    uint32_t flags;
+    uint32_t reserved;
+} b200ude_desc;
+
+int32_t b200ude_version(void);
+
+/* Message of the last error on this handle (h may be NULL: last create() error of the calling thread). */
+const char *b200ude_last_error(const b200ude_handle *h);
+
+int32_t b200ude_create(const b200ude_desc *desc, b200ude_handle **out);
+void b200ude_destroy(b200ude_handle *h);
+
+/* length P of theta, number of saved time points, bytes of device memory held by the handle */
+size_t b200ude_num_params(const b200ude_handle *h);
+size_t b200ude_num_save(const b200ude_handle *h);
+size_t b200ude_device_bytes(const b200ude_handle *h);
+
+/* theta[P] (float) from host or device memory -> the handle's device copy. */
+int32_t b200ude_set_params(b200ude_handle *h, const void *theta, size_t P, int32_t mem, void *stream);
+
+/* FORWARD  (replaces: the UDE RHS closure + OrdinaryDiffEq perform_step! loop behind
+ * concrete_solve(prob, Tsit5(), u0, p; saveat, ...), one trajectory per ensemble member).
+ * u0 [d][N], out [n_save][d][N], status [N] (may be NULL): DEVICE pointers.
+ * Also stores the dense output (stage derivatives) the adjoint interpolates. */
+int32_t b200ude_forward(b200ude_handle *h, const void *u0, size_t N, void *out, int32_t *status,
+                        void *stream);
+
+/* ADJOINT  (replaces: DiffEqSensitivity InterpolatingAdjoint backward solve + ReverseDiffVJP).
+ * Uses the forward solution stored by the last b200ude_forward on this handle.
+ * dL_dout [n_save][d][N]: cotangent of the saved states (the Zygote pullback's Delta).
+ * grad_theta [P]: SUM over the N trajectories (overwritten). grad_u0 [d][N] or NULL. DEVICE pointers. */
+int32_t b200ude_adjoint(b200ude_handle *h, const void *dL_dout, void *grad_theta, void *grad_u0,
+                        void *stream);
+
+/* ADJOINT with the L2 trajectory-matching loss fused (scenario_1.jl:91-94, seir_exposure.jl:144-147):
+ * L = sum_n sum_i sum_k w_k (out - data)^2, Delta = 2 w (out - data) formed in-kernel.
+ * data [n_save][d][N]; loss: float[1] (sum over the ensemble, overwritten). DEVICE pointers. */
+int32_t b200ude_adjoint_l2(b200ude_handle *h, const void *data, void *loss, void *grad_theta,
+                           void *grad_u0, void *stream);
+
+/* HOST-BUFFER entry points (what a host-language binding calls with ordinary arrays): copy
+ * inputs host->device, run the kernels, copy results back, synchronise.  Pinned host memory makes
+ * the copies asynchronous; pageable memory works but is slower. */
+int32_t b200ude_solve_host(b200ude_handle *h, const void *theta, const void *u0, size_t N, void *out,
+                           int32_t *status);
+int32_t b200ude_loss_gradient_host(b200ude_handle *h, const void *theta, const void *u0,
+                                   const void *data, size_t N, double *loss, void *grad_theta,
+                                   void *grad_u0 /* may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200UDE_H */

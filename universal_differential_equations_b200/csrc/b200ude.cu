@@ -1,0 +1,365 @@
+// b200ude.cu -- C-ABI entry points (include/b200ude.h) over the sm_100a kernels.
+//
+// No torch types, no exceptions across the boundary, no CPU fallback: if there is no usable
+// CUDA device, or the requested configuration has no kernel, the call fails with a code and a
+// message.  Nothing here includes or links the CPU oracle.
+#include "../../include/b200ude.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "params.h"
+
+using namespace b200ude;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// kernel families compiled into this build (one translation unit each, see k_*.cu)
+//   K_LV32   LV 2 -> 32 -> 32 -> 2 tanh                      BASELINE config 2
+//   K_LV5Px  LV 2 -> 5 -> 5 -> 5 -> 2, per-layer activations, x trainable linear rates
+//            scenario_1.jl:62-73 (x=0), scenario_2.jl:79-98 (x=1), hudson_bay.jl:77-91 (x=2)
+enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2 };
+
+int kernel_num_params(KernelId k)
+{
+    switch (k) {
+    case K_LV32: return 2 * 32 + 32 + 32 * 32 + 32 + 32 * 2 + 2;
+    case K_LV5P0: return 87;
+    case K_LV5P1: return 88;
+    case K_LV5P2: return 89;
+    default: return 0;
+    }
+}
+
+uint64_t g_serial = 0;
+
+}  // namespace
+
+struct b200ude_handle {
+    b200ude_desc desc;
+    KernelId kid = K_NONE;
+    Variant var;
+    ConstTables tab;
+    int P = 0, n_save = 0, D = 0;
+    size_t cap = 0;  // max trajectories
+    size_t N = 0;    // trajectories of the last forward
+    bool have_forward = false;
+    bool have_theta = false;
+    int sm_count = 0;
+    // device buffers
+    float *d_theta = nullptr;
+    float *d_ustep = nullptr;
+    float *d_dense = nullptr;
+    float *d_partial = nullptr;
+    size_t partial_blocks = 0;
+    // host-buffer path
+    float *d_u0 = nullptr, *d_out = nullptr, *d_data = nullptr, *d_gu0 = nullptr, *d_grad = nullptr, *d_loss = nullptr;
+    int32_t *d_status = nullptr;
+    float *h_loss = nullptr;  // pinned
+    cudaStream_t own_stream = nullptr;
+    size_t dev_bytes = 0;
+    std::string err;
+};
+
+namespace {
+
+int32_t fail(b200ude_handle *h, int32_t code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                                \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            return fail((h), (int32_t)e_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(b200ude_handle *h, T **p, size_t count)
+{
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e == cudaSuccess) h->dev_bytes += count * sizeof(T);
+    return e;
+}
+
+KernelId pick_kernel(const b200ude_desc &d)
+{
+    if (d.model != B200UDE_MODEL_LV || d.state_dim != 2) return K_NONE;
+    if (d.acts[d.n_layers - 1] != B200UDE_ACT_IDENTITY) return K_NONE;
+    if (d.n_layers == 3 && d.widths[0] == 2 && d.widths[1] == 32 && d.widths[2] == 32 && d.widths[3] == 2 &&
+        d.acts[0] == B200UDE_ACT_TANH && d.acts[1] == B200UDE_ACT_TANH && d.n_prefix == 0)
+        return K_LV32;
+    if (d.n_layers == 4 && d.widths[0] == 2 && d.widths[1] == 5 && d.widths[2] == 5 && d.widths[3] == 5 &&
+        d.widths[4] == 2) {
+        if (d.n_prefix == 0) return K_LV5P0;
+        if (d.n_prefix == 1) return K_LV5P1;
+        if (d.n_prefix == 2) return K_LV5P2;
+    }
+    return K_NONE;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int32_t *status, cudaStream_t st)
+{
+    if (!h->have_theta) return fail(h, B200UDE_ESTATE, "forward: set_params has not been called");
+    if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "forward: N=%zu outside (0, max_trajectories=%zu]", N, h->cap);
+    if (!u0 || !out) return fail(h, B200UDE_EINVAL, "forward: null pointer");
+    FwdParams p;
+    p.u0 = u0; p.out = out; p.ustep = h->d_ustep; p.dense = h->d_dense; p.status = status; p.theta = h->d_theta;
+    p.N = (int)N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P; p.dt = (float)h->desc.dt;
+    cudaError_t e = cudaSuccess;
+    switch (h->kid) {
+    case K_LV32: e = launch_fwd_lv32(h->var, h->tab, p, st); break;
+    case K_LV5P0: e = launch_fwd_lv5(0, h->var, h->tab, p, st); break;
+    case K_LV5P1: e = launch_fwd_lv5(1, h->var, h->tab, p, st); break;
+    case K_LV5P2: e = launch_fwd_lv5(2, h->var, h->tab, p, st); break;
+    default: return fail(h, B200UDE_EUNSUPPORTED, "forward: no kernel");
+    }
+    CUDA_TRY(h, e);
+    h->N = N;
+    h->have_forward = true;
+    return B200UDE_OK;
+}
+
+int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, float *grad_theta,
+                   float *grad_u0, cudaStream_t st)
+{
+    if (!h->have_forward) return fail(h, B200UDE_ESTATE, "adjoint: no stored forward solution (call b200ude_forward first)");
+    if (!cot || !grad_theta) return fail(h, B200UDE_EINVAL, "adjoint: null pointer");
+    AdjParams p;
+    p.ustep = h->d_ustep; p.dense = h->d_dense; p.cot = cot; p.grad_u0 = grad_u0; p.partial = h->d_partial;
+    p.theta = h->d_theta; p.N = (int)h->N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P;
+    p.fused_l2 = l2 ? 1 : 0;
+    p.dt = (float)h->desc.dt;
+    cudaError_t e = cudaSuccess;
+    int grid = 0;
+    switch (h->kid) {
+    case K_LV32: e = launch_adj_lv32(h->var, h->tab, p, st, &grid); break;
+    case K_LV5P0: e = launch_adj_lv5(0, h->var, h->tab, p, st, &grid); break;
+    case K_LV5P1: e = launch_adj_lv5(1, h->var, h->tab, p, st, &grid); break;
+    case K_LV5P2: e = launch_adj_lv5(2, h->var, h->tab, p, st, &grid); break;
+    default: return fail(h, B200UDE_EUNSUPPORTED, "adjoint: no kernel");
+    }
+    CUDA_TRY(h, e);
+    CUDA_TRY(h, launch_reduce(h->d_partial, grid, h->P + 1, grad_theta, loss, st));
+    return B200UDE_OK;
+}
+
+}  // namespace
+
+// ---- exported entry points ------------------------------------------------------------------------
+extern "C" {
+
+int32_t b200ude_version(void) { return B200UDE_ABI_VERSION; }
+
+const char *b200ude_last_error(const b200ude_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
+{
+    if (!d || !out) return fail(nullptr, B200UDE_EINVAL, "create: null argument");
+    *out = nullptr;
+    if (d->struct_size != sizeof(b200ude_desc))
+        return fail(nullptr, B200UDE_EINVAL, "create: struct_size %u != %zu (ABI mismatch)", d->struct_size, sizeof(b200ude_desc));
+    if (d->dtype != B200UDE_F32) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only B200UDE_F32 kernels exist in this build");
+    if (d->n_layers < 2 || d->n_layers > B200UDE_MAX_LAYERS) return fail(nullptr, B200UDE_EINVAL, "create: n_layers=%d out of range", d->n_layers);
+    if (d->solver != B200UDE_TSIT5) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only Tsit5 has a kernel in this build");
+    if (d->sensealg != B200UDE_INTERPOLATING_ADJOINT) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: unknown sensealg %d", d->sensealg);
+    if (!(d->dt > 0) || d->n_steps < 1 || d->save_every < 1 || d->n_steps % d->save_every != 0)
+        return fail(nullptr, B200UDE_EINVAL, "create: need dt>0, n_steps>=1, save_every>=1 dividing n_steps");
+    if (d->max_trajectories == 0 || d->max_trajectories > (1ull << 26)) return fail(nullptr, B200UDE_EINVAL, "create: max_trajectories out of range");
+    if (d->n_loss_weights != 0 && d->n_loss_weights != d->state_dim) return fail(nullptr, B200UDE_EINVAL, "create: n_loss_weights must be 0 or state_dim");
+    const KernelId kid = pick_kernel(*d);
+    if (kid == K_NONE)
+        return fail(nullptr, B200UDE_EUNSUPPORTED,
+                    "create: no sm_100a kernel for this model/chain (built: LV 2-32-32-2 tanh; LV 2-5-5-5-2 with 0/1/2 trainable rates)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, B200UDE_ENODEVICE, "create: no CUDA device (%s)", cudaGetErrorString(e));
+    if (d->device < 0 || d->device >= ndev) return fail(nullptr, B200UDE_EINVAL, "create: device %d of %d", d->device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, d->device);
+    if (e != cudaSuccess) return fail(nullptr, (int32_t)e, "create: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, B200UDE_ENODEVICE, "create: device %d is sm_%d%d; this library carries sm_100a code only", d->device, prop.major, prop.minor);
+    e = cudaSetDevice(d->device);
+    if (e != cudaSuccess) return fail(nullptr, (int32_t)e, "create: cudaSetDevice: %s", cudaGetErrorString(e));
+
+    b200ude_handle *h = new (std::nothrow) b200ude_handle();
+    if (!h) return fail(nullptr, B200UDE_ENOMEM, "create: out of host memory");
+    h->desc = *d;
+    h->kid = kid;
+    h->D = d->state_dim;
+    h->n_save = d->n_steps / d->save_every + 1;
+    h->cap = (size_t)d->max_trajectories;
+    h->sm_count = prop.multiProcessorCount;
+    h->P = kernel_num_params(kid);
+    h->var.approx_tanh = (d->flags & B200UDE_FLAG_APPROX_TANH) ? 1 : 0;
+    // tuning knobs for experiments (defaults are the measured-best variant)
+    h->var.fwd_smem = env_int("B200UDE_FWD_SMEM", 0);
+    h->var.fwd_T = env_int("B200UDE_FWD_T", 1) == 2 ? 2 : 1;
+    h->var.adj_smem = env_int("B200UDE_ADJ_SMEM", 0);
+
+    const size_t N = h->cap, D = (size_t)h->D;
+    h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : adj_grid_lv5((int)N));
+    bool ok = true;
+    ok = ok && dalloc(h, &h->d_theta, (size_t)((h->P + 3) / 4) * 4) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_ustep, (size_t)(d->n_steps + 1) * D * N) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_dense, (size_t)(d->n_steps * 6 + 1) * D * N) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_partial, h->partial_blocks * (size_t)(h->P + 1)) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_grad, (size_t)h->P) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_loss, 1) == cudaSuccess;
+    if (!ok) {
+        cudaError_t le = cudaGetLastError();
+        g_create_error = std::string("create: device allocation failed: ") + cudaGetErrorString(le);
+        b200ude_destroy(h);
+        return B200UDE_ENOMEM;
+    }
+    cudaMemset(h->d_theta, 0, sizeof(float) * ((h->P + 3) / 4) * 4);
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void **)&h->h_loss, sizeof(float)) != cudaSuccess) {
+        g_create_error = "create: stream / pinned allocation failed";
+        b200ude_destroy(h);
+        return B200UDE_ENOMEM;
+    }
+    h->tab.serial = ++g_serial;
+    h->tab.d_theta = h->d_theta;
+    h->tab.P = h->P;
+    for (int i = 0; i < 16; ++i) {
+        h->tab.consts[i] = i < d->n_consts ? (float)d->consts[i] : 0.0f;
+        h->tab.lossw[i] = d->n_loss_weights > 0 ? (i < d->n_loss_weights ? (float)d->loss_weights[i] : 0.0f) : 1.0f;
+    }
+    for (int i = 0; i < 8; ++i) h->tab.acts[i] = i < d->n_layers ? d->acts[i] : 0;
+    *out = h;
+    return B200UDE_OK;
+}
+
+void b200ude_destroy(b200ude_handle *h)
+{
+    if (!h) return;
+    cudaFree(h->d_theta); cudaFree(h->d_ustep); cudaFree(h->d_dense); cudaFree(h->d_partial);
+    cudaFree(h->d_u0); cudaFree(h->d_out); cudaFree(h->d_data); cudaFree(h->d_gu0); cudaFree(h->d_grad);
+    cudaFree(h->d_loss); cudaFree(h->d_status);
+    if (h->h_loss) cudaFreeHost(h->h_loss);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+size_t b200ude_num_params(const b200ude_handle *h) { return h ? (size_t)h->P : 0; }
+size_t b200ude_num_save(const b200ude_handle *h) { return h ? (size_t)h->n_save : 0; }
+size_t b200ude_device_bytes(const b200ude_handle *h) { return h ? h->dev_bytes : 0; }
+
+int32_t b200ude_set_params(b200ude_handle *h, const void *theta, size_t P, int32_t mem, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (!theta || P != (size_t)h->P) return fail(h, B200UDE_EINVAL, "set_params: P=%zu, expected %d", P, h->P);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_theta, theta, sizeof(float) * P,
+                                mem == B200UDE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    h->have_theta = true;
+    return B200UDE_OK;
+}
+
+int32_t b200ude_forward(b200ude_handle *h, const void *u0, size_t N, void *out, int32_t *status, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    return do_forward(h, (const float *)u0, N, (float *)out, status, (cudaStream_t)stream);
+}
+
+int32_t b200ude_adjoint(b200ude_handle *h, const void *dL_dout, void *grad_theta, void *grad_u0, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    return do_adjoint(h, false, (const float *)dL_dout, nullptr, (float *)grad_theta, (float *)grad_u0,
+                      (cudaStream_t)stream);
+}
+
+int32_t b200ude_adjoint_l2(b200ude_handle *h, const void *data, void *loss, void *grad_theta, void *grad_u0, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    return do_adjoint(h, true, (const float *)data, (float *)loss, (float *)grad_theta, (float *)grad_u0,
+                      (cudaStream_t)stream);
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------
+static int32_t ensure_host_path(b200ude_handle *h)
+{
+    if (h->d_u0) return B200UDE_OK;
+    const size_t N = h->cap, D = (size_t)h->D;
+    bool ok = true;
+    ok = ok && dalloc(h, &h->d_u0, D * N) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_out, (size_t)h->n_save * D * N) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_data, (size_t)h->n_save * D * N) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_gu0, D * N) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_status, N) == cudaSuccess;
+    if (!ok) return fail(h, B200UDE_ENOMEM, "host path: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return B200UDE_OK;
+}
+
+int32_t b200ude_solve_host(b200ude_handle *h, const void *theta, const void *u0, size_t N, void *out, int32_t *status)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (!theta || !u0 || !out) return fail(h, B200UDE_EINVAL, "solve_host: null pointer");
+    if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "solve_host: N=%zu outside (0, %zu]", N, h->cap);
+    int32_t rc = ensure_host_path(h);
+    if (rc) return rc;
+    cudaStream_t st = h->own_stream;
+    const size_t D = (size_t)h->D;
+    rc = b200ude_set_params(h, theta, (size_t)h->P, B200UDE_HOST, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_u0, u0, sizeof(float) * D * N, cudaMemcpyHostToDevice, st));
+    rc = do_forward(h, h->d_u0, N, h->d_out, status ? h->d_status : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_out, sizeof(float) * (size_t)h->n_save * D * N, cudaMemcpyDeviceToHost, st));
+    if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return B200UDE_OK;
+}
+
+int32_t b200ude_loss_gradient_host(b200ude_handle *h, const void *theta, const void *u0, const void *data, size_t N,
+                                   double *loss, void *grad_theta, void *grad_u0)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (!theta || !u0 || !data || !grad_theta) return fail(h, B200UDE_EINVAL, "loss_gradient_host: null pointer");
+    if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "loss_gradient_host: N=%zu outside (0, %zu]", N, h->cap);
+    int32_t rc = ensure_host_path(h);
+    if (rc) return rc;
+    cudaStream_t st = h->own_stream;
+    const size_t D = (size_t)h->D;
+    rc = b200ude_set_params(h, theta, (size_t)h->P, B200UDE_HOST, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_u0, u0, sizeof(float) * D * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_data, data, sizeof(float) * (size_t)h->n_save * D * N, cudaMemcpyHostToDevice, st));
+    rc = do_forward(h, h->d_u0, N, h->d_out, nullptr, st);
+    if (rc) return rc;
+    rc = do_adjoint(h, true, h->d_data, h->d_loss, h->d_grad, grad_u0 ? h->d_gu0 : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(grad_theta, h->d_grad, sizeof(float) * (size_t)h->P, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (grad_u0) CUDA_TRY(h, cudaMemcpyAsync(grad_u0, h->d_gu0, sizeof(float) * D * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (loss) *loss = (double)*h->h_loss;
+    return B200UDE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+// k_lv32_fwd.cu -- forward-solve kernels of the LV 2 -> 32 -> 32 -> 2 tanh UDE (BASELINE config 2).
+#include "lv32_packed.cuh"
+
+namespace b200ude {
+
+template <int TM, class W>
+static cudaError_t launch_one(const FwdParams &p, cudaStream_t st)
+{
+    auto kern = lv32::forward_kernel<TM, W, FWD_BLOCK, 1>;
+    const int half = (p.N + 1) / 2;
+    const int grid = (half + FWD_BLOCK - 1) / FWD_BLOCK;
+    const size_t smem = WeightStage<W>::kSmem ? sizeof(float) * ((lv32::P + 3) / 4) * 4 : 0;
+    kern<<<grid, FWD_BLOCK, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_lv32(const Variant &v, const ConstTables &t, const FwdParams &p, cudaStream_t st)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    if (v.approx_tanh) return launch_one<1, WConst>(p, st);
+    if (v.fwd_smem) return launch_one<0, WSmem>(p, st);
+    return launch_one<0, WConst>(p, st);
+}
+
+}  // namespace b200ude

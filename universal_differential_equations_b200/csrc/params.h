@@ -1,0 +1,61 @@
+// params.h -- plain structs shared by the C-ABI layer and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200ude {
+
+struct FwdParams {
+    const float *u0;    // [D][N]
+    float *out;         // [n_save][D][N]
+    float *ustep;       // [n_steps+1][D][N]  state at every step start (adjoint's interpolation base)
+    float *dense;       // [n_steps*6+1][D][N] stage derivatives: row n*6+i = k_{i+1} of step n; k_7(n) = k_1(n+1)
+    int32_t *status;    // [N] or nullptr
+    const float *theta; // device copy of theta (shared-memory weight variant only)
+    int N, n_steps, save_every, P;
+    float dt;
+};
+
+struct AdjParams {
+    const float *ustep;   // [n_steps+1][D][N]
+    const float *dense;   // [n_steps*6+1][D][N]
+    const float *cot;     // fused_l2 ? data [n_save][D][N] : dL/dout [n_save][D][N]
+    float *grad_u0;       // [D][N] or nullptr
+    float *partial;       // [gridDim.x][P+1]  per-CTA partial gradient, last entry = partial loss
+    const float *theta;   // device theta (shared-memory weight variant only)
+    int N, n_steps, save_every, P;
+    int fused_l2;         // 1: cot is the data, form 2 w (u - data) and the loss in-kernel
+    float dt;
+};
+
+// per-handle tables every launch pushes into the launching translation unit's constant bank
+struct ConstTables {
+    uint64_t serial;  // unique per handle: the small tables are re-sent only when it changes
+    const float *d_theta;
+    int P;
+    float consts[16];
+    float lossw[16];
+    int acts[8];
+};
+
+struct Variant {
+    int fwd_smem = 0;    // 0: constant-bank weights, 1: shared-memory (TMA-staged) weights
+    int fwd_T = 1;       // trajectories per thread in the forward kernel
+    int adj_smem = 0;
+    int approx_tanh = 0;
+};
+
+constexpr int FWD_BLOCK = 128;
+constexpr int ADJ_BLOCK_GEMM = 32;   // H=32 adjoint: one warp (64 trajectories) per CTA
+constexpr int ADJ_BLOCK_LANE = 128;  // small-chain adjoint
+
+// launchers (one translation unit per kernel family; each owns its constant-bank symbols)
+cudaError_t launch_fwd_lv32(const Variant &, const ConstTables &, const FwdParams &, cudaStream_t);
+cudaError_t launch_adj_lv32(const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *grid_out);
+cudaError_t launch_fwd_lv5(int n_prefix, const Variant &, const ConstTables &, const FwdParams &, cudaStream_t);
+cudaError_t launch_adj_lv5(int n_prefix, const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *grid_out);
+int adj_grid_lv32(int N);
+int adj_grid_lv5(int N);
+cudaError_t launch_reduce(const float *partial, int nblocks, int P1, float *grad, float *loss, cudaStream_t);
+
+}  // namespace b200ude
