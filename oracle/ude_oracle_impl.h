@@ -416,6 +416,7 @@ int FN(ude_solve_adaptive)(const ude_model *m, const REAL *th, const REAL *u0, c
             t = tn;
             for (int k = 0; k < d; ++k) u[k] = un[k];
             if (tb->fsal) { memcpy(kf, ks + (size_t)(s - 1) * d, sizeof(REAL) * d); have_fsal = 1; }
+            else have_fsal = 0;   /* k1 kept from a rejected attempt is stale once u has moved */
         } else {
             ++nrej;
             REAL qr = q11 / gamma;

@@ -1,0 +1,229 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI, against the CPU oracle.
+
+Tolerances (fp32 kernels; the oracle is evaluated in fp64 and, where stated, fp32):
+  trajectories  |out - oracle64| <= 3e-4 * (1 + |oracle|)     (fp32 vs fp64 over 30 Tsit5 steps: ~1.4e-4 rel)
+  loss          rel <= 1e-4
+  grad_theta    ||g - g_oracle64|| / ||g_oracle64|| <= 2e-3 ; vs the fp32 oracle <= 2e-3 as well (both carry fp32 round-off)
+  grad_u0       max-abs rel <= 2e-3
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from helpers import glorot_theta, synthetic_ensemble  # noqa: E402
+
+
+def _ude():
+    import universal_differential_equations_b200 as ude
+    return ude
+
+
+def _lv32(ude):
+    chain = ude.FastChain(ude.FastDense(2, 32, ude.tanh), ude.FastDense(32, 32, ude.tanh), ude.FastDense(32, 2))
+    return ude.LotkaVolterraUDE(chain)
+
+
+def _lv5(ude, acts=("rbf", "rbf", "rbf"), rates=0):
+    chain = ude.FastChain(ude.FastDense(2, 5, acts[0]), ude.FastDense(5, 5, acts[1]), ude.FastDense(5, 5, acts[2]), ude.FastDense(5, 2))
+    return ude.LotkaVolterraUDE(chain, trainable_rates=rates)
+
+
+def _run(solver, theta, u0, data, want_gu0=True):
+    th = torch.from_numpy(theta.astype(np.float32)).cuda()
+    solver.set_params(th)
+    status = torch.full((u0.shape[1],), -1, dtype=torch.int32, device="cuda")
+    out = solver.forward(torch.from_numpy(u0).cuda(), status=status)
+    loss, g, gu = solver.adjoint_l2(torch.from_numpy(data).cuda(), want_grad_u0=want_gu0)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), float(loss), g.cpu().numpy(), (gu.cpu().numpy() if gu is not None else None), status.cpu().numpy()
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 64, 65, 1000, 4097])
+def test_lv32_forward_adjoint_vs_oracle(O, N):
+    ude = _ude()
+    theta = glorot_theta((2, 32, 32, 2), seed=1)
+    u0, y = synthetic_ensemble(N)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    out, loss, g, gu, status = _run(solver, theta, u0, y)
+    m = O.lv_model()
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.1, 30, want_out=True)
+    assert (status == 0).all()
+    assert np.all(np.abs(out - out64) <= 3e-4 * (1 + np.abs(out64)))
+    assert abs(loss - l64) <= 1e-4 * abs(l64)
+    assert np.linalg.norm(g - g64) <= 2e-3 * np.linalg.norm(g64)
+    assert np.abs(gu - gu64).max() <= 2e-3 * np.abs(gu64).max()
+    l32, g32, gu32 = O.ensemble_loss_grad(m, theta.astype(np.float32), u0, y, np.ones(2, np.float32), 0.1, 30)
+    assert np.linalg.norm(g - g32) <= 2e-3 * np.linalg.norm(g64)
+    solver.close()
+
+
+def test_lv32_save_every_and_generic_cotangent(O):
+    """dt = 0.05 with saveat = 0.1 (save_every = 2); generic dL/dout cotangent path == fused L2 path."""
+    ude = _ude()
+    N = 777
+    theta = glorot_theta((2, 32, 32, 2), seed=3)
+    u0, y = synthetic_ensemble(N)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.05, 60, 2, max_trajectories=N)
+    out, loss, g, gu, _ = _run(solver, theta, u0, y)
+    m = O.lv_model()
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.05, 60, save_every=2, want_out=True)
+    assert out.shape == (31, 2, N)
+    assert np.all(np.abs(out - out64) <= 3e-4 * (1 + np.abs(out64)))
+    assert np.linalg.norm(g - g64) <= 2e-3 * np.linalg.norm(g64)
+    cot = 2.0 * (torch.from_numpy(out).cuda() - torch.from_numpy(y).cuda())
+    g2, gu2 = solver.adjoint(cot)
+    torch.cuda.synchronize()
+    assert np.linalg.norm(g2.cpu().numpy() - g) <= 1e-5 * np.linalg.norm(g)
+    assert np.abs(gu2.cpu().numpy() - gu).max() <= 1e-5 * np.abs(gu).max()
+    solver.close()
+
+
+def test_lv32_deterministic_and_linear(O):
+    """Bitwise run-to-run reproducibility; adjoint is linear in the cotangent; ensemble gradient is additive."""
+    ude = _ude()
+    N = 2048
+    theta = glorot_theta((2, 32, 32, 2), seed=5)
+    u0, y = synthetic_ensemble(N, seed=7)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    out1, l1, g1, gu1, _ = _run(solver, theta, u0, y)
+    out2, l2, g2, gu2, _ = _run(solver, theta, u0, y)
+    assert np.array_equal(out1, out2) and np.array_equal(g1, g2) and np.array_equal(gu1, gu2) and l1 == l2
+    cot = torch.randn(31, 2, N, device="cuda")
+    ga, _ = solver.adjoint(cot)
+    gb, _ = solver.adjoint(2.0 * cot)
+    assert torch.allclose(gb, 2.0 * ga, rtol=1e-5, atol=1e-5 * float(ga.abs().max()))
+    # additivity over a split of the ensemble
+    h = N // 2
+    _, la, gA, _, _ = _run(solver, theta, u0[:, :h].copy(), y[:, :, :h].copy(), want_gu0=False)
+    _, lb, gB, _, _ = _run(solver, theta, u0[:, h:].copy(), y[:, :, h:].copy(), want_gu0=False)
+    assert abs((la + lb) - l1) <= 1e-5 * abs(l1)
+    assert np.linalg.norm(gA + gB - g1) <= 1e-4 * np.linalg.norm(g1)
+    solver.close()
+
+
+def test_lv32_host_buffer_entry_points(O):
+    ude = _ude()
+    N = 513
+    theta = glorot_theta((2, 32, 32, 2), seed=2)
+    u0, y = synthetic_ensemble(N)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    out, loss, g, gu, _ = _run(solver, theta, u0, y)
+    out_h, status = solver.solve_host(theta, u0)
+    assert np.array_equal(out_h, out) and (status == 0).all()
+    gu_h = np.empty_like(u0)
+    l_h, g_h, _ = solver.loss_gradient_host(theta, u0, y, grad_u0=gu_h)
+    assert np.array_equal(g_h, g) and np.array_equal(gu_h, gu) and abs(l_h - loss) <= 1e-6 * abs(loss)
+    solver.close()
+
+
+def test_autograd_concrete_solve_matches_adjoint(O):
+    """loss.backward() through concrete_solve(EnsembleProblem) == fused adjoint == oracle."""
+    ude = _ude()
+    N = 300
+    theta = glorot_theta((2, 32, 32, 2), seed=4)
+    u0, y = synthetic_ensemble(N)
+    f = _lv32(ude)
+    prob = ude.EnsembleProblem(ude.ODEProblem(f, None, (0.0, 3.0), None), torch.from_numpy(u0).cuda())
+    p = torch.from_numpy(theta).cuda().requires_grad_(True)
+    pred = ude.concrete_solve(prob, ude.Tsit5(), p=p, saveat=0.1, sensealg=ude.InterpolatingAdjoint(autojacvec=ude.ReverseDiffVJP()))
+    loss = ((pred - torch.from_numpy(y).cuda()) ** 2).sum()
+    loss.backward()
+    m = O.lv_model()
+    l64, g64, _ = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.1, 30)
+    assert abs(float(loss.detach()) - l64) <= 1e-4 * abs(l64)
+    assert np.linalg.norm(p.grad.cpu().numpy() - g64) <= 2e-3 * np.linalg.norm(g64)
+
+
+@pytest.mark.parametrize("name,rates,acts,tend,nsub", [
+    ("scenario_1", 0, ("rbf", "rbf", "rbf"), 3.0, 4),
+    ("scenario_2", 1, ("rbf", "rbf", "rbf"), 6.0, 4),
+    ("hudson_bay", 2, ("rbf", "rbf", "tanh"), 20.0, 8),
+])
+def test_reference_shapes_golden_forward(golden, O, name, rates, acts, tend, nsub):
+    """KAT-2/5/8 on the GPU: the reference's trained parameters reproduce the reference's stored
+    X-hat (its own Vern7@1e-6 solve) with the 2-5-5-5-2 kernels; tolerance = fp32 + the reference
+    solver's own 1e-6..1e-5 error."""
+    ude = _ude()
+    g = golden[name]
+    theta = g["theta_trained"].astype(np.float32)
+    Xhat = g["Xhat"]
+    n_save = Xhat.shape[1]
+    save_dt = tend / (n_save - 1)
+    f = _lv5(ude, acts, rates)
+    solver = ude.UDESolver(f, 0.0, save_dt / nsub, (n_save - 1) * nsub, nsub, max_trajectories=4)
+    u0 = np.repeat(g["X"][:, :1].astype(np.float32), 3, axis=1)
+    out, status = solver.solve_host(theta, u0)
+    assert (status == 0).all()
+    scale = np.abs(Xhat).max()
+    assert np.abs(out[:, :, 0].T - Xhat).max() <= 3e-4 * scale
+    assert np.array_equal(out[:, :, 0], out[:, :, 2])
+    solver.close()
+
+
+@pytest.mark.parametrize("rates,acts", [(0, ("rbf", "rbf", "rbf")), (1, ("rbf", "rbf", "rbf")), (2, ("rbf", "rbf", "tanh"))])
+def test_reference_shapes_adjoint_vs_oracle(golden, O, rates, acts):
+    """2-5-5-5-2 chain with 0/1/2 trainable rates: gradient incl. the physics-rate entries vs the oracle."""
+    ude = _ude()
+    rng = np.random.default_rng(11)
+    N = 193
+    P = 87 + rates
+    theta = (0.5 * rng.standard_normal(P)).astype(np.float32)
+    if rates:
+        theta[:rates] = rng.uniform(0.5, 1.5, rates)
+    u0, y = synthetic_ensemble(N, n_steps=20, dt=0.05)
+    f = _lv5(ude, acts, rates)
+    solver = ude.UDESolver(f, 0.0, 0.05, 20, 1, max_trajectories=N)
+    out, loss, gth, gu, status = _run(solver, theta, u0, y)
+    m = O.lv_model((2, 5, 5, 5, 2), acts + ("identity",), n_prefix=rates)
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.05, 20, want_out=True)
+    assert np.all(np.abs(out - out64) <= 3e-4 * (1 + np.abs(out64)))
+    assert abs(loss - l64) <= 1e-4 * abs(l64)
+    assert np.linalg.norm(gth - g64) <= 2e-3 * np.linalg.norm(g64)
+    if rates:
+        assert np.all(np.abs(gth[:rates] - g64[:rates]) <= 2e-3 * np.abs(g64).max())
+    assert np.abs(gu - gu64).max() <= 2e-3 * np.abs(gu64).max()
+    solver.close()
+
+
+def test_error_behaviour():
+    ude = _ude()
+    from universal_differential_equations_b200._lib import B200UDEError, EINVAL, ESTATE, EUNSUPPORTED
+    f = _lv32(ude)
+    solver = ude.UDESolver(f, 0.0, 0.1, 30, 1, max_trajectories=64)
+    with pytest.raises(B200UDEError) as e:
+        solver.adjoint(torch.zeros(31, 2, 64, device="cuda"))
+    assert e.value.code == ESTATE
+    solver.set_params(torch.zeros(solver.P, device="cuda"))
+    with pytest.raises(B200UDEError) as e:
+        solver.forward(torch.zeros(2, 65, device="cuda"))
+    assert e.value.code == EINVAL
+    chain = ude.FastChain(ude.FastDense(2, 7, ude.tanh), ude.FastDense(7, 2))
+    with pytest.raises(B200UDEError) as e:
+        ude.UDESolver(ude.LotkaVolterraUDE(chain), 0.0, 0.1, 30, 1, max_trajectories=8)
+    assert e.value.code == EUNSUPPORTED
+    # a diverging trajectory is flagged in status, the batch still completes
+    theta = np.zeros(solver.P, np.float32)
+    theta[-2:] = 3e38
+    u0 = np.ones((2, 64), np.float32)
+    _, status = solver.solve_host(theta, u0)
+    assert (status == 1).all()
+    solver.close()
+
+
+def test_full_size_properties():
+    """BASELINE size (65 536): permutation equivariance of the solve, invariance of the summed gradient."""
+    ude = _ude()
+    N = 65536
+    theta = glorot_theta((2, 32, 32, 2), seed=1)
+    u0, y = synthetic_ensemble(N)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    out, loss, g, gu, status = _run(solver, theta, u0, y)
+    assert (status == 0).all() and np.isfinite(out).all() and np.isfinite(g).all()
+    perm = np.random.default_rng(0).permutation(N)
+    out_p, loss_p, g_p, gu_p, _ = _run(solver, theta, u0[:, perm].copy(), y[:, :, perm].copy())
+    assert np.array_equal(out_p, out[:, :, perm]) and np.array_equal(gu_p, gu[:, perm])
+    assert abs(loss_p - loss) <= 1e-5 * abs(loss)
+    assert np.linalg.norm(g_p - g) <= 1e-4 * np.linalg.norm(g)
+    solver.close()

@@ -1,0 +1,210 @@
+"""Pins the CPU oracle against everything the reference commits for this path.
+
+The reference has no test suite for the UDE solve/adjoint; its known answers are the result files
+its own scripts wrote (tests/golden/*.npz, extracted by tools/make_golden.py).  Julia is not available,
+so these artefacts -- not a live run of the reference -- are what pins the oracle.
+"""
+import numpy as np
+import pytest
+
+from helpers import theta_scenario1_init
+
+RBF3 = ("rbf", "rbf", "rbf", "identity")
+
+
+def test_tableaus_match_ordinarydiffeq_serialized_constants(O, golden):
+    """KAT-7: Tsit5 and Vern7 constants equal the copy OrdinaryDiffEq serialized into the reference's .jld2."""
+    g = golden["scenario_1"]
+    assert np.array_equal(O.tsit5_constants(), g["tsit5_consts"][:56])
+    assert np.array_equal(O.vern7_constants(), g["vern7_consts"][:58])
+    c = O.tsit5_constants()
+    b = c[21:27]
+    cc = np.array([0.0, *c[0:5]])
+    assert abs(b.sum() - 1) < 1e-15 and abs(b @ cc - 0.5) < 1e-15 and abs(b @ cc**2 - 1 / 3) < 1e-15
+    assert abs(c[27:34].sum()) < 1e-15  # sum(btilde) = 0
+
+
+def test_kat1_mlp_forward_scenario1(O, golden):
+    g = golden["scenario_1"]
+    m = O.lv_model((2, 5, 5, 5, 2), RBF3)
+    Y = np.stack([O.mlp_forward(m, g["theta_trained"], g["Xhat"][:, i]) for i in range(61)], 1)
+    assert np.abs(Y - g["Yhat"]).max() < 1e-13
+
+
+def test_kat2_forward_solve_scenario1(O, golden):
+    """Stored X-hat = predict(theta_trained, Xn[:,1], 0:0.05:3) (reference: Vern7, tol 1e-6)."""
+    g = golden["scenario_1"]
+    m = O.lv_model((2, 5, 5, 5, 2), RBF3)
+    ts = np.linspace(0, 3, 61)
+    for solver, tol in ((O.TSIT5, 1e-12), (O.VERN7, 1e-10)):
+        out, nacc, nrej = O.solve_adaptive(m, g["theta_trained"], g["X"][:, 0], ts, tol, tol, solver=solver)
+        assert np.abs(out.T - g["Xhat"]).max() < 5e-7
+    out, _, _ = O.solve_adaptive(m, g["theta_trained"], g["X"][:, 0], ts, 1e-6, 1e-6, solver=O.VERN7)
+    assert np.abs(out.T - g["Xhat"]).max() < 5e-7
+    out = O.solve_fixed(m, g["theta_trained"], g["X"][:, 0], 0.05 / 4, 240, solver=O.TSIT5, save_every=4)
+    assert np.abs(out.T - g["Xhat"]).max() < 5e-7
+
+
+def _loss_grad_s1(O, m, th, X, sub=16):
+    dt, ns = 0.1 / sub, 30 * sub
+    out, dense = O.solve_fixed(m, th, X[:, 0], dt, ns, save_every=sub, want_dense=True)
+    r = out - X.T
+    gth, gu = O.adjoint_fixed(m, th, out, dense, dt, ns, 2 * r, save_every=sub)
+    return (r**2).sum(), gth
+
+
+def test_kat3_loss_values_scenario1(O, golden):
+    g = golden["scenario_1"]
+    m = O.lv_model((2, 5, 5, 5, 2), RBF3)
+    l0, _ = _loss_grad_s1(O, m, theta_scenario1_init(g), g["X"])
+    l1, _ = _loss_grad_s1(O, m, g["theta_trained"], g["X"])
+    assert abs(l0 - g["losses"][0]) < 1e-7 * g["losses"][0]
+    assert abs(l1 - g["losses"][-1]) < 1e-5 * g["losses"][-1]
+
+
+def test_kat4_gradient_pinned_by_adam_replay(O, golden):
+    """The reference's stored loss history losses[k] = L(theta_k) under ADAM(0.1) (scenario_1.jl:114) is
+    reproduced by replaying ADAM with the ORACLE'S interpolating-adjoint gradient: this pins d L / d theta
+    (the reference computed it with ForwardDiffSensitivity; any correct gradient must agree)."""
+    g = golden["scenario_1"]
+    m = O.lv_model((2, 5, 5, 5, 2), RBF3)
+    th = theta_scenario1_init(g)
+    mm, vv = np.zeros_like(th), np.zeros_like(th)
+    b1, b2, eta, eps = 0.9, 0.999, 0.1, 1e-8
+    for it in range(1, 7):
+        l, gr = _loss_grad_s1(O, m, th, g["X"])
+        assert abs(l - g["losses"][it - 1]) < 2e-6 * g["losses"][it - 1], (it, l, g["losses"][it - 1])  # reference solver tol 1e-6
+        mm = b1 * mm + (1 - b1) * gr
+        vv = b2 * vv + (1 - b2) * gr * gr
+        th = th - eta * (mm / (1 - b1**it)) / (np.sqrt(vv / (1 - b2**it)) + eps)
+
+
+def test_adjoint_matches_finite_differences(O, golden):
+    g = golden["scenario_1"]
+    m = O.lv_model((2, 5, 5, 5, 2), RBF3)
+    th = theta_scenario1_init(g)
+    _, gr = _loss_grad_s1(O, m, th, g["X"], sub=8)
+    for i in (0, 7, 20, 50, 86):
+        e = np.zeros_like(th)
+        e[i] = 1e-6
+        fd = (_loss_grad_s1(O, m, th + e, g["X"], sub=8)[0] - _loss_grad_s1(O, m, th - e, g["X"], sub=8)[0]) / 2e-6
+        assert abs(fd - gr[i]) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_kat5_scenario2_trainable_decay_rate(O, golden):
+    """theta = [delta; U] (scenario_2.jl:87): MLP and forward solve over tspan (0, 6)."""
+    g = golden["scenario_2"]
+    m = O.lv_model((2, 5, 5, 5, 2), RBF3, n_prefix=1)
+    th = g["theta_trained"]
+    assert abs(th[0] - 1.78527) < 1e-4
+    Y = np.stack([O.mlp_forward(m, th[1:], g["Xhat"][:, i]) for i in range(121)], 1)
+    assert np.abs(Y - g["Yhat"]).max() < 1e-12
+    out, _, _ = O.solve_adaptive(m, th, g["X"][:, 0], np.linspace(0, 6, 121), 1e-11, 1e-11)
+    assert np.abs(out.T - g["Xhat"]).max() < 1e-4
+
+
+def test_kat6_scenario3_pde_rhs(O, golden):
+    """Fisher-KPP UPDE on the 26-point grid, Float32 (scenario_3.jl): pointwise net + stencil."""
+    g = golden["scenario_3"]
+    m = O.fkpp_model(26, (1, 5, 5, 5, 1), RBF3)
+    th = g["theta_trained"].astype(np.float64)
+    assert O.num_params(m) == 81
+    R = np.array([[O.mlp_forward(m, th, np.array([g["Xhat"][i, k]], dtype=np.float64))[0] for k in range(11)] for i in range(26)])
+    assert np.abs(R - g["Rhat"]).max() < 5e-6
+    out, _, _ = O.solve_adaptive(m, th, g["X"][:, 0].astype(np.float64), np.linspace(0, 5, 11), 1e-9, 1e-9)
+    assert np.abs(out.T - g["Xhat"]).max() < 3e-4
+    loss = ((out.T - g["X"]) ** 2).sum() + abs(th[76:79].sum())
+    assert abs(loss - g["losses"][-1]) < 2e-3 * g["losses"][-1] + 2e-5
+
+
+def test_kat8_hudson_bay_fastchain_layout(O, golden):
+    """FastChain(rbf, rbf, tanh, linear) with two trainable rates in front (hudson_bay.jl:77-91)."""
+    g = golden["hudson_bay"]
+    m = O.lv_model((2, 5, 5, 5, 2), ("rbf", "rbf", "tanh", "identity"), n_prefix=2)
+    th = g["theta_trained"].astype(np.float64)
+    Y = np.stack([O.mlp_forward(m, th[2:], g["Xhat"][:, i]) for i in range(41)], 1)
+    assert np.abs(Y - g["Yhat"]).max() < 1e-6
+    out, _, _ = O.solve_adaptive(m, th, g["X"][:, 0].astype(np.float64), g["tsample"], 1e-10, 1e-10)
+    assert np.abs(out.T - g["Xhat"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("model", ["lv", "seir", "fkpp"])
+def test_rhs_vjp_matches_finite_differences(O, model):
+    rng = np.random.default_rng(3)
+    if model == "lv":
+        m = O.lv_model((2, 8, 8, 2), ("tanh", "rbf", "identity"), n_prefix=2)
+        u = np.array([0.7, 2.3])
+    elif model == "seir":
+        m = O.seir_model((3, 16, 16, 1))
+        u = np.array([1.2e7, 80.0, 90.0, 130.0, 1.4e7, 20.0, 250.0])
+    else:
+        m = O.fkpp_model(9, (1, 6, 6, 1), ("tanh", "tanh", "identity"))
+        u = rng.uniform(0, 1, 9)
+    P = O.num_params(m)
+    th = 0.3 * rng.standard_normal(P)
+    lam = rng.standard_normal(m.d)
+    dlam, gth = O.rhs_vjp(m, th, u, lam)
+    for k in range(m.d):
+        e = np.zeros(m.d)
+        h = 1e-6 * max(1.0, abs(u[k]))
+        e[k] = h
+        fd = lam @ (O.rhs(m, th, u + e) - O.rhs(m, th, u - e)) / (2 * h)
+        assert abs(fd - dlam[k]) < 5e-6 * max(1.0, abs(fd)), (k, fd, dlam[k])
+    for i in rng.choice(P, 12, replace=False):
+        e = np.zeros(P)
+        e[i] = 1e-6
+        fd = lam @ (O.rhs(m, th + e, u) - O.rhs(m, th - e, u)) / 2e-6
+        assert abs(fd - gth[i]) < 5e-6 * max(1.0, abs(fd)), (i, fd, gth[i])
+
+
+def test_interpolating_adjoint_vs_autograd_through_the_scheme(O):
+    """Independent cross-oracle: torch-fp64 autograd through a pure-torch Tsit5 (discrete adjoint) agrees
+    with the oracle's continuous interpolating adjoint to truncation error (~3e-8 at dt=0.1)."""
+    torch = pytest.importorskip("torch")
+    from helpers import glorot_theta, synthetic_ensemble
+    N = 16
+    theta = glorot_theta((2, 32, 32, 2), seed=1).astype(np.float64)
+    u0, y = synthetic_ensemble(N)
+    m = O.lv_model()
+    l, g, gu = O.ensemble_loss_grad(m, theta, u0, y, np.ones(2), 0.1, 30)
+    c = O.tsit5_constants()
+    A = np.zeros((7, 7))
+    p = 6
+    for i in range(1, 7):
+        for j in range(i):
+            A[i, j] = c[p]
+            p += 1
+    th = torch.tensor(theta, requires_grad=True)
+    U0 = torch.tensor(u0.astype(np.float64), requires_grad=True)
+
+    def rhs(u):
+        W1 = th[0:64].reshape(2, 32).T; b1 = th[64:96]
+        W2 = th[96:1120].reshape(32, 32).T; b2 = th[1120:1152]
+        W3 = th[1152:1216].reshape(32, 2).T; b3 = th[1216:1218]
+        h = torch.tanh(W1 @ u + b1[:, None]); h = torch.tanh(W2 @ h + b2[:, None]); o = W3 @ h + b3[:, None]
+        return torch.stack([1.3 * u[0] + o[0], -1.8 * u[1] + o[1]])
+    u = U0
+    loss = ((u - torch.tensor(y[0].astype(np.float64))) ** 2).sum()
+    for s in range(30):
+        ks = [rhs(u)]
+        for i in range(1, 7):
+            ks.append(rhs(u + 0.1 * sum(A[i, j] * ks[j] for j in range(i))))
+            if i == 5:
+                pass
+        u = u + 0.1 * sum(A[6, j] * ks[j] for j in range(6))
+        loss = loss + ((u - torch.tensor(y[s + 1].astype(np.float64))) ** 2).sum()
+    loss.backward()
+    assert abs(float(loss) - l) < 1e-10 * l
+    assert np.linalg.norm(th.grad.numpy() - g) < 1e-6 * np.linalg.norm(g)
+    assert np.abs(U0.grad.numpy() - gu).max() < 1e-6 * np.abs(gu).max()
+
+
+def test_fp32_oracle_close_to_fp64(O):
+    from helpers import glorot_theta, synthetic_ensemble
+    theta = glorot_theta((2, 32, 32, 2), seed=1)
+    u0, y = synthetic_ensemble(256)
+    m = O.lv_model()
+    l64, g64, gu64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.1, 30)
+    l32, g32, gu32 = O.ensemble_loss_grad(m, theta, u0, y, np.ones(2, np.float32), 0.1, 30)
+    assert abs(l32 - l64) < 1e-5 * l64
+    assert np.linalg.norm(g32 - g64) < 1e-4 * np.linalg.norm(g64)
