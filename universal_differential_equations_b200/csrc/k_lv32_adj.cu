@@ -10,9 +10,7 @@ template <int TM, class W>
 static cudaError_t launch_one(const AdjParams &p, int grid, cudaStream_t st)
 {
     auto kern = lv32::adjoint_kernel<TM, W, ADJ_BLOCK_GEMM, 1>;
-    constexpr size_t theta = WeightStage<W>::kSmem ? sizeof(float) * ((lv32::P + 3) / 4) * 4 : 0;
-    constexpr size_t smem = theta + sizeof(lv32::WarpStage2) * (ADJ_BLOCK_GEMM / 32);
-    static_assert(sizeof(lv32::WarpStage2) >= sizeof(float) * (lv32::P + 1), "reduction buffer aliases the stages");
+    constexpr size_t smem = sizeof(lv32::WarpStage3);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -32,13 +30,12 @@ cudaError_t launch_adj_lv32(const Variant &v, const ConstTables &t, const AdjPar
     const int grid = adj_grid_lv32(p.N);
     *grid_out = grid;
     if (v.approx_tanh) return launch_one<1, WConst>(p, grid, st);
-    if (v.adj_smem) return launch_one<0, WSmem>(p, grid, st);
     return launch_one<0, WConst>(p, grid, st);
 }
 
 cudaError_t launch_reduce(const float *partial, int nblocks, int P1, float *grad, float *loss, cudaStream_t st)
 {
-    ude_reduce_kernel<<<(P1 + 127) / 128, 128, 0, st>>>(partial, nblocks, P1, grad, loss);
+    ude_reduce_kernel<<<(P1 + 7) / 8, 256, 0, st>>>(partial, nblocks, P1, grad, loss);
     return cudaGetLastError();
 }
 

@@ -6,11 +6,11 @@ namespace b200ude {
 template <int TM, class W>
 static cudaError_t launch_one(const FwdParams &p, cudaStream_t st)
 {
-    auto kern = lv32::forward_kernel<TM, W, FWD_BLOCK, 1>;
+    auto kern = lv32::forward_kernel<TM, W, FWD_BLOCK_LV32, 1>;
     const int half = (p.N + 1) / 2;
-    const int grid = (half + FWD_BLOCK - 1) / FWD_BLOCK;
+    const int grid = (half + FWD_BLOCK_LV32 - 1) / FWD_BLOCK_LV32;
     const size_t smem = WeightStage<W>::kSmem ? sizeof(float) * ((lv32::P + 3) / 4) * 4 : 0;
-    kern<<<grid, FWD_BLOCK, smem, st>>>(p);
+    kern<<<grid, FWD_BLOCK_LV32, smem, st>>>(p);
     return cudaGetLastError();
 }
 

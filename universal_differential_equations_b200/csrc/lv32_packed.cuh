@@ -178,185 +178,26 @@ __global__ void __launch_bounds__(BLOCK, MINB) forward_kernel(FwdParams p)
 // ---- adjoint ---------------------------------------------------------------------------------------
 // Per-warp shared-memory staging.  Row r belongs to lane r and holds, for every hidden unit j, the
 // PAIR (value for trajectory a, value for trajectory b) -- exactly the thread's register pairs, so the
-// 128-bit row stores need no shuffling.  LD = 68 floats makes both the row stores (8 consecutive lanes
-// -> 8 distinct bank groups) and the broadcast tile loads conflict-free.
+// 128-bit row stores need no shuffling.  Element (j, a|b) of a row sits at 2j + (a|b) + (j >= 16 ? 4 : 0):
+// the 4-float gap in the middle of the row makes the four 64-byte j-tiles (and the eight 32-byte
+// i-tiles) that the 32 lanes read in ONE instruction fall on distinct banks; LD = 68 keeps the
+// 128-bit row stores conflict-free (8 consecutive lanes -> 8 distinct bank groups).
 constexpr int LD = 68;
-struct __align__(16) WarpStage2 {
-    float B1[32 * LD];   // h2, then q2, then q1     [lane][j][a|b]
-    float B2[32 * LD];   // h1                        [lane][j][a|b]
+__device__ __forceinline__ constexpr int rowoff(int j) { return 2 * j + (j >= 16 ? 4 : 0); }
+struct __align__(16) WarpStage3 {
+    float B1[32 * LD];   // h2 rows                   [lane][j][a|b]
+    float B2[32 * LD];   // h1 rows, later q1 rows    [lane][j][a|b]
+    float B3[32 * LD];   // q2 rows                   [lane][j][a|b]
     float SG[32 * 4];    // scaled output cotangent   [lane][m][a|b]
     float U[32 * 4];     // chain input               [lane][m][a|b]
-    float ACC[64 * 32];  // dW2 tile accumulators: lane (jt, it) owns [jj 0..7][ii 0..3][a|b]; stored [(c*32 + lane)*4 + k]
-    float THIN[16 * 32]; // lane-owned rows of the thin layers: 8 float2 per lane, stored [(c*32 + lane)*4 + k], c < 4
 };
 
-struct AdjStageIn {
-    Pair2 x;    // u(t) at this stage (chain input)
-    Pair2 g;    // backward stage argument lambda_i
-    float sc;   // quadrature weight dt*b_i
-    float isc;  // 1/sc
-    float lva, lvb;  // 1 for live trajectories, 0 for padding (contribute zero to the gradient)
-};
-
-// One backward stage: chain forward, reverse sweep, (df/du)^T g, and this stage's contribution to the
-// ensemble-summed parameter gradient (per-warp outer-product GEMM over the warp's 64 trajectories).
-template <int TM, class W>
-__device__ __noinline__ Pair2 adj_stage(W w, WarpStage2 *st, AdjStageIn in)
-{
-    const int lane = threadIdx.x & 31;
-    const int jt = lane >> 3, it = lane & 7;
-    const float2 lv = make_float2(in.lva, in.lvb);
-    const float2 sg0 = mul2(bc(in.sc), in.g.c0), sg1 = mul2(bc(in.sc), in.g.c1);
-    {
-        const float2 m0 = mul2(lv, sg0), m1 = mul2(lv, sg1);
-        *reinterpret_cast<float4 *>(&st->SG[lane * 4]) = make_float4(m0.x, m0.y, m1.x, m1.y);
-        *reinterpret_cast<float4 *>(&st->U[lane * 4]) = make_float4(in.x.c0.x, in.x.c0.y, in.x.c1.x, in.x.c1.y);
-    }
-    // ---- layer 1 ----
-    float2 h1[H];
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        float2 a = bc(w(OFF_B1 + j));
-        a = fmas(w(OFF_W1 + j), in.x.c0, a);
-        a = fmas(w(OFF_W1 + H + j), in.x.c1, a);
-        h1[j] = tanh2<TM>(a);
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c)
-        *reinterpret_cast<float4 *>(&st->B2[lane * LD + 4 * c]) = make_float4(h1[2 * c].x, h1[2 * c].y, h1[2 * c + 1].x, h1[2 * c + 1].y);
-    // ---- layer 2 in blocks of 4 outputs; h2 goes straight to B1, q2 stays in registers ----
-    float2 q2[H];
-#pragma unroll
-    for (int jb = 0; jb < 8; ++jb) {
-        float2 acc[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) acc[jj] = bc(w(OFF_B2 + jb * 4 + jj));
-#pragma unroll
-        for (int i = 0; i < H; ++i)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[jj] = fmas(w(OFF_W2 + i * H + jb * 4 + jj), h1[i], acc[jj]);
-        float2 h2[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            h2[jj] = tanh2<TM>(acc[jj]);
-            const int j = jb * 4 + jj;
-            const float2 t = fmas(w(OFF_W3 + j * 2 + 1), sg1, mul2(bc(w(OFF_W3 + j * 2)), sg0));
-            q2[j] = mul2(t, fma2(mul2(h2[jj], bc(-1.0f)), h2[jj], bc(1.0f)));  // * (1 - h2^2)
-        }
-        *reinterpret_cast<float4 *>(&st->B1[lane * LD + 8 * jb]) = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
-        *reinterpret_cast<float4 *>(&st->B1[lane * LD + 8 * jb + 4]) = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
-    }
-    __syncwarp();
-    // ---- thin pass A: lane j owns output-layer column j: dW3[m][j] += sum_t SG[t][m] * h2[t][j]; db3 ----
-    {
-        float4 ta = *reinterpret_cast<const float4 *>(&st->THIN[(0 * 32 + lane) * 4]);  // (w30.a, w30.b, w31.a, w31.b)
-        float4 tb = *reinterpret_cast<const float4 *>(&st->THIN[(1 * 32 + lane) * 4]);  // (b30.a, b30.b, b31.a, b31.b)
-        float2 w30 = make_float2(ta.x, ta.y), w31 = make_float2(ta.z, ta.w);
-        float2 b30 = make_float2(tb.x, tb.y), b31 = make_float2(tb.z, tb.w);
-#pragma unroll 8
-        for (int t = 0; t < 32; ++t) {
-            const float2 hh = *reinterpret_cast<const float2 *>(&st->B1[t * LD + 2 * lane]);
-            const float4 s4 = *reinterpret_cast<const float4 *>(&st->SG[t * 4]);
-            const float2 s0 = make_float2(s4.x, s4.y), s1 = make_float2(s4.z, s4.w);
-            w30 = fma2(s0, hh, w30);
-            w31 = fma2(s1, hh, w31);
-            b30 = add2(b30, s0);
-            b31 = add2(b31, s1);
-        }
-        *reinterpret_cast<float4 *>(&st->THIN[(0 * 32 + lane) * 4]) = make_float4(w30.x, w30.y, w31.x, w31.y);
-        *reinterpret_cast<float4 *>(&st->THIN[(1 * 32 + lane) * 4]) = make_float4(b30.x, b30.y, b31.x, b31.y);
-    }
-    __syncwarp();
-    // ---- B1 <- q2 (masked); q1 = (W2^T q2) * (1 - h1^2) overwrites h1 ----
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const float2 m0 = mul2(lv, q2[2 * c]), m1 = mul2(lv, q2[2 * c + 1]);
-        *reinterpret_cast<float4 *>(&st->B1[lane * LD + 4 * c]) = make_float4(m0.x, m0.y, m1.x, m1.y);
-    }
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        float2 a0 = bc(0.0f), a1 = bc(0.0f);
-#pragma unroll
-        for (int j = 0; j < H; j += 2) {
-            a0 = fmas(w(OFF_W2 + i * H + j), q2[j], a0);
-            a1 = fmas(w(OFF_W2 + i * H + j + 1), q2[j + 1], a1);
-        }
-        h1[i] = mul2(add2(a0, a1), fma2(mul2(h1[i], bc(-1.0f)), h1[i], bc(1.0f)));  // h1[] now holds q1[]
-    }
-    __syncwarp();
-    // ---- GEMM pass: ACC[j][i](a|b) += q2[t][j](a|b) * h1[t][i](a|b) over the 32 staged rows ----
-    {
-        float2 acc[32];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const float4 v = *reinterpret_cast<const float4 *>(&st->ACC[(c * 32 + lane) * 4]);
-            acc[2 * c] = make_float2(v.x, v.y);
-            acc[2 * c + 1] = make_float2(v.z, v.w);
-        }
-        float4 tc = *reinterpret_cast<const float4 *>(&st->THIN[(2 * 32 + lane) * 4]);  // (b2.a, b2.b, b1.a, b1.b)
-        float2 gb2 = make_float2(tc.x, tc.y);
-#pragma unroll 2
-        for (int t = 0; t < 32; ++t) {
-            float2 gj[8], hi[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float4 v = *reinterpret_cast<const float4 *>(&st->B1[t * LD + jt * 16 + 4 * c]);
-                gj[2 * c] = make_float2(v.x, v.y);
-                gj[2 * c + 1] = make_float2(v.z, v.w);
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const float4 v = *reinterpret_cast<const float4 *>(&st->B2[t * LD + it * 8 + 4 * c]);
-                hi[2 * c] = make_float2(v.x, v.y);
-                hi[2 * c + 1] = make_float2(v.z, v.w);
-            }
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii) acc[jj * 4 + ii] = fma2(gj[jj], hi[ii], acc[jj * 4 + ii]);
-            gb2 = add2(gb2, *reinterpret_cast<const float2 *>(&st->B1[t * LD + 2 * lane]));  // db2[lane]
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c)
-            *reinterpret_cast<float4 *>(&st->ACC[(c * 32 + lane) * 4]) = make_float4(acc[2 * c].x, acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y);
-        *reinterpret_cast<float2 *>(&st->THIN[(2 * 32 + lane) * 4]) = gb2;
-    }
-    // ---- input cotangent and (df/du)^T g ----
-    float2 dx0 = bc(0.0f), dx1 = bc(0.0f);
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        dx0 = fmas(w(OFF_W1 + j), h1[j], dx0);
-        dx1 = fmas(w(OFF_W1 + H + j), h1[j], dx1);
-    }
-    Pair2 kl;
-    kl.c0 = fmas(c_consts[0], in.g.c0, mul2(dx0, bc(in.isc)));    // LV physics: diag(p1, -p4)
-    kl.c1 = fmas(-c_consts[1], in.g.c1, mul2(dx1, bc(in.isc)));
-    __syncwarp();
-    // ---- B1 <- q1 (masked); thin pass B: lane i owns input-layer row i: dW1[i][m] += sum_t q1[t][i] x[t][m]; db1 ----
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const float2 m0 = mul2(lv, h1[2 * c]), m1 = mul2(lv, h1[2 * c + 1]);
-        *reinterpret_cast<float4 *>(&st->B1[lane * LD + 4 * c]) = make_float4(m0.x, m0.y, m1.x, m1.y);
-    }
-    __syncwarp();
-    {
-        float2 gb1 = *reinterpret_cast<const float2 *>(&st->THIN[(2 * 32 + lane) * 4 + 2]);
-        float4 td = *reinterpret_cast<const float4 *>(&st->THIN[(3 * 32 + lane) * 4]);  // (w10.a, w10.b, w11.a, w11.b)
-        float2 w10 = make_float2(td.x, td.y), w11 = make_float2(td.z, td.w);
-#pragma unroll 8
-        for (int t = 0; t < 32; ++t) {
-            const float2 qq = *reinterpret_cast<const float2 *>(&st->B1[t * LD + 2 * lane]);
-            const float4 u4 = *reinterpret_cast<const float4 *>(&st->U[t * 4]);
-            gb1 = add2(gb1, qq);
-            w10 = fma2(qq, make_float2(u4.x, u4.y), w10);
-            w11 = fma2(qq, make_float2(u4.z, u4.w), w11);
-        }
-        *reinterpret_cast<float2 *>(&st->THIN[(2 * 32 + lane) * 4 + 2]) = gb1;
-        *reinterpret_cast<float4 *>(&st->THIN[(3 * 32 + lane) * 4]) = make_float4(w10.x, w10.y, w11.x, w11.y);
-    }
-    __syncwarp();
-    return kl;
-}
+// Loop-variant zero: adding c_zero[i] (unknown to ptxas) to every constant-bank weight address keeps
+// the weight loads INSIDE the stage loop (otherwise ptxas hoists the loop-invariant loads out of the
+// time loops and spills them, see ude_common.cuh), at the cost of one LDCU per stage.
+static __constant__ int c_zero[8];
+// four consecutive weights with one 128-bit constant-bank load (idx must be a multiple of 4)
+__device__ __forceinline__ float4 ldw4(int idx) { return *reinterpret_cast<const float4 *>(&c_theta[idx]); }
 
 // u(t_{s+1} - c_I dt) for both trajectories from the stored dense output of forward step s
 template <int I>
@@ -396,12 +237,21 @@ __device__ __forceinline__ void jump_pair(const AdjParams &p, int isave, size_t 
     }
 }
 
+
+// The whole InterpolatingAdjoint backward solve for 64 trajectories per warp.  One warp per CTA.
+// Stage body (executed 6 x n_steps times, as ONE rolled loop so that it fits the instruction cache):
+//   1. chain forward: h1 -> registers + B2; h2 -> B1; q2 = W3^T sg * (1 - h2^2) -> B3
+//   2. GEMM/thin pass over the 32 staged rows (software-pipelined 128-bit shared loads):
+//        dW2[j][i] += q2[t][j] h1[t][i]   (lane (jt, it) owns an 8 x 4 tile, accumulators in registers)
+//        db2, dW3, db3 as lane-owned columns
+//   3. q1 = (W2^T q2) * (1 - h1^2) -> B2 (in place of h1), (df/du)^T g
+//   4. thin pass: dW1, db1 as lane-owned columns
 template <int TM, class W, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
 {
-    constexpr int NWARP = BLOCK / 32;
-    const W w = WeightStage<W>::load(p.theta, p.P);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    static_assert(BLOCK == 32, "one warp (64 trajectories) per CTA");
+    static_assert(!WeightStage<W>::kSmem, "the adjoint reads its weights from the constant bank");
+    const int lane = threadIdx.x & 31;
     const int jt = lane >> 3, it = lane & 7;
     const int half = (p.N + 1) >> 1;
     const int tid = blockIdx.x * BLOCK + threadIdx.x;
@@ -411,15 +261,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
     const bool live_b = live_a && (tid + half < p.N);
     const size_t nb = live_b ? (size_t)(tid + half) : na;
     const float dt = p.dt;
+    // padding trajectories carry a zero mask on their cotangents: they contribute nothing to the sums
+    const float2 lv = make_float2(live_a ? 1.0f : 0.0f, live_b ? 1.0f : 0.0f);
 
     extern __shared__ __align__(16) unsigned char s_raw[];
-    constexpr int THETA_SMEM_FLOATS = WeightStage<W>::kSmem ? ((P + 3) / 4) * 4 : 0;
-    WarpStage2 *st = reinterpret_cast<WarpStage2 *>(s_raw + sizeof(float) * THETA_SMEM_FLOATS) + warp;
+    WarpStage3 *st = reinterpret_cast<WarpStage3 *>(s_raw);
+    float *const rowB1 = st->B1 + lane * LD, *const rowB2 = st->B2 + lane * LD, *const rowB3 = st->B3 + lane * LD;
+    const int goff = jt * 16 + (jt >= 2 ? 4 : 0);   // this lane's j-tile inside a row
+    const int hoff = it * 8 + (it >= 4 ? 4 : 0);    // this lane's i-tile inside a row
+    const int coff = rowoff(lane);                  // this lane's column inside a row
+
+    // ---- gradient accumulators (registers, live across the whole backward solve) ----
+    float2 acc[32];       // dW2 tile: acc[jj*4 + ii] for j = jt*8 + jj, i = it*4 + ii; halves a|b added at the end
 #pragma unroll
-    for (int c = 0; c < 16; ++c) *reinterpret_cast<float4 *>(&st->ACC[(c * 32 + lane) * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) *reinterpret_cast<float4 *>(&st->THIN[(c * 32 + lane) * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
+    for (int q = 0; q < 32; ++q) acc[q] = bc(0.0f);
+    float2 g_w30 = bc(0.f), g_w31 = bc(0.f), g_b30 = bc(0.f), g_b31 = bc(0.f), g_b2 = bc(0.f);
+    float2 g_b1 = bc(0.f), g_w10 = bc(0.f), g_w11 = bc(0.f);
 
     Pair2 lam;
     lam.c0 = bc(0.0f);
@@ -427,36 +284,209 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
     float2 loss = bc(0.0f);
     const int n_save = p.n_steps / p.save_every + 1;
     jump_pair(p, n_save - 1, na, nb, N, lam, loss);
-
-    AdjStageIn in;
-    in.lva = live_a ? 1.0f : 0.0f;
-    in.lvb = live_b ? 1.0f : 0.0f;
+    const float p1 = c_consts[0], p4 = c_consts[1];
+    const float inv_dt = 1.0f / dt;
 
 #pragma unroll 1
     for (int s = p.n_steps - 1; s >= 0; --s) {
         Pair2 kl[6];
-#define B200UDE_ADJ_STAGE(I)                                                          \
-    {                                                                                 \
-        in.x = interp_pair<I>(p, s, na, nb, N, dt);                                   \
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { kl[j].c0 = bc(0.0f); kl[j].c1 = bc(0.0f); }
+#pragma unroll 1
+        for (int stage = 0; stage < 6; ++stage) {
+            Pair2 x, g;
+            float sc, isc;
+            // stage-specific part: interpolation weights, Runge-Kutta row, quadrature weight (all static per case)
+#define B200UDE_STAGE_PRE(I)                                                          \
+    case I: {                                                                         \
+        x = interp_pair<I>(p, s, na, nb, N, dt);                                      \
         float2 a0 = bc(0.0f), a1 = bc(0.0f);                                          \
         _Pragma("unroll") for (int j = 0; j < I; ++j) if (Tsit5::a(I, j) != 0.0) {    \
             a0 = fmas((float)Tsit5::a(I, j), kl[j].c0, a0);                           \
             a1 = fmas((float)Tsit5::a(I, j), kl[j].c1, a1);                           \
         }                                                                             \
-        in.g.c0 = fmas(dt, a0, lam.c0);                                               \
-        in.g.c1 = fmas(dt, a1, lam.c1);                                               \
-        in.sc = dt * (float)Tsit5::b(I);                                              \
-        in.isc = 1.0f / in.sc;                                                        \
-        kl[I] = adj_stage<TM>(w, st, in);                                             \
-    }
-        // k_7 of the backward step only feeds FSAL / error estimation: not needed
-        B200UDE_ADJ_STAGE(0)
-        B200UDE_ADJ_STAGE(1)
-        B200UDE_ADJ_STAGE(2)
-        B200UDE_ADJ_STAGE(3)
-        B200UDE_ADJ_STAGE(4)
-        B200UDE_ADJ_STAGE(5)
-#undef B200UDE_ADJ_STAGE
+        g.c0 = fmas(dt, a0, lam.c0);                                                  \
+        g.c1 = fmas(dt, a1, lam.c1);                                                  \
+        sc = dt * (float)Tsit5::b(I);                                                 \
+        isc = inv_dt * (float)(1.0 / Tsit5::b(I));                                    \
+    } break;
+            switch (stage) {
+                B200UDE_STAGE_PRE(0)
+                B200UDE_STAGE_PRE(1)
+                B200UDE_STAGE_PRE(2)
+                B200UDE_STAGE_PRE(3)
+                B200UDE_STAGE_PRE(4)
+            default:
+                B200UDE_STAGE_PRE(5)
+            }
+#undef B200UDE_STAGE_PRE
+            const int zb = c_zero[stage] << 2;   // == 0 (and provably a multiple of 4), opaque to ptxas: pins the weight loads inside this loop
+            // cotangent of the chain output, carrying the quadrature weight and the padding mask
+            const float2 sg0 = mul2(mul2(lv, bc(sc)), g.c0), sg1 = mul2(mul2(lv, bc(sc)), g.c1);
+            *reinterpret_cast<float4 *>(&st->SG[lane * 4]) = make_float4(sg0.x, sg0.y, sg1.x, sg1.y);
+            *reinterpret_cast<float4 *>(&st->U[lane * 4]) = make_float4(x.c0.x, x.c0.y, x.c1.x, x.c1.y);
+
+            // ---- 1. chain forward ----
+            float2 h1[H];
+#pragma unroll
+            for (int j4 = 0; j4 < H; j4 += 4) {
+                const float4 wb1 = ldw4(zb + OFF_B1 + j4), w10 = ldw4(zb + OFF_W1 + j4), w11 = ldw4(zb + OFF_W1 + H + j4);
+                const float b_[4] = {wb1.x, wb1.y, wb1.z, wb1.w}, w0_[4] = {w10.x, w10.y, w10.z, w10.w}, w1_[4] = {w11.x, w11.y, w11.z, w11.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h1[j4 + k] = tanh2<TM>(fmas(w1_[k], x.c1, fmas(w0_[k], x.c0, bc(b_[k]))));
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                *reinterpret_cast<float4 *>(rowB2 + 4 * c + (c >= 8 ? 4 : 0)) = make_float4(h1[2 * c].x, h1[2 * c].y, h1[2 * c + 1].x, h1[2 * c + 1].y);
+#pragma unroll 1
+            for (int jb = 0; jb < 4; ++jb) {   // 8 outputs per iteration
+                const int wb = zb + jb * 8;
+                float2 a8[8];
+                {
+                    const float4 bA = ldw4(wb + OFF_B2), bB = ldw4(wb + OFF_B2 + 4);
+                    a8[0] = bc(bA.x); a8[1] = bc(bA.y); a8[2] = bc(bA.z); a8[3] = bc(bA.w);
+                    a8[4] = bc(bB.x); a8[5] = bc(bB.y); a8[6] = bc(bB.z); a8[7] = bc(bB.w);
+                }
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const float4 wA = ldw4(wb + OFF_W2 + i * H), wB = ldw4(wb + OFF_W2 + i * H + 4);
+                    a8[0] = fmas(wA.x, h1[i], a8[0]); a8[1] = fmas(wA.y, h1[i], a8[1]);
+                    a8[2] = fmas(wA.z, h1[i], a8[2]); a8[3] = fmas(wA.w, h1[i], a8[3]);
+                    a8[4] = fmas(wB.x, h1[i], a8[4]); a8[5] = fmas(wB.y, h1[i], a8[5]);
+                    a8[6] = fmas(wB.z, h1[i], a8[6]); a8[7] = fmas(wB.w, h1[i], a8[7]);
+                }
+                float2 h2[8], q2[8];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {   // W3[m][j] at j*2 + m: (w0j, w1j, w0j+1, w1j+1)
+                    const float4 w3 = ldw4(2 * wb - zb + OFF_W3 + 4 * c);
+                    const float w3_[4] = {w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int jj = 2 * c + k;
+                        h2[jj] = tanh2<TM>(a8[jj]);
+                        const float2 t = fmas(w3_[2 * k + 1], sg1, mul2(bc(w3_[2 * k]), sg0));
+                        q2[jj] = mul2(t, fma2(mul2(h2[jj], bc(-1.0f)), h2[jj], bc(1.0f)));   // * (1 - h2^2)
+                    }
+                }
+                const int ro = jb * 16 + (jb >= 2 ? 4 : 0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    *reinterpret_cast<float4 *>(rowB1 + ro + 4 * c) = make_float4(h2[2 * c].x, h2[2 * c].y, h2[2 * c + 1].x, h2[2 * c + 1].y);
+                    *reinterpret_cast<float4 *>(rowB3 + ro + 4 * c) = make_float4(q2[2 * c].x, q2[2 * c].y, q2[2 * c + 1].x, q2[2 * c + 1].y);
+                }
+            }
+            __syncwarp();
+
+            // ---- 2. GEMM + thin pass over the staged rows, operands double-buffered in registers ----
+            {
+                float4 G[2][4], Hh[2][2], S[2];
+                float2 hc[2], qc[2];
+                auto load_row = [&](int t, int b) {
+                    const float *r3 = st->B3 + t * LD, *r2 = st->B2 + t * LD, *r1 = st->B1 + t * LD;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) G[b][c] = *reinterpret_cast<const float4 *>(r3 + goff + 4 * c);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) Hh[b][c] = *reinterpret_cast<const float4 *>(r2 + hoff + 4 * c);
+                    hc[b] = *reinterpret_cast<const float2 *>(r1 + coff);
+                    qc[b] = *reinterpret_cast<const float2 *>(r3 + coff);
+                    S[b] = *reinterpret_cast<const float4 *>(&st->SG[t * 4]);
+                };
+                auto use_row = [&](int b) {
+                    const float2 gj[8] = {make_float2(G[b][0].x, G[b][0].y), make_float2(G[b][0].z, G[b][0].w),
+                                          make_float2(G[b][1].x, G[b][1].y), make_float2(G[b][1].z, G[b][1].w),
+                                          make_float2(G[b][2].x, G[b][2].y), make_float2(G[b][2].z, G[b][2].w),
+                                          make_float2(G[b][3].x, G[b][3].y), make_float2(G[b][3].z, G[b][3].w)};
+                    const float2 hi[4] = {make_float2(Hh[b][0].x, Hh[b][0].y), make_float2(Hh[b][0].z, Hh[b][0].w),
+                                          make_float2(Hh[b][1].x, Hh[b][1].y), make_float2(Hh[b][1].z, Hh[b][1].w)};
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) acc[jj * 4 + ii] = fma2(gj[jj], hi[ii], acc[jj * 4 + ii]);
+                    const float2 s0 = make_float2(S[b].x, S[b].y), s1 = make_float2(S[b].z, S[b].w);
+                    g_w30 = fma2(s0, hc[b], g_w30);
+                    g_w31 = fma2(s1, hc[b], g_w31);
+                    g_b30 = add2(g_b30, s0);
+                    g_b31 = add2(g_b31, s1);
+                    g_b2 = add2(g_b2, qc[b]);
+                };
+                load_row(0, 0);
+#pragma unroll 1
+                for (int t = 0; t < 32; t += 2) {
+                    load_row(t + 1, 1);
+                    use_row(0);
+                    if (t + 2 < 32) load_row(t + 2, 0);
+                    use_row(1);
+                }
+            }
+            __syncwarp();
+
+            // ---- 3. q1 = (W2^T q2) * (1 - h1^2), written over h1 in B2; (df/du)^T g ----
+            float2 dx0 = bc(0.0f), dx1 = bc(0.0f);
+            {
+                float2 q2[H];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float4 v = *reinterpret_cast<const float4 *>(rowB3 + 4 * c + (c >= 8 ? 4 : 0));
+                    q2[2 * c] = make_float2(v.x, v.y);
+                    q2[2 * c + 1] = make_float2(v.z, v.w);
+                }
+#pragma unroll 1
+                for (int ib = 0; ib < 8; ++ib) {   // 4 inputs i per iteration, two partial sums each
+                    const int wb = zb + ib * 4 * H;
+                    float2 a0[4], a1[4];
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) { a0[ii] = bc(0.0f); a1[ii] = bc(0.0f); }
+#pragma unroll
+                    for (int j = 0; j < H; j += 4)
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) {
+                            const float4 w4 = ldw4(wb + OFF_W2 + ii * H + j);
+                            a0[ii] = fmas(w4.x, q2[j], a0[ii]);
+                            a1[ii] = fmas(w4.y, q2[j + 1], a1[ii]);
+                            a0[ii] = fmas(w4.z, q2[j + 2], a0[ii]);
+                            a1[ii] = fmas(w4.w, q2[j + 3], a1[ii]);
+                        }
+                    const int ro = ib * 8 + (ib >= 4 ? 4 : 0);
+                    const float4 hA = *reinterpret_cast<const float4 *>(rowB2 + ro), hB = *reinterpret_cast<const float4 *>(rowB2 + ro + 4);
+                    const float2 hb[4] = {make_float2(hA.x, hA.y), make_float2(hA.z, hA.w), make_float2(hB.x, hB.y), make_float2(hB.z, hB.w)};
+                    float2 q1[4];
+                    const float4 wx0 = ldw4(zb + OFF_W1 + ib * 4), wx1 = ldw4(zb + OFF_W1 + H + ib * 4);
+                    const float wx0_[4] = {wx0.x, wx0.y, wx0.z, wx0.w}, wx1_[4] = {wx1.x, wx1.y, wx1.z, wx1.w};
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        q1[ii] = mul2(add2(a0[ii], a1[ii]), fma2(mul2(hb[ii], bc(-1.0f)), hb[ii], bc(1.0f)));
+                        dx0 = fmas(wx0_[ii], q1[ii], dx0);
+                        dx1 = fmas(wx1_[ii], q1[ii], dx1);
+                    }
+                    *reinterpret_cast<float4 *>(rowB2 + ro) = make_float4(q1[0].x, q1[0].y, q1[1].x, q1[1].y);
+                    *reinterpret_cast<float4 *>(rowB2 + ro + 4) = make_float4(q1[2].x, q1[2].y, q1[3].x, q1[3].y);
+                }
+            }
+            // (df/du)^T g with the LV physics diag(p1, -p4); dx carries sc (and the mask of padding lanes)
+            Pair2 kn;
+            kn.c0 = fmas(p1, g.c0, mul2(dx0, bc(isc)));
+            kn.c1 = fmas(-p4, g.c1, mul2(dx1, bc(isc)));
+            switch (stage) {
+            case 0: kl[0] = kn; break;
+            case 1: kl[1] = kn; break;
+            case 2: kl[2] = kn; break;
+            case 3: kl[3] = kn; break;
+            case 4: kl[4] = kn; break;
+            default: kl[5] = kn; break;
+            }
+            __syncwarp();
+
+            // ---- 4. thin pass: lane i owns input-layer row i: dW1[i][m] += sum_t q1[t][i] x[t][m]; db1 ----
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) {
+                const float2 qq = *reinterpret_cast<const float2 *>(st->B2 + t * LD + coff);
+                const float4 u4 = *reinterpret_cast<const float4 *>(&st->U[t * 4]);
+                g_b1 = add2(g_b1, qq);
+                g_w10 = fma2(qq, make_float2(u4.x, u4.y), g_w10);
+                g_w11 = fma2(qq, make_float2(u4.z, u4.w), g_w11);
+            }
+            __syncwarp();
+        }
         float2 a0 = bc(0.0f), a1 = bc(0.0f);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
@@ -471,48 +501,27 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
         if (live_a) { p.grad_u0[na] = lam.c0.x; p.grad_u0[N + na] = lam.c1.x; }
         if (live_b) { p.grad_u0[nb] = lam.c0.y; p.grad_u0[N + nb] = lam.c1.y; }
     }
-    float lsum = loss.x * in.lva + loss.y * in.lvb;
+    float lsum = loss.x * lv.x + loss.y * lv.y;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
 
-    // ---- CTA reduction, fixed warp order -> deterministic ----
-    float acc[32];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const float4 v = *reinterpret_cast<const float4 *>(&st->ACC[(c * 32 + lane) * 4]);
-        acc[2 * c] = v.x + v.y;       // halves a|b added here
-        acc[2 * c + 1] = v.z + v.w;
-    }
-    const float4 t0 = *reinterpret_cast<const float4 *>(&st->THIN[(0 * 32 + lane) * 4]);
-    const float4 t1 = *reinterpret_cast<const float4 *>(&st->THIN[(1 * 32 + lane) * 4]);
-    const float4 t2 = *reinterpret_cast<const float4 *>(&st->THIN[(2 * 32 + lane) * 4]);
-    const float4 t3 = *reinterpret_cast<const float4 *>(&st->THIN[(3 * 32 + lane) * 4]);
-    __syncthreads();
-    float *red = reinterpret_cast<float *>(s_raw + sizeof(float) * THETA_SMEM_FLOATS);  // [P+1], aliases the stages
-    for (int q = threadIdx.x; q < P + 1; q += BLOCK) red[q] = 0.0f;
-    __syncthreads();
-    for (int wv = 0; wv < NWARP; ++wv) {
-        if (warp == wv) {
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii) red[OFF_W2 + (it * 4 + ii) * H + (jt * 8 + jj)] += acc[jj * 4 + ii];
-            red[OFF_W3 + lane * 2 + 0] += t0.x + t0.y;
-            red[OFF_W3 + lane * 2 + 1] += t0.z + t0.w;
-            red[OFF_B2 + lane] += t2.x + t2.y;
-            red[OFF_B1 + lane] += t2.z + t2.w;
-            red[OFF_W1 + lane] += t3.x + t3.y;
-            red[OFF_W1 + H + lane] += t3.z + t3.w;
-            if (lane == 0) {
-                red[OFF_B3 + 0] += t1.x + t1.y;   // identical in every lane (sum over the staged rows)
-                red[OFF_B3 + 1] += t1.z + t1.w;
-                red[P] += lsum;
-            }
-        }
-        __syncthreads();
-    }
+    // ---- this warp's partial gradient (halves a|b added here) ----
     float *dst = p.partial + (size_t)blockIdx.x * (P + 1);
-    for (int q = threadIdx.x; q < P + 1; q += BLOCK) dst[q] = red[q];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) dst[OFF_W2 + (it * 4 + ii) * H + (jt * 8 + jj)] = acc[jj * 4 + ii].x + acc[jj * 4 + ii].y;
+    dst[OFF_W3 + lane * 2 + 0] = g_w30.x + g_w30.y;
+    dst[OFF_W3 + lane * 2 + 1] = g_w31.x + g_w31.y;
+    dst[OFF_B2 + lane] = g_b2.x + g_b2.y;
+    dst[OFF_B1 + lane] = g_b1.x + g_b1.y;
+    dst[OFF_W1 + lane] = g_w10.x + g_w10.y;
+    dst[OFF_W1 + H + lane] = g_w11.x + g_w11.y;
+    if (lane == 0) {
+        dst[OFF_B3 + 0] = g_b30.x + g_b30.y;   // identical in every lane (sums over the staged rows)
+        dst[OFF_B3 + 1] = g_b31.x + g_b31.y;
+        dst[P] = lsum;
+    }
 }
 
 }  // namespace lv32

@@ -45,7 +45,8 @@ struct Variant {
     int approx_tanh = 0;
 };
 
-constexpr int FWD_BLOCK = 128;
+constexpr int FWD_BLOCK = 128;      // small-chain forward kernels
+constexpr int FWD_BLOCK_LV32 = 32;  // packed LV32 forward: one warp (64 trajectories) per CTA -> even spread over the SMs
 constexpr int ADJ_BLOCK_GEMM = 32;   // H=32 adjoint: one warp (64 trajectories) per CTA
 constexpr int ADJ_BLOCK_LANE = 128;  // small-chain adjoint
 

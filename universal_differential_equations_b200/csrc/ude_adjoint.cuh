@@ -247,26 +247,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) ude_adjoint_lane_kernel(AdjParams
     for (int q2 = threadIdx.x; q2 < P + 1; q2 += BLOCK) dst[q2] = red[q2];
 }
 
-// fixed-order reduction of the per-CTA partials: out[q] = sum_b partial[b][q]; q == P1-1 is the loss
+// fixed-order reduction of the per-CTA partials: out[q] = sum_b partial[b][q]; q == P1-1 is the loss.
+// One warp per output entry (8 entries per 256-thread CTA): lane l sums partials l, l+32, ... in order,
+// then a fixed butterfly combines the lanes -> deterministic, and ~1000 partials cost a few microseconds.
 static __global__ void ude_reduce_kernel(const float *__restrict__ partial, int nblocks, int P1, float *__restrict__ grad,
                                          float *__restrict__ loss)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= P1) return;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= nblocks; b += 4) {
-        acc0 += partial[(size_t)(b + 0) * P1 + q];
-        acc1 += partial[(size_t)(b + 1) * P1 + q];
-        acc2 += partial[(size_t)(b + 2) * P1 + q];
-        acc3 += partial[(size_t)(b + 3) * P1 + q];
-    }
-    for (; b < nblocks; ++b) acc0 += partial[(size_t)b * P1 + q];
-    const float v = (acc0 + acc1) + (acc2 + acc3);
-    if (q == P1 - 1) {
-        if (loss) *loss = v;
-    } else {
-        grad[q] = v;
+    float acc = 0.f;
+    for (int b = lane; b < nblocks; b += 32) acc += partial[(size_t)b * P1 + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        if (q == P1 - 1) {
+            if (loss) *loss = acc;
+        } else {
+            grad[q] = acc;
+        }
     }
 }
 

@@ -35,7 +35,7 @@ constexpr int GRAD_LANE = 0;   // every lane keeps all P partial sums in registe
 constexpr int GRAD_WARPGEMM = 1;  // H x H layer via per-warp smem-staged outer-product GEMM
 
 constexpr int MAX_THETA = 8192;  // floats; 32 KB of the 64 KB constant bank
-static __constant__ float c_theta[MAX_THETA];
+static __constant__ __align__(16) float c_theta[MAX_THETA];
 static __constant__ float c_consts[16];
 static __constant__ float c_lossw[16];
 static __constant__ int c_acts[8];

@@ -422,8 +422,12 @@ def sciml_train(loss: Callable, theta0, opt, cb: Optional[Callable] = None, maxi
     forwarded to cb, seir_exposure.jl:144-158).  cb(theta, l, extras...) returning True halts
     (Fisher-KPP-CNN-Small.jl:230).  The callback sees the loss at the pre-update theta of the iteration.
     """
-    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-    th = torch.as_tensor(theta0, dtype=torch.float32).to(dev).clone()
+    if isinstance(theta0, torch.Tensor):   # keep the caller's dtype and device (e.g. a float64 host replay)
+        th = theta0.detach().clone()
+        dev = th.device
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        th = torch.as_tensor(theta0, dtype=torch.float32).to(dev).clone()
     best, best_th, it = float("inf"), th.clone(), 0
     if isinstance(opt, ADAM):
         m = torch.zeros_like(th)
@@ -456,7 +460,7 @@ def sciml_train(loss: Callable, theta0, opt, cb: Optional[Callable] = None, maxi
                 gd = float(g.double() @ d)
             a, ok = 1.0, False
             for _ in range(30):
-                th_new = (th.double() + a * d).float()
+                th_new = (th.double() + a * d).to(th.dtype)
                 l_new, g_new, extra_new = _loss_and_grad(loss, th_new)
                 if math.isfinite(l_new) and l_new <= l + 1e-4 * a * gd:
                     ok = True
