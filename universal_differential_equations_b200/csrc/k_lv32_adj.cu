@@ -1,10 +1,13 @@
 // k_lv32_adj.cu -- interpolating-adjoint kernels of the LV 2 -> 32 -> 32 -> 2 tanh UDE (BASELINE config 2).
 #include "lv32_packed.cuh"
 #include "ude_adjoint.cuh"
+#include "lv32_tc.cuh"
 
 namespace b200ude {
 
-int adj_grid_lv32(int N) { return ((N + 1) / 2 + ADJ_BLOCK_GEMM - 1) / ADJ_BLOCK_GEMM; }
+// rows of the per-warp partial-gradient buffer: enough for either variant (packed: one row per 64 trajectories,
+// tensor-core: one row per 32)
+int adj_grid_lv32(int N) { return ((N + 127) / 128) * 4; }
 
 template <int TM, class W>
 static cudaError_t launch_one(const AdjParams &p, int grid, cudaStream_t st)
@@ -23,11 +26,31 @@ static cudaError_t launch_one(const AdjParams &p, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
+template <int TM>
+static cudaError_t launch_tc(const AdjParams &p, int *rows_out, cudaStream_t st)
+{
+    auto kern = lv32::tc::adjoint_kernel<TM, 128, 4>;
+    constexpr size_t smem = sizeof(lv32::tc::WarpStageT) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int grid = (p.N + 127) / 128;
+    *rows_out = grid * 4;
+    kern<<<grid, 128, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_adj_lv32(const Variant &v, const ConstTables &t, const AdjParams &p, cudaStream_t st, int *grid_out)
 {
     cudaError_t e = upload_tables(t, st);
     if (e != cudaSuccess) return e;
-    const int grid = adj_grid_lv32(p.N);
+    if (v.adj_tc) return v.approx_tanh ? launch_tc<1>(p, grid_out, st) : launch_tc<0>(p, grid_out, st);
+    const int grid = ((p.N + 1) / 2 + ADJ_BLOCK_GEMM - 1) / ADJ_BLOCK_GEMM;
     *grid_out = grid;
     if (v.approx_tanh) return launch_one<1, WConst>(p, grid, st);
     return launch_one<0, WConst>(p, grid, st);

@@ -1,5 +1,6 @@
 // k_lv32_fwd.cu -- forward-solve kernels of the LV 2 -> 32 -> 32 -> 2 tanh UDE (BASELINE config 2).
 #include "lv32_packed.cuh"
+#include "lv32_tc.cuh"
 
 namespace b200ude {
 
@@ -14,10 +15,20 @@ static cudaError_t launch_one(const FwdParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
+template <int TM>
+static cudaError_t launch_tc(const FwdParams &p, cudaStream_t st)
+{
+    auto kern = lv32::tc::forward_kernel<TM, 128, 4>;
+    const int grid = (p.N + 127) / 128;
+    kern<<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fwd_lv32(const Variant &v, const ConstTables &t, const FwdParams &p, cudaStream_t st)
 {
     cudaError_t e = upload_tables(t, st);
     if (e != cudaSuccess) return e;
+    if (v.fwd_tc) return v.approx_tanh ? launch_tc<1>(p, st) : launch_tc<0>(p, st);
     if (v.approx_tanh) return launch_one<1, WConst>(p, st);
     if (v.fwd_smem) return launch_one<0, WSmem>(p, st);
     return launch_one<0, WConst>(p, st);

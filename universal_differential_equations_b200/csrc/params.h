@@ -43,6 +43,8 @@ struct Variant {
     int fwd_T = 1;       // trajectories per thread in the forward kernel
     int adj_smem = 0;
     int approx_tanh = 0;
+    int fwd_tc = 0;      // 1: tcgen05 (3xTF32) forward kernel
+    int adj_tc = 0;      // 1: tcgen05 (3xTF32) adjoint kernel
 };
 
 constexpr int FWD_BLOCK = 128;      // small-chain forward kernels
