@@ -261,7 +261,7 @@ def main():
     adj_ms = float(np.mean(t_adj))
     fwd_ms = float(np.mean(t_fwd))
     roofline = {
-        "kernel": "lv32::adjoint_kernel (+ the 3 us fixed-order reduce; events bracket both)",
+        "kernel": "lv32::tc::adjoint_kernel (+ the ~5 us fixed-order reduce; events bracket both)",
         "bound": "hbm", "achieved": n * BYTES_ADJ / (adj_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": n * BYTES_ADJ / (adj_ms * 1e-3) / 1e9 / hbm_peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
@@ -295,7 +295,7 @@ def main():
                    "timing": "CUDA events per step on the launch stream, summed over steps, max over ranks"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "b200ude_loss_gradient_host: pinned host theta/u0/data -> H2D -> kernels -> D2H grad+loss, wall clock"},
-        "gpu_launches": 3 * a.steps, "kernels_per_step": ["lv32::forward_kernel", "lv32::adjoint_kernel", "ude_reduce_kernel"],
+        "gpu_launches": 3 * a.steps, "kernels_per_step": ["lv32::tc::forward_kernel", "lv32::tc::adjoint_kernel", "ude_reduce_kernel"],
         "clocks": clocks, "roofline": roofline, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu,
         "kernel_ms": {"forward": fwd_ms, "adjoint_plus_reduce": adj_ms, "step": float(np.mean(t_step))},
     }

@@ -220,8 +220,9 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->var.fwd_smem = env_int("B200UDE_FWD_SMEM", 0);
     h->var.fwd_T = env_int("B200UDE_FWD_T", 1) == 2 ? 2 : 1;
     h->var.adj_smem = env_int("B200UDE_ADJ_SMEM", 0);
-    h->var.fwd_tc = env_int("B200UDE_FWD_TC", 0);
-    h->var.adj_tc = env_int("B200UDE_ADJ_TC", 0);
+    // default: tcgen05 (3xTF32) kernels; B200UDE_FWD_TC=0 / B200UDE_ADJ_TC=0 select the FFMA2-packed CUDA-core kernels
+    h->var.fwd_tc = env_int("B200UDE_FWD_TC", 1);
+    h->var.adj_tc = env_int("B200UDE_ADJ_TC", 1);
 
     const size_t N = h->cap, D = (size_t)h->D;
     h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : adj_grid_lv5((int)N));
