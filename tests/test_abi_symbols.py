@@ -68,7 +68,7 @@ def test_no_silent_cpu_fallback(libpath):
     rc = L.b200ude_create(C.byref(d), C.byref(h))
     assert rc == _lib.ENODEVICE and not h.value
     # unsupported chain shape is reported as such even before the device is probed
-    d.widths[1] = 7
+    d.widths[1] = 65   # wider than any kernel family supports
     assert L.b200ude_create(C.byref(d), C.byref(h)) == _lib.EUNSUPPORTED
     # usage errors
     d.widths[1] = 32

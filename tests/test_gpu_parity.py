@@ -199,7 +199,7 @@ def test_error_behaviour():
     with pytest.raises(B200UDEError) as e:
         solver.forward(torch.zeros(2, 65, device="cuda"))
     assert e.value.code == EINVAL
-    chain = ude.FastChain(ude.FastDense(2, 7, ude.tanh), ude.FastDense(7, 2))
+    chain = ude.FastChain(ude.FastDense(2, 65, ude.tanh), ude.FastDense(65, 2))   # wider than any kernel supports
     with pytest.raises(B200UDEError) as e:
         ude.UDESolver(ude.LotkaVolterraUDE(chain), 0.0, 0.1, 30, 1, max_trajectories=8)
     assert e.value.code == EUNSUPPORTED
@@ -226,4 +226,63 @@ def test_full_size_properties():
     assert np.array_equal(out_p, out[:, :, perm]) and np.array_equal(gu_p, gu[:, perm])
     assert abs(loss_p - loss) <= 1e-5 * abs(loss)
     assert np.linalg.norm(g_p - g) <= 1e-4 * np.linalg.norm(g)
+    solver.close()
+
+
+def test_generic_lv_chain_vs_oracle(O):
+    """A chain shape with no specialised kernel (2-16-16-2, tanh/rbf, one trainable rate) runs on the generic
+    kernels and matches the oracle."""
+    ude = _ude()
+    rng = np.random.default_rng(5)
+    N = 150
+    chain = ude.FastChain(ude.FastDense(2, 16, ude.tanh), ude.FastDense(16, 16, ude.rbf), ude.FastDense(16, 2))
+    f = ude.LotkaVolterraUDE(chain, trainable_rates=1)
+    P = f.num_params()
+    theta = (0.4 * rng.standard_normal(P)).astype(np.float32)
+    theta[0] = 1.7
+    u0, y = synthetic_ensemble(N, n_steps=20, dt=0.1)
+    solver = ude.UDESolver(f, 0.0, 0.1, 20, 1, max_trajectories=N)
+    out, loss, gth, gu, status = _run(solver, theta, u0, y)
+    m = O.lv_model((2, 16, 16, 2), ("tanh", "rbf", "identity"), n_prefix=1)
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.1, 20, want_out=True)
+    assert (status == 0).all()
+    assert np.all(np.abs(out - out64) <= 3e-4 * (1 + np.abs(out64)))
+    assert abs(loss - l64) <= 1e-4 * abs(l64)
+    assert np.linalg.norm(gth - g64) <= 2e-3 * np.linalg.norm(g64)
+    assert np.abs(gu - gu64).max() <= 2e-3 * np.abs(gu64).max()
+    # deterministic reduction: bitwise identical on a second run
+    out2, loss2, gth2, gu2, _ = _run(solver, theta, u0, y)
+    assert np.array_equal(gth, gth2) and loss == loss2
+    solver.close()
+
+
+def test_seir_exposure_ude_vs_oracle(O):
+    """SEIR exposure UDE (7 states, chain 3-64-64-1 tanh on [S/N, I, D/N], seir_exposure.jl:114-130), Tsit5
+    dt = 0.25 over (0, 21), saved daily, loss on rows E, I, R (seir_exposure.jl:146).  fp32 state with
+    S, N ~ 1.4e7: per-component relative tolerances; adjoint parity for this model is oracle-only (unpinned)."""
+    ude = _ude()
+    rng = np.random.default_rng(9)
+    N = 96
+    chain = ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1))
+    f = ude.SEIRExposureUDE(chain)
+    theta = glorot_theta((3, 64, 64, 1), seed=2)
+    S0 = 14e6
+    u0 = np.zeros((7, N), np.float32)
+    u0[0] = 0.9 * S0 * rng.uniform(0.9, 1.0, N)
+    u0[1] = rng.uniform(0, 50, N); u0[2] = rng.uniform(0, 50, N); u0[3] = rng.uniform(0, 50, N)
+    u0[4] = S0; u0[5] = rng.uniform(0, 10, N); u0[6] = rng.uniform(0, 100, N)
+    n_steps, dt, every = 84, 0.25, 4
+    m = O.seir_model()
+    w = np.array([0, 1, 1, 1, 0, 0, 0], np.float64)
+    # targets: the oracle's own solution for a perturbed theta (keeps residuals O(1))
+    th2 = theta.astype(np.float64) * 1.05
+    y = np.stack([O.solve_fixed(m, th2, u0[:, k].astype(np.float64), dt, n_steps, save_every=every) for k in range(N)], axis=2).astype(np.float32)
+    solver = ude.UDESolver(f, 0.0, dt, n_steps, every, max_trajectories=N, loss_weights=w)
+    out, loss, gth, gu, status = _run(solver, theta, u0, y)
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, w, dt, n_steps, save_every=every, want_out=True)
+    assert (status == 0).all() and out.shape == (22, 7, N)
+    scale = np.abs(out64).max(axis=(0, 2), keepdims=True)
+    assert np.all(np.abs(out - out64) <= 2e-5 * scale + 1e-3)
+    assert abs(loss - l64) <= 2e-3 * abs(l64)
+    assert np.linalg.norm(gth - g64) <= 1e-2 * np.linalg.norm(g64)
     solver.close()

@@ -26,7 +26,9 @@ thread_local std::string g_create_error;
 //   K_LV32   LV 2 -> 32 -> 32 -> 2 tanh                      BASELINE config 2
 //   K_LV5Px  LV 2 -> 5 -> 5 -> 5 -> 2, per-layer activations, x trainable linear rates
 //            scenario_1.jl:62-73 (x=0), scenario_2.jl:79-98 (x=1), hudson_bay.jl:77-91 (x=2)
-enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2 };
+//   K_GENERIC  any LV / SEIR / NODE form with chain widths <= 64 and <= 5 layers (k_generic.cu): functional
+//            coverage (seir_exposure.jl:114-130 shapes), not tuned
+enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2, K_GENERIC };
 
 int kernel_num_params(KernelId k)
 {
@@ -48,6 +50,7 @@ struct b200ude_handle {
     KernelId kid = K_NONE;
     Variant var;
     ConstTables tab;
+    GenericShape gen;
     int P = 0, n_save = 0, D = 0;
     size_t cap = 0;  // max trajectories
     size_t N = 0;    // trajectories of the last forward
@@ -65,6 +68,8 @@ struct b200ude_handle {
     int32_t *d_status = nullptr;
     float *h_loss = nullptr;  // pinned
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host-buffer path: the data upload overlaps the forward kernel
+    cudaEvent_t data_ready = nullptr;
     size_t dev_bytes = 0;
     std::string err;
 };
@@ -99,20 +104,33 @@ cudaError_t dalloc(b200ude_handle *h, T **p, size_t count)
     return e;
 }
 
+bool generic_ok(const b200ude_desc &d)
+{
+    if (d.n_layers < 1 || d.n_layers > 5) return false;
+    for (int l = 0; l <= d.n_layers; ++l)
+        if (d.widths[l] < 1 || d.widths[l] > 64) return false;
+    for (int l = 0; l < d.n_layers; ++l)
+        if (d.acts[l] < 0 || d.acts[l] > 2) return false;
+    const int din = d.widths[0], dout = d.widths[d.n_layers];
+    if (d.model == B200UDE_MODEL_LV) return d.state_dim == 2 && din == 2 && dout == 2 && d.n_prefix >= 0 && d.n_prefix <= 2 && d.n_consts >= 2;
+    if (d.model == B200UDE_MODEL_SEIR) return d.state_dim == 7 && din == 3 && dout == 1 && d.n_prefix == 0 && d.n_consts >= 9;
+    if (d.model == B200UDE_MODEL_NODE) return d.state_dim >= 1 && d.state_dim <= 8 && din == d.state_dim && dout == d.state_dim && d.n_prefix == 0;
+    return false;
+}
+
 KernelId pick_kernel(const b200ude_desc &d)
 {
-    if (d.model != B200UDE_MODEL_LV || d.state_dim != 2) return K_NONE;
-    if (d.acts[d.n_layers - 1] != B200UDE_ACT_IDENTITY) return K_NONE;
-    if (d.n_layers == 3 && d.widths[0] == 2 && d.widths[1] == 32 && d.widths[2] == 32 && d.widths[3] == 2 &&
-        d.acts[0] == B200UDE_ACT_TANH && d.acts[1] == B200UDE_ACT_TANH && d.n_prefix == 0)
-        return K_LV32;
-    if (d.n_layers == 4 && d.widths[0] == 2 && d.widths[1] == 5 && d.widths[2] == 5 && d.widths[3] == 5 &&
-        d.widths[4] == 2) {
-        if (d.n_prefix == 0) return K_LV5P0;
-        if (d.n_prefix == 1) return K_LV5P1;
-        if (d.n_prefix == 2) return K_LV5P2;
+    if (d.model == B200UDE_MODEL_LV && d.state_dim == 2 && d.acts[d.n_layers - 1] == B200UDE_ACT_IDENTITY) {
+        if (d.n_layers == 3 && d.widths[0] == 2 && d.widths[1] == 32 && d.widths[2] == 32 && d.widths[3] == 2 &&
+            d.acts[0] == B200UDE_ACT_TANH && d.acts[1] == B200UDE_ACT_TANH && d.n_prefix == 0)
+            return K_LV32;
+        if (d.n_layers == 4 && d.widths[0] == 2 && d.widths[1] == 5 && d.widths[2] == 5 && d.widths[3] == 5 && d.widths[4] == 2) {
+            if (d.n_prefix == 0) return K_LV5P0;
+            if (d.n_prefix == 1) return K_LV5P1;
+            if (d.n_prefix == 2) return K_LV5P2;
+        }
     }
-    return K_NONE;
+    return generic_ok(d) ? K_GENERIC : K_NONE;
 }
 
 int env_int(const char *name, int dflt)
@@ -135,6 +153,7 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
     case K_LV5P0: e = launch_fwd_lv5(0, h->var, h->tab, p, st); break;
     case K_LV5P1: e = launch_fwd_lv5(1, h->var, h->tab, p, st); break;
     case K_LV5P2: e = launch_fwd_lv5(2, h->var, h->tab, p, st); break;
+    case K_GENERIC: e = launch_fwd_generic(h->gen, h->tab, p, st); break;
     default: return fail(h, B200UDE_EUNSUPPORTED, "forward: no kernel");
     }
     CUDA_TRY(h, e);
@@ -160,6 +179,7 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     case K_LV5P0: e = launch_adj_lv5(0, h->var, h->tab, p, st, &grid); break;
     case K_LV5P1: e = launch_adj_lv5(1, h->var, h->tab, p, st, &grid); break;
     case K_LV5P2: e = launch_adj_lv5(2, h->var, h->tab, p, st, &grid); break;
+    case K_GENERIC: e = launch_adj_generic(h->gen, h->tab, p, st, &grid); break;
     default: return fail(h, B200UDE_EUNSUPPORTED, "adjoint: no kernel");
     }
     CUDA_TRY(h, e);
@@ -183,7 +203,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     if (d->struct_size != sizeof(b200ude_desc))
         return fail(nullptr, B200UDE_EINVAL, "create: struct_size %u != %zu (ABI mismatch)", d->struct_size, sizeof(b200ude_desc));
     if (d->dtype != B200UDE_F32) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only B200UDE_F32 kernels exist in this build");
-    if (d->n_layers < 2 || d->n_layers > B200UDE_MAX_LAYERS) return fail(nullptr, B200UDE_EINVAL, "create: n_layers=%d out of range", d->n_layers);
+    if (d->n_layers < 1 || d->n_layers > B200UDE_MAX_LAYERS) return fail(nullptr, B200UDE_EINVAL, "create: n_layers=%d out of range", d->n_layers);
     if (d->solver != B200UDE_TSIT5) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only Tsit5 has a kernel in this build");
     if (d->sensealg != B200UDE_INTERPOLATING_ADJOINT) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: unknown sensealg %d", d->sensealg);
     if (!(d->dt > 0) || d->n_steps < 1 || d->save_every < 1 || d->n_steps % d->save_every != 0)
@@ -193,7 +213,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     const KernelId kid = pick_kernel(*d);
     if (kid == K_NONE)
         return fail(nullptr, B200UDE_EUNSUPPORTED,
-                    "create: no sm_100a kernel for this model/chain (built: LV 2-32-32-2 tanh; LV 2-5-5-5-2 with 0/1/2 trainable rates)");
+                    "create: no sm_100a kernel for this model/chain (built: LV 2-32-32-2 tanh; LV 2-5-5-5-2; generic LV/SEIR/NODE chains with widths <= 64, <= 5 layers)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail(nullptr, B200UDE_ENODEVICE, "create: no CUDA device (%s)", cudaGetErrorString(e));
@@ -215,6 +235,16 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->cap = (size_t)d->max_trajectories;
     h->sm_count = prop.multiProcessorCount;
     h->P = kernel_num_params(kid);
+    if (kid == K_GENERIC) {
+        int P = d->n_prefix;
+        for (int l = 0; l < d->n_layers; ++l) P += d->widths[l] * d->widths[l + 1] + d->widths[l + 1];
+        h->P = P;
+        h->gen.serial = g_serial + 1;   // same serial as the tables set below
+        h->gen.model = d->model; h->gen.D = d->state_dim; h->gen.din = d->widths[0]; h->gen.dout = d->widths[d->n_layers];
+        h->gen.n_layers = d->n_layers; h->gen.n_prefix = d->n_prefix; h->gen.P = P;
+        for (int l = 0; l < 8; ++l) { h->gen.widths[l] = l <= d->n_layers ? d->widths[l] : 0; h->gen.acts[l] = l < d->n_layers ? d->acts[l] : 0; }
+        if (P > 8192) { delete h; return fail(nullptr, B200UDE_EUNSUPPORTED, "create: %d parameters exceed the constant-bank budget", P); }
+    }
     h->var.approx_tanh = (d->flags & B200UDE_FLAG_APPROX_TANH) ? 1 : 0;
     // tuning knobs for experiments (defaults are the measured-best variant)
     h->var.fwd_smem = env_int("B200UDE_FWD_SMEM", 0);
@@ -225,7 +255,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->var.adj_tc = env_int("B200UDE_ADJ_TC", 1);
 
     const size_t N = h->cap, D = (size_t)h->D;
-    h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : adj_grid_lv5((int)N));
+    h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : kid == K_GENERIC ? adj_rows_generic((int)N) : adj_grid_lv5((int)N));
     bool ok = true;
     ok = ok && dalloc(h, &h->d_theta, (size_t)((h->P + 3) / 4) * 4) == cudaSuccess;
     ok = ok && dalloc(h, &h->d_ustep, (size_t)(d->n_steps + 1) * D * N) == cudaSuccess;
@@ -241,6 +271,8 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     }
     cudaMemset(h->d_theta, 0, sizeof(float) * ((h->P + 3) / 4) * 4);
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->data_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void **)&h->h_loss, sizeof(float)) != cudaSuccess) {
         g_create_error = "create: stream / pinned allocation failed";
         b200ude_destroy(h);
@@ -266,6 +298,8 @@ void b200ude_destroy(b200ude_handle *h)
     cudaFree(h->d_loss); cudaFree(h->d_status);
     if (h->h_loss) cudaFreeHost(h->h_loss);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->data_ready) cudaEventDestroy(h->data_ready);
     delete h;
 }
 
@@ -352,9 +386,13 @@ int32_t b200ude_loss_gradient_host(b200ude_handle *h, const void *theta, const v
     rc = b200ude_set_params(h, theta, (size_t)h->P, B200UDE_HOST, st);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(h->d_u0, u0, sizeof(float) * D * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_data, data, sizeof(float) * (size_t)h->n_save * D * N, cudaMemcpyHostToDevice, st));
+    // the data (n_save x larger than u0) is only needed by the adjoint: upload it on a second stream while
+    // the forward kernel runs (pinned host memory makes the two overlap)
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_data, data, sizeof(float) * (size_t)h->n_save * D * N, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(h, cudaEventRecord(h->data_ready, h->copy_stream));
     rc = do_forward(h, h->d_u0, N, h->d_out, nullptr, st);
     if (rc) return rc;
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->data_ready, 0));
     rc = do_adjoint(h, true, h->d_data, h->d_loss, h->d_grad, grad_u0 ? h->d_gu0 : nullptr, st);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(grad_theta, h->d_grad, sizeof(float) * (size_t)h->P, cudaMemcpyDeviceToHost, st));

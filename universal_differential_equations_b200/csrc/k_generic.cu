@@ -1,0 +1,54 @@
+// k_generic.cu -- shape-generic UDE kernels (runtime chain widths / activations; LV, SEIR, NODE forms).
+#include "ude_generic.cuh"
+
+namespace b200ude {
+
+constexpr int GEN_BLOCK = 128;
+
+int adj_rows_generic(int N) { return ((N + GEN_BLOCK - 1) / GEN_BLOCK) * (GEN_BLOCK / 32); }
+
+static cudaError_t upload_gen(const GenericShape &g, cudaStream_t st)
+{
+    static uint64_t last_serial = 0;
+    if (last_serial == g.serial) return cudaSuccess;
+    generic::GenDesc d;
+    d.model = g.model; d.D = g.D; d.din = g.din; d.dout = g.dout; d.n_layers = g.n_layers; d.n_prefix = g.n_prefix; d.P = g.P;
+    int off = g.n_prefix;
+    for (int l = 0; l <= generic::MAXL; ++l) d.widths[l] = l <= g.n_layers ? g.widths[l] : 0;
+    for (int l = 0; l < generic::MAXL; ++l) {
+        d.acts[l] = l < g.n_layers ? g.acts[l] : 0;
+        d.woff[l] = off;
+        if (l < g.n_layers) off += g.widths[l] * g.widths[l + 1] + g.widths[l + 1];
+    }
+    cudaError_t e = cudaMemcpyToSymbolAsync(generic::c_gen, &d, sizeof(d), 0, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) last_serial = g.serial;
+    return e;
+}
+
+cudaError_t launch_fwd_generic(const GenericShape &g, const ConstTables &t, const FwdParams &p, cudaStream_t st)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    e = upload_gen(g, st);
+    if (e != cudaSuccess) return e;
+    generic::forward_kernel<GEN_BLOCK><<<(p.N + GEN_BLOCK - 1) / GEN_BLOCK, GEN_BLOCK, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adj_generic(const GenericShape &g, const ConstTables &t, const AdjParams &p, cudaStream_t st, int *rows_out)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    e = upload_gen(g, st);
+    if (e != cudaSuccess) return e;
+    auto kern = generic::adjoint_kernel<GEN_BLOCK>;
+    const size_t smem = sizeof(float) * (size_t)(GEN_BLOCK / 32) * (g.P + 1);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (p.N + GEN_BLOCK - 1) / GEN_BLOCK;
+    *rows_out = grid * (GEN_BLOCK / 32);
+    kern<<<grid, GEN_BLOCK, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace b200ude

@@ -52,6 +52,14 @@ constexpr int FWD_BLOCK_LV32 = 32;  // packed LV32 forward: one warp (64 traject
 constexpr int ADJ_BLOCK_GEMM = 32;   // H=32 adjoint: one warp (64 trajectories) per CTA
 constexpr int ADJ_BLOCK_LANE = 128;  // small-chain adjoint
 
+// runtime shape of a UDE handled by the generic kernels (k_generic.cu)
+struct GenericShape {
+    uint64_t serial;
+    int model, D, din, dout, n_layers, n_prefix, P;
+    int widths[8];
+    int acts[8];
+};
+
 // launchers (one translation unit per kernel family; each owns its constant-bank symbols)
 cudaError_t launch_fwd_lv32(const Variant &, const ConstTables &, const FwdParams &, cudaStream_t);
 cudaError_t launch_adj_lv32(const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *grid_out);
@@ -59,6 +67,9 @@ cudaError_t launch_fwd_lv5(int n_prefix, const Variant &, const ConstTables &, c
 cudaError_t launch_adj_lv5(int n_prefix, const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *grid_out);
 int adj_grid_lv32(int N);
 int adj_grid_lv5(int N);
+cudaError_t launch_fwd_generic(const GenericShape &, const ConstTables &, const FwdParams &, cudaStream_t);
+cudaError_t launch_adj_generic(const GenericShape &, const ConstTables &, const AdjParams &, cudaStream_t, int *rows_out);
+int adj_rows_generic(int N);
 cudaError_t launch_reduce(const float *partial, int nblocks, int P1, float *grad, float *loss, cudaStream_t);
 
 }  // namespace b200ude

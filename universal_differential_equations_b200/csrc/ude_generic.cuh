@@ -1,0 +1,285 @@
+// ude_generic.cuh -- shape-generic (runtime widths / activations) UDE kernels.
+//
+// Functional coverage for every recognised UDE form whose chain has no specialised kernel: any dense chain
+// with widths <= 64 and <= 5 layers, models LV (0/1/2 trainable rates), SEIR (7 states, chain on
+// [S/N, I, D/N], SEIR_exposure/seir_exposure.jl:117-130) and NODE.  One trajectory per thread, weights read
+// from the constant bank with runtime indices, activations in per-thread local arrays, Tsit5 forward with
+// dense output and the interpolating adjoint exactly as in the specialised kernels.  The ensemble-summed
+// parameter gradient is reduced deterministically: every contribution is summed over the warp's lanes with a
+// fixed shuffle tree and added by lane 0 into a per-warp shared-memory vector.  Correctness first: these
+// kernels are ~10-30x slower per FLOP than lv32::tc and are reported as such.
+#pragma once
+#include "ude_adjoint.cuh"
+
+namespace b200ude {
+namespace generic {
+
+constexpr int MAXW = 64;   // max layer width
+constexpr int MAXL = 5;    // max dense layers
+constexpr int MAXD = 8;    // max state dimension / chain input / chain output
+
+struct GenDesc {
+    int model, D, din, dout, n_layers, n_prefix, P;
+    int widths[MAXL + 1];
+    int acts[MAXL];
+    int woff[MAXL];   // offset of layer l's W in theta (column-major, out x in), its bias follows at woff + in*out
+};
+static __constant__ GenDesc c_gen;
+
+__device__ __forceinline__ float act_rt(int k, float a)
+{
+    return k == ACT_TANH ? tanh_dev<0>(a) : (k == ACT_RBF ? rbf_dev(a) : a);
+}
+__device__ __forceinline__ float actder_rt(int k, float a, float h)
+{
+    return k == ACT_TANH ? fmaf(-h, h, 1.0f) : (k == ACT_RBF ? -2.0f * a * h : 1.0f);
+}
+
+// chain forward; when KEEP, stores every layer's output (hs[l+1]) and pre-activation (pre[l])
+template <bool KEEP>
+__device__ __noinline__ void chain_fwd(const float *x, float *y, float (*hs)[MAXW], float (*pre)[MAXW])
+{
+    float cur[MAXW], nxt[MAXW];
+    const int L = c_gen.n_layers;
+    for (int i = 0; i < c_gen.widths[0]; ++i) {
+        cur[i] = x[i];
+        if (KEEP) hs[0][i] = x[i];
+    }
+    for (int l = 0; l < L; ++l) {
+        const int nin = c_gen.widths[l], nout = c_gen.widths[l + 1], wo = c_gen.woff[l], act = c_gen.acts[l];
+        for (int j = 0; j < nout; ++j) {
+            float a = c_theta[wo + nin * nout + j];
+            for (int i = 0; i < nin; ++i) a = fmaf(c_theta[wo + i * nout + j], cur[i], a);
+            const float h = act_rt(act, a);
+            nxt[j] = h;
+            if (KEEP) { pre[l][j] = a; hs[l + 1][j] = h; }
+        }
+        for (int j = 0; j < nout; ++j) cur[j] = nxt[j];
+    }
+    for (int j = 0; j < c_gen.widths[L]; ++j) y[j] = cur[j];
+}
+
+__device__ __forceinline__ void model_inputs(const float *u, float *x)
+{
+    if (c_gen.model == MODEL_SEIR) {
+        const float invN = 1.0f / u[4];
+        x[0] = u[0] * invN; x[1] = u[2]; x[2] = u[5] * invN;
+    } else {
+        for (int i = 0; i < c_gen.din; ++i) x[i] = u[i];
+    }
+}
+
+__device__ __forceinline__ void model_rhs(const float *u, float *du)
+{
+    float x[MAXD], y[MAXD];
+    model_inputs(u, x);
+    chain_fwd<false>(x, y, nullptr, nullptr);
+    if (c_gen.model == MODEL_LV) {
+        float a1 = c_consts[0], a2 = c_consts[1];
+        if (c_gen.n_prefix == 1) a2 = c_theta[0];
+        if (c_gen.n_prefix == 2) { a1 = c_theta[0]; a2 = c_theta[1]; }
+        du[0] = fmaf(a1, u[0], y[0]);
+        du[1] = fmaf(-a2, u[1], y[1]);
+    } else if (c_gen.model == MODEL_SEIR) {
+        // seir_exposure.jl:117-130; consts = F, beta0, alpha, kappa, mu, sigma, gamma, d, lambda (:33)
+        const float F = c_consts[0], b0 = c_consts[1], mu = c_consts[4], sg = c_consts[5], gm = c_consts[6], dd = c_consts[7], lm = c_consts[8];
+        const float S = u[0], E = u[1], I = u[2], R = u[3], N = u[4], Dd = u[5];
+        const float inf = b0 * S * F / N, z = y[0];
+        du[0] = -inf - z - mu * S;
+        du[1] = inf + z - (sg + mu) * E;
+        du[2] = sg * E - (gm + mu) * I;
+        du[3] = gm * I - mu * R;
+        du[4] = -mu * N;
+        du[5] = dd * gm * I - lm * Dd;
+        du[6] = sg * E;
+    } else {
+        for (int k = 0; k < c_gen.D; ++k) du[k] = y[k];
+    }
+}
+
+struct GenFwdParams {
+    FwdParams f;
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) forward_kernel(FwdParams p)
+{
+    const int D = c_gen.D;
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    if (gid >= p.N) return;
+    const size_t n = (size_t)gid;
+    const float dt = p.dt;
+    float u[MAXD], g[MAXD], k[7][MAXD];
+    for (int c = 0; c < D; ++c) u[c] = __ldg(p.u0 + (size_t)c * N + n);
+    auto store = [&](float *base, int row, const float *v) {
+        for (int c = 0; c < D; ++c) base[((size_t)row * D + c) * N + n] = v[c];
+    };
+    store(p.out, 0, u);
+    store(p.ustep, 0, u);
+    model_rhs(u, k[0]);
+    store(p.dense, 0, k[0]);
+    int isave = 1;
+    for (int s = 0; s < p.n_steps; ++s) {
+#pragma unroll
+        for (int i = 1; i < 7; ++i) {
+            for (int c = 0; c < D; ++c) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                    if (Tsit5::a(i, j) != 0.0) acc = fmaf((float)Tsit5::a(i, j), k[j][c], acc);
+                g[c] = fmaf(dt, acc, u[c]);
+            }
+            if (i == 6) for (int c = 0; c < D; ++c) u[c] = g[c];
+            model_rhs(g, k[i]);
+            store(p.dense, s * 6 + i, k[i]);
+        }
+        store(p.ustep, s + 1, u);
+        if ((s + 1) % p.save_every == 0) { store(p.out, isave, u); ++isave; }
+        for (int c = 0; c < D; ++c) k[0][c] = k[6][c];
+    }
+    if (p.status) {
+        bool ok = true;
+        for (int c = 0; c < D; ++c) ok = ok && (fabsf(u[c]) <= 3.0e38f);
+        p.status[n] = ok ? 0 : 1;
+    }
+}
+
+// sum v over the warp's lanes with a fixed tree and add it into this warp's shared gradient vector
+__device__ __forceinline__ void warp_acc(float *gw, int idx, float v, int lane)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) gw[idx] += v;
+}
+
+// kl = (df/du)^T g ; this warp's gradient vector += sc * (df/dtheta)^T g   (all lanes of the warp participate)
+__device__ __noinline__ void model_vjp(const float *u, const float *g, float sc, float lv, float *kl, float *gw, int lane)
+{
+    float x[MAXD], y[MAXD], dy[MAXD], dx[MAXD];
+    float hs[MAXL + 1][MAXW], pre[MAXL][MAXW];
+    model_inputs(u, x);
+    chain_fwd<true>(x, y, hs, pre);
+    const int L = c_gen.n_layers;
+    const float w = sc * lv;   // quadrature weight, zero for padding lanes
+    if (c_gen.model == MODEL_SEIR) dy[0] = g[1] - g[0];   // z enters dS with -, dE with +
+    else for (int m = 0; m < c_gen.dout; ++m) dy[m] = g[m];
+    // reverse sweep
+    float q[MAXW], qn[MAXW];
+    for (int j = 0; j < c_gen.widths[L]; ++j) q[j] = dy[j];
+    for (int l = L - 1; l >= 0; --l) {
+        const int nin = c_gen.widths[l], nout = c_gen.widths[l + 1], wo = c_gen.woff[l], act = c_gen.acts[l];
+        for (int j = 0; j < nout; ++j) q[j] *= actder_rt(act, pre[l][j], hs[l + 1][j]);
+        for (int i = 0; i < nin; ++i) {
+            float sacc = 0.0f;
+            const float hi = hs[l][i];
+            for (int j = 0; j < nout; ++j) {
+                sacc = fmaf(c_theta[wo + i * nout + j], q[j], sacc);
+                warp_acc(gw, wo + i * nout + j, w * q[j] * hi, lane);
+            }
+            qn[i] = sacc;
+        }
+        for (int j = 0; j < nout; ++j) warp_acc(gw, wo + nin * nout + j, w * q[j], lane);
+        for (int i = 0; i < nin; ++i) q[i] = qn[i];
+    }
+    for (int i = 0; i < c_gen.din; ++i) dx[i] = q[i];
+    if (c_gen.model == MODEL_LV) {
+        float a1 = c_consts[0], a2 = c_consts[1];
+        if (c_gen.n_prefix == 1) a2 = c_theta[0];
+        if (c_gen.n_prefix == 2) { a1 = c_theta[0]; a2 = c_theta[1]; }
+        kl[0] = fmaf(a1, g[0], dx[0]);
+        kl[1] = fmaf(-a2, g[1], dx[1]);
+        if (c_gen.n_prefix == 1) warp_acc(gw, 0, w * (-u[1] * g[1]), lane);
+        if (c_gen.n_prefix == 2) {
+            warp_acc(gw, 0, w * (u[0] * g[0]), lane);
+            warp_acc(gw, 1, w * (-u[1] * g[1]), lane);
+        }
+    } else if (c_gen.model == MODEL_SEIR) {
+        const float F = c_consts[0], b0 = c_consts[1], mu = c_consts[4], sg = c_consts[5], gm = c_consts[6], dd = c_consts[7], lm = c_consts[8];
+        const float S = u[0], N = u[4], Dd = u[5];
+        const float cS = b0 * F / N, cN = -b0 * S * F / (N * N);
+        kl[0] = g[0] * (-cS - mu) + g[1] * cS + dx[0] / N;
+        kl[1] = g[1] * (-(sg + mu)) + g[2] * sg + g[6] * sg;
+        kl[2] = g[2] * (-(gm + mu)) + g[3] * gm + g[5] * dd * gm + dx[1];
+        kl[3] = g[3] * (-mu);
+        kl[4] = g[0] * (-cN) + g[1] * cN + g[4] * (-mu) - dx[0] * S / (N * N) - dx[2] * Dd / (N * N);
+        kl[5] = g[5] * (-lm) + dx[2] / N;
+        kl[6] = 0.0f;
+    } else {
+        for (int k = 0; k < c_gen.D; ++k) kl[k] = dx[k];
+    }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
+{
+    extern __shared__ __align__(16) float s_g[];   // [BLOCK/32][P+1]
+    const int D = c_gen.D, P = c_gen.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *gw = s_g + (size_t)warp * (P + 1);
+    for (int q = lane; q < P + 1; q += 32) gw[q] = 0.0f;
+    __syncwarp();
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = gid < p.N;
+    const size_t n = live ? (size_t)gid : (size_t)(p.N - 1);
+    const float lv = live ? 1.0f : 0.0f;
+    const float dt = p.dt;
+    float lam[MAXD], x[MAXD], g[MAXD], kl[6][MAXD];
+    float loss = 0.0f;
+    for (int c = 0; c < D; ++c) lam[c] = 0.0f;
+    auto jump = [&](int isave) {
+        for (int c = 0; c < D; ++c) {
+            const size_t idx = ((size_t)isave * D + c) * N + n;
+            if (p.fused_l2) {
+                const size_t idu = ((size_t)(isave * p.save_every) * D + c) * N + n;
+                const float r = __ldg(p.ustep + idu) - __ldg(p.cot + idx);
+                const float wgt = c_lossw[c];
+                loss = fmaf(wgt * r, r, loss);
+                lam[c] = fmaf(2.0f * wgt, r, lam[c]);
+            } else {
+                lam[c] += __ldg(p.cot + idx);
+            }
+        }
+    };
+    const int n_save = p.n_steps / p.save_every + 1;
+    jump(n_save - 1);
+    for (int s = p.n_steps - 1; s >= 0; --s) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {   // k_7 of the backward step only feeds FSAL / error control
+            for (int c = 0; c < D; ++c) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 7; ++j)
+                    if (Tsit5::bw(i, j) != 0.0)
+                        acc = fmaf((float)Tsit5::bw(i, j), __ldg(p.dense + ((size_t)(s * 6 + j) * D + c) * N + n), acc);
+                x[c] = fmaf(dt, acc, __ldg(p.ustep + ((size_t)s * D + c) * N + n));
+                float a2 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                    if (Tsit5::a(i, j) != 0.0) a2 = fmaf((float)Tsit5::a(i, j), kl[j][c], a2);
+                g[c] = fmaf(dt, a2, lam[c]);
+            }
+            model_vjp(x, g, dt * (float)Tsit5::b(i), lv, kl[i], gw, lane);
+        }
+        for (int c = 0; c < D; ++c) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc = fmaf((float)Tsit5::b(j), kl[j][c], acc);
+            lam[c] = fmaf(dt, acc, lam[c]);
+        }
+        if (s % p.save_every == 0) jump(s / p.save_every);
+    }
+    if (p.grad_u0 && live)
+        for (int c = 0; c < D; ++c) p.grad_u0[(size_t)c * N + n] = lam[c];
+    loss *= lv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (lane == 0) gw[P] = loss;
+    __syncwarp();
+    float *dst = p.partial + ((size_t)blockIdx.x * (BLOCK / 32) + warp) * (P + 1);
+    for (int q = lane; q < P + 1; q += 32) dst[q] = gw[q];
+}
+
+}  // namespace generic
+}  // namespace b200ude

@@ -115,6 +115,46 @@ class LotkaVolterraUDE:
         return self.trainable_rates + self.chain.num_params()
 
 
+SEIR_P = (10.0, 0.5944, 0.4239, 1117.3, 0.02, 1 / 3, 1 / 5, 0.2, 1 / 11.2)  # F, beta0, alpha, kappa, mu, sigma, gamma, d, lambda (seir_exposure.jl:33)
+
+
+@dataclass(frozen=True)
+class SEIRExposureUDE:
+    """7-state SEIR-type model whose exposure term is the chain: z = ann([S/N, I, D/N], p)  (seir_exposure.jl:117-130).
+
+    dS = -b0*S*F/N - z - mu*S;  dE = b0*S*F/N + z - (sigma+mu)*E;  dI, dR, dN, dD, dC as in `corona!` (:16-29).
+    """
+    chain: FastChain
+    p_true: Sequence[float] = SEIR_P
+
+    model = _lib.MODEL_SEIR
+    state_dim = 7
+
+    def consts(self):
+        return tuple(float(x) for x in self.p_true)
+
+    def num_params(self):
+        return self.chain.num_params()
+
+
+@dataclass(frozen=True)
+class NeuralODE:
+    """du = ann(u, p): the black-box form (seir_exposure.jl:52-64 without its input scaling)."""
+    chain: FastChain
+
+    model = _lib.MODEL_NODE
+
+    @property
+    def state_dim(self):
+        return self.chain.widths[0]
+
+    def consts(self):
+        return ()
+
+    def num_params(self):
+        return self.chain.num_params()
+
+
 # --------------------------------------------------------------------------- problem / algorithm types
 @dataclass
 class ODEProblem:
