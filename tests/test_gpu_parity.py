@@ -286,3 +286,47 @@ def test_seir_exposure_ude_vs_oracle(O):
     assert abs(loss - l64) <= 2e-3 * abs(l64)
     assert np.linalg.norm(gth - g64) <= 1e-2 * np.linalg.norm(g64)
     solver.close()
+
+
+@pytest.mark.parametrize("widths,acts,nx,N", [((1, 10, 20, 10, 1), ("tanh", "tanh", "tanh", "identity"), 26, 37),
+                                             ((1, 5, 5, 5, 1), ("rbf", "rbf", "rbf", "identity"), 26, 5),
+                                             ((1, 16, 16, 1), ("tanh", "tanh", "identity"), 256, 3)])
+def test_fisher_kpp_upde_vs_oracle(O, widths, acts, nx, N):
+    """Fisher-KPP UPDE (pointwise reaction chain + 3-tap periodic stencil, Fisher-KPP-CNN.jl:111-126): forward and
+    interpolating adjoint incl. the stencil weights and D0 vs the oracle (parity for this model is oracle-only)."""
+    ude = _ude()
+    rng = np.random.default_rng(21)
+    layers = [ude.FastDense(a, b, c) for a, b, c in zip(widths[:-1], widths[1:], acts)]
+    f = ude.FisherKPPUDE(ude.FastChain(*layers), nx)
+    m = O.fkpp_model(nx, widths, acts)
+    P = O.num_params(m)
+    assert P == f.num_params()
+    theta = np.concatenate([glorot_theta(widths, seed=3), [1.1, -2.5, 1.0, 0.0, 6.5 if nx == 26 else 30.0]]).astype(np.float32)   # Fisher-KPP-CNN.jl:99-104
+    x = np.linspace(0, 1, nx)
+    u0 = np.stack([0.5 * (np.tanh((x - (0.5 - d / 2)) / (d / 10)) - np.tanh((x - (0.5 + d / 2)) / (d / 10))) for d in rng.uniform(0.15, 0.5, N)], axis=1).astype(np.float32)
+    n_steps, dt, every = 40, 0.0125 if nx == 26 else 0.002, 4
+    y = (u0[None] * rng.uniform(0.8, 1.2, (n_steps // every + 1, 1, 1))).astype(np.float32)
+    solver = ude.UDESolver(f, 0.0, dt, n_steps, every, max_trajectories=N)
+    out, loss, gth, gu, status = _run(solver, theta, u0, y)
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(nx), dt, n_steps, save_every=every, want_out=True)
+    assert (status == 0).all() and out.shape == (n_steps // every + 1, nx, N)
+    assert np.all(np.abs(out - out64) <= 3e-4 * (1 + np.abs(out64)))
+    assert abs(loss - l64) <= 2e-4 * abs(l64)
+    assert np.linalg.norm(gth - g64) <= 3e-3 * np.linalg.norm(g64)
+    assert np.all(np.abs(gth[-5:] - g64[-5:]) <= 3e-3 * np.abs(g64[-5:]).max() + 1e-6)    # stencil weights, D0
+    assert np.abs(gu - gu64).max() <= 3e-3 * np.abs(gu64).max()
+    solver.close()
+
+
+def test_fisher_kpp_golden_forward(golden, O):
+    """KAT-6 on the GPU: scenario_3's trained parameters reproduce its stored X-hat (26 x 11, Float32)."""
+    ude = _ude()
+    g = golden["scenario_3"]
+    chain = ude.FastChain(ude.FastDense(1, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 1))
+    f = ude.FisherKPPUDE(chain, 26)
+    solver = ude.UDESolver(f, 0.0, 0.5 / 40, 400, 40, max_trajectories=2)
+    u0 = np.repeat(g["X"][:, :1].astype(np.float32), 2, axis=1)
+    out, status = solver.solve_host(g["theta_trained"].astype(np.float32), u0)
+    assert (status == 0).all()
+    assert np.abs(out[:, :, 0].T - g["Xhat"]).max() <= 5e-4
+    solver.close()

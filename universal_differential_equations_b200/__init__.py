@@ -7,7 +7,7 @@ mirror of the reference's call surface (sciml.py).  See DESIGN.md.
 """
 from . import _lib  # noqa: F401
 from .sciml import (  # noqa: F401
-    ADAM, BFGS, Chain, Dense, EnsembleProblem, FastChain, FastDense, ForwardDiffSensitivity,
+    ADAM, BFGS, Chain, Dense, EnsembleProblem, FastChain, FastDense, FisherKPPUDE, ForwardDiffSensitivity,
     InterpolatingAdjoint, LotkaVolterraUDE, NeuralODE, ODEProblem, SEIRExposureUDE, ReverseDiffVJP, Tsit5, UDESolver, Vern7,
     concrete_solve, identity, initial_params, rbf, remake, sciml_train, solve, tanh,
 )

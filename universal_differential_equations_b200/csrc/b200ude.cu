@@ -28,7 +28,8 @@ thread_local std::string g_create_error;
 //            scenario_1.jl:62-73 (x=0), scenario_2.jl:79-98 (x=1), hudson_bay.jl:77-91 (x=2)
 //   K_GENERIC  any LV / SEIR / NODE form with chain widths <= 64 and <= 5 layers (k_generic.cu): functional
 //            coverage (seir_exposure.jl:114-130 shapes), not tuned
-enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2, K_GENERIC };
+//   K_FKPP     Fisher-KPP UPDE: pointwise chain 1 -> ... -> 1 + 3-tap periodic stencil (Fisher-KPP-CNN.jl:111-126)
+enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2, K_GENERIC, K_FKPP };
 
 int kernel_num_params(KernelId k)
 {
@@ -114,6 +115,7 @@ bool generic_ok(const b200ude_desc &d)
     const int din = d.widths[0], dout = d.widths[d.n_layers];
     if (d.model == B200UDE_MODEL_LV) return d.state_dim == 2 && din == 2 && dout == 2 && d.n_prefix >= 0 && d.n_prefix <= 2 && d.n_consts >= 2;
     if (d.model == B200UDE_MODEL_SEIR) return d.state_dim == 7 && din == 3 && dout == 1 && d.n_prefix == 0 && d.n_consts >= 9;
+    if (d.model == B200UDE_MODEL_FKPP) return d.state_dim >= 3 && d.state_dim <= 256 && din == 1 && dout == 1 && d.n_prefix == 0 && d.n_suffix == 5 && d.n_loss_weights == 0;
     if (d.model == B200UDE_MODEL_NODE) return d.state_dim >= 1 && d.state_dim <= 8 && din == d.state_dim && dout == d.state_dim && d.n_prefix == 0;
     return false;
 }
@@ -130,7 +132,8 @@ KernelId pick_kernel(const b200ude_desc &d)
             if (d.n_prefix == 2) return K_LV5P2;
         }
     }
-    return generic_ok(d) ? K_GENERIC : K_NONE;
+    if (!generic_ok(d)) return K_NONE;
+    return d.model == B200UDE_MODEL_FKPP ? K_FKPP : K_GENERIC;
 }
 
 int env_int(const char *name, int dflt)
@@ -154,6 +157,7 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
     case K_LV5P1: e = launch_fwd_lv5(1, h->var, h->tab, p, st); break;
     case K_LV5P2: e = launch_fwd_lv5(2, h->var, h->tab, p, st); break;
     case K_GENERIC: e = launch_fwd_generic(h->gen, h->tab, p, st); break;
+    case K_FKPP: e = launch_fwd_fkpp(h->gen, h->tab, p, st); break;
     default: return fail(h, B200UDE_EUNSUPPORTED, "forward: no kernel");
     }
     CUDA_TRY(h, e);
@@ -180,6 +184,7 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     case K_LV5P1: e = launch_adj_lv5(1, h->var, h->tab, p, st, &grid); break;
     case K_LV5P2: e = launch_adj_lv5(2, h->var, h->tab, p, st, &grid); break;
     case K_GENERIC: e = launch_adj_generic(h->gen, h->tab, p, st, &grid); break;
+    case K_FKPP: e = launch_adj_fkpp(h->gen, h->tab, p, st, &grid); break;
     default: return fail(h, B200UDE_EUNSUPPORTED, "adjoint: no kernel");
     }
     CUDA_TRY(h, e);
@@ -235,8 +240,8 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->cap = (size_t)d->max_trajectories;
     h->sm_count = prop.multiProcessorCount;
     h->P = kernel_num_params(kid);
-    if (kid == K_GENERIC) {
-        int P = d->n_prefix;
+    if (kid == K_GENERIC || kid == K_FKPP) {
+        int P = d->n_prefix + d->n_suffix;
         for (int l = 0; l < d->n_layers; ++l) P += d->widths[l] * d->widths[l + 1] + d->widths[l + 1];
         h->P = P;
         h->gen.serial = g_serial + 1;   // same serial as the tables set below
@@ -255,7 +260,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->var.adj_tc = env_int("B200UDE_ADJ_TC", 1);
 
     const size_t N = h->cap, D = (size_t)h->D;
-    h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : kid == K_GENERIC ? adj_rows_generic((int)N) : adj_grid_lv5((int)N));
+    h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : adj_grid_lv5((int)N));
     bool ok = true;
     ok = ok && dalloc(h, &h->d_theta, (size_t)((h->P + 3) / 4) * 4) == cudaSuccess;
     ok = ok && dalloc(h, &h->d_ustep, (size_t)(d->n_steps + 1) * D * N) == cudaSuccess;

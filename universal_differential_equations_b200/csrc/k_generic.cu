@@ -51,4 +51,50 @@ cudaError_t launch_adj_generic(const GenericShape &g, const ConstTables &t, cons
     return cudaGetLastError();
 }
 
+// ---- Fisher-KPP ----
+static void fkpp_geom(int Nx, generic::FkppGeom *g, int *threads)
+{
+    g->Nx = Nx;
+    g->tpc = Nx >= 128 ? 1 : 128 / Nx;
+    *threads = ((g->tpc * Nx + 31) / 32) * 32;
+}
+
+int adj_rows_fkpp(int N, int Nx)
+{
+    generic::FkppGeom g; int th;
+    fkpp_geom(Nx, &g, &th);
+    return ((N + g.tpc - 1) / g.tpc) * (th / 32);
+}
+
+cudaError_t launch_fwd_fkpp(const GenericShape &gs, const ConstTables &t, const FwdParams &p, cudaStream_t st)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    e = upload_gen(gs, st);
+    if (e != cudaSuccess) return e;
+    generic::FkppGeom g; int th;
+    fkpp_geom(gs.D, &g, &th);
+    const int grid = (p.N + g.tpc - 1) / g.tpc;
+    generic::fkpp_forward_kernel<0><<<grid, th, sizeof(float) * g.tpc * g.Nx, st>>>(p, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adj_fkpp(const GenericShape &gs, const ConstTables &t, const AdjParams &p, cudaStream_t st, int *rows_out)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    e = upload_gen(gs, st);
+    if (e != cudaSuccess) return e;
+    generic::FkppGeom g; int th;
+    fkpp_geom(gs.D, &g, &th);
+    const int grid = (p.N + g.tpc - 1) / g.tpc;
+    const size_t smem = sizeof(float) * (((g.tpc * g.Nx + 3) / 4) * 4 + (size_t)(th / 32) * (gs.P + 1));
+    auto kern = generic::fkpp_adjoint_kernel<0>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    *rows_out = grid * (th / 32);
+    kern<<<grid, th, smem, st>>>(p, g);
+    return cudaGetLastError();
+}
+
 }  // namespace b200ude

@@ -153,18 +153,13 @@ __device__ __forceinline__ void warp_acc(float *gw, int idx, float v, int lane)
     if (lane == 0) gw[idx] += v;
 }
 
-// kl = (df/du)^T g ; this warp's gradient vector += sc * (df/dtheta)^T g   (all lanes of the warp participate)
-__device__ __noinline__ void model_vjp(const float *u, const float *g, float sc, float lv, float *kl, float *gw, int lane)
+// chain VJP: dx = (dchain/dx)^T dy; this warp's gradient vector += w * (dchain/dtheta)^T dy (w per lane; all lanes participate)
+__device__ __noinline__ void chain_vjp(const float *x, const float *dy, float w, float *dx, float *gw, int lane)
 {
-    float x[MAXD], y[MAXD], dy[MAXD], dx[MAXD];
+    float y[MAXD];
     float hs[MAXL + 1][MAXW], pre[MAXL][MAXW];
-    model_inputs(u, x);
     chain_fwd<true>(x, y, hs, pre);
     const int L = c_gen.n_layers;
-    const float w = sc * lv;   // quadrature weight, zero for padding lanes
-    if (c_gen.model == MODEL_SEIR) dy[0] = g[1] - g[0];   // z enters dS with -, dE with +
-    else for (int m = 0; m < c_gen.dout; ++m) dy[m] = g[m];
-    // reverse sweep
     float q[MAXW], qn[MAXW];
     for (int j = 0; j < c_gen.widths[L]; ++j) q[j] = dy[j];
     for (int l = L - 1; l >= 0; --l) {
@@ -182,7 +177,18 @@ __device__ __noinline__ void model_vjp(const float *u, const float *g, float sc,
         for (int j = 0; j < nout; ++j) warp_acc(gw, wo + nin * nout + j, w * q[j], lane);
         for (int i = 0; i < nin; ++i) q[i] = qn[i];
     }
-    for (int i = 0; i < c_gen.din; ++i) dx[i] = q[i];
+    for (int i = 0; i < c_gen.widths[0]; ++i) dx[i] = q[i];
+}
+
+// kl = (df/du)^T g ; this warp's gradient vector += sc * (df/dtheta)^T g   (all lanes of the warp participate)
+__device__ __forceinline__ void model_vjp(const float *u, const float *g, float sc, float lv, float *kl, float *gw, int lane)
+{
+    float x[MAXD], dy[MAXD], dx[MAXD];
+    model_inputs(u, x);
+    const float w = sc * lv;   // quadrature weight, zero for padding lanes
+    if (c_gen.model == MODEL_SEIR) dy[0] = g[1] - g[0];   // z enters dS with -, dE with +
+    else for (int m = 0; m < c_gen.dout; ++m) dy[m] = g[m];
+    chain_vjp(x, dy, w, dx, gw, lane);
     if (c_gen.model == MODEL_LV) {
         float a1 = c_consts[0], a2 = c_consts[1];
         if (c_gen.n_prefix == 1) a2 = c_theta[0];
@@ -278,6 +284,168 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
     if (lane == 0) gw[P] = loss;
     __syncwarp();
     float *dst = p.partial + ((size_t)blockIdx.x * (BLOCK / 32) + warp) * (P + 1);
+    for (int q = lane; q < P + 1; q += 32) dst[q] = gw[q];
+}
+
+// =====================================================================================================
+// Fisher-KPP UPDE (FisherKPP/Fisher-KPP-CNN.jl:111-126, LotkaVolterra/scenario_3.jl:103-114):
+//   du_i = NN(u_i) + D0 * (w1 u_{i-1} + w2 u_i + w3 u_{i+1}),  periodic, theta = [chain | w1 w2 w3 b | D0].
+// One thread per grid point; a CTA holds `tpc` whole trajectories (tpc * Nx threads, rounded up to a warp
+// multiple); neighbours are exchanged through shared memory.  The handle's internal stores (ustep, dense)
+// are point-fastest ([row][trajectory][point]) so that every warp access is contiguous; the ABI arrays
+// (u0, out, data, grad_u0) keep the documented trajectory-fastest layout.
+// =====================================================================================================
+struct FkppGeom {
+    int Nx, tpc;
+};
+
+__device__ __forceinline__ float fkpp_exchange(float *sU, int slot, int base, int i, int Nx, bool valid, float v, float &vm, float &vp)
+{
+    if (valid) sU[slot] = v;
+    __syncthreads();
+    vm = sU[base + (i + Nx - 1) % Nx];
+    vp = sU[base + (i + 1) % Nx];
+    __syncthreads();
+    return v;
+}
+
+template <int DUMMY>
+__global__ void fkpp_forward_kernel(FwdParams p, FkppGeom geo)
+{
+    extern __shared__ __align__(16) float s_dyn[];
+    float *sU = s_dyn;
+    const int Nx = geo.Nx, slots = geo.tpc * Nx;
+    const int slot = threadIdx.x;
+    const bool valid = slot < slots;
+    const int t_loc = valid ? slot / Nx : 0, i = valid ? slot % Nx : 0;
+    const int base = t_loc * Nx;
+    const int traj = blockIdx.x * geo.tpc + t_loc;
+    const bool live = valid && traj < p.N;
+    const size_t N = (size_t)p.N, n = (size_t)(live ? traj : p.N - 1);
+    const float dt = p.dt;
+    const int sx = c_gen.P - 5;
+    const float w1 = c_theta[sx], w2 = c_theta[sx + 1], w3 = c_theta[sx + 2], D0 = c_theta[sx + 4];
+    float u = __ldg(p.u0 + (size_t)i * N + n);
+    auto rhs = [&](float g) {
+        float gm, gp, y;
+        fkpp_exchange(sU, slot, base, i, Nx, valid, g, gm, gp);
+        chain_fwd<false>(&g, &y, nullptr, nullptr);
+        return fmaf(D0, fmaf(w1, gm, fmaf(w2, g, w3 * gp)), y);
+    };
+    auto store_int = [&](float *b, int row, float v) { if (live) b[((size_t)row * N + n) * Nx + i] = v; };
+    auto store_abi = [&](float *b, int row, float v) { if (live) b[((size_t)row * Nx + i) * N + n] = v; };
+    store_abi(p.out, 0, u);
+    store_int(p.ustep, 0, u);
+    float k[7];
+    k[0] = rhs(u);
+    store_int(p.dense, 0, k[0]);
+    int isave = 1;
+    for (int s = 0; s < p.n_steps; ++s) {
+#pragma unroll
+        for (int st = 1; st < 7; ++st) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < st; ++j)
+                if (Tsit5::a(st, j) != 0.0) acc = fmaf((float)Tsit5::a(st, j), k[j], acc);
+            const float g = fmaf(dt, acc, u);
+            if (st == 6) u = g;
+            k[st] = rhs(g);
+            store_int(p.dense, s * 6 + st, k[st]);
+        }
+        store_int(p.ustep, s + 1, u);
+        if ((s + 1) % p.save_every == 0) { store_abi(p.out, isave, u); ++isave; }
+        k[0] = k[6];
+    }
+    if (p.status) {
+        // a trajectory is flagged when any of its points is non-finite
+        const int bad = __syncthreads_or((live && !(fabsf(u) <= 3.0e38f)) ? 1 : 0);   // CTA-wide; refined per trajectory below
+        if (bad) {
+            if (valid) sU[slot] = (fabsf(u) <= 3.0e38f) ? 0.0f : 1.0f;
+            __syncthreads();
+            if (live && i == 0) {
+                float any = 0.0f;
+                for (int q = 0; q < Nx; ++q) any += sU[base + q];
+                p.status[n] = any > 0.0f ? 1 : 0;
+            }
+        } else if (live && i == 0) {
+            p.status[n] = 0;
+        }
+    }
+}
+
+template <int DUMMY>
+__global__ void fkpp_adjoint_kernel(AdjParams p, FkppGeom geo)
+{
+    extern __shared__ __align__(16) float s_dyn[];
+    const int Nx = geo.Nx, slots = geo.tpc * Nx, P = c_gen.P;
+    float *sU = s_dyn;                                   // [slots] neighbour exchange
+    float *s_g = s_dyn + ((slots + 3) / 4) * 4;          // [nwarps][P+1]
+    const int slot = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *gw = s_g + (size_t)warp * (P + 1);
+    for (int q = lane; q < P + 1; q += 32) gw[q] = 0.0f;
+    __syncwarp();
+    const bool valid = slot < slots;
+    const int t_loc = valid ? slot / Nx : 0, i = valid ? slot % Nx : 0;
+    const int base = t_loc * Nx;
+    const int traj = blockIdx.x * geo.tpc + t_loc;
+    const bool live = valid && traj < p.N;
+    const size_t N = (size_t)p.N, n = (size_t)(live ? traj : p.N - 1);
+    const float lv = live ? 1.0f : 0.0f;
+    const float dt = p.dt;
+    const int sx = P - 5;
+    const float w1 = c_theta[sx], w2 = c_theta[sx + 1], w3 = c_theta[sx + 2], D0 = c_theta[sx + 4];
+    float lam = 0.0f, loss = 0.0f, kl[6];
+    auto jump = [&](int isave) {
+        const size_t idx = ((size_t)isave * Nx + i) * N + n;   // ABI layout
+        if (p.fused_l2) {
+            const float r = __ldg(p.ustep + ((size_t)(isave * p.save_every) * N + n) * Nx + i) - __ldg(p.cot + idx);
+            loss = fmaf(r, r, loss);
+            lam = fmaf(2.0f, r, lam);
+        } else {
+            lam += __ldg(p.cot + idx);
+        }
+    };
+    const int n_save = p.n_steps / p.save_every + 1;
+    jump(n_save - 1);
+    for (int s = p.n_steps - 1; s >= 0; --s) {
+#pragma unroll
+        for (int st = 0; st < 6; ++st) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j)
+                if (Tsit5::bw(st, j) != 0.0)
+                    acc = fmaf((float)Tsit5::bw(st, j), __ldg(p.dense + ((size_t)(s * 6 + j) * N + n) * Nx + i), acc);
+            const float x = fmaf(dt, acc, __ldg(p.ustep + ((size_t)s * N + n) * Nx + i));
+            float a2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < st; ++j)
+                if (Tsit5::a(st, j) != 0.0) a2 = fmaf((float)Tsit5::a(st, j), kl[j], a2);
+            const float g = fmaf(dt, a2, lam);
+            const float w = dt * (float)Tsit5::b(st) * lv;
+            // neighbours of u (for the stencil-weight gradients) and of lambda (for the transposed stencil)
+            float xm, xp, gm, gp, dx;
+            fkpp_exchange(sU, slot, base, i, Nx, valid, x, xm, xp);
+            fkpp_exchange(sU, slot, base, i, Nx, valid, g, gm, gp);
+            chain_vjp(&x, &g, w, &dx, gw, lane);
+            kl[st] = dx + D0 * fmaf(w2, g, fmaf(w1, gp, w3 * gm));   // (J^T g)_i: w1 couples i+1 -> i, w3 couples i-1 -> i
+            warp_acc(gw, sx + 0, w * D0 * xm * g, lane);
+            warp_acc(gw, sx + 1, w * D0 * x * g, lane);
+            warp_acc(gw, sx + 2, w * D0 * xp * g, lane);
+            warp_acc(gw, sx + 4, w * fmaf(w1, xm, fmaf(w2, x, w3 * xp)) * g, lane);
+        }
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc = fmaf((float)Tsit5::b(j), kl[j], acc);
+        lam = fmaf(dt, acc, lam);
+        if (s % p.save_every == 0) jump(s / p.save_every);
+    }
+    if (p.grad_u0 && live) p.grad_u0[(size_t)i * N + n] = lam;
+    loss *= lv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (lane == 0) gw[P] = loss;
+    __syncwarp();
+    float *dst = p.partial + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (P + 1);
     for (int q = lane; q < P + 1; q += 32) dst[q] = gw[q];
 }
 

@@ -138,6 +138,30 @@ class SEIRExposureUDE:
 
 
 @dataclass(frozen=True)
+class FisherKPPUDE:
+    """Fisher-KPP universal PDE on a periodic grid of `nx` points (FisherKPP/Fisher-KPP-CNN.jl:111-126,
+    LotkaVolterra/scenario_3.jl:103-114):  du_i = rx_nn(u_i) + D0 * (w1 u_{i-1} + w2 u_i + w3 u_{i+1}).
+
+    theta = [chain(1 -> ... -> 1); w1, w2, w3, conv-bias (unused); D0]  (Fisher-KPP-CNN.jl:106-109).
+    """
+    chain: FastChain
+    nx: int
+
+    model = _lib.MODEL_FKPP
+    n_suffix = 5
+
+    @property
+    def state_dim(self):
+        return self.nx
+
+    def consts(self):
+        return ()
+
+    def num_params(self):
+        return self.chain.num_params() + 5
+
+
+@dataclass(frozen=True)
 class NeuralODE:
     """du = ann(u, p): the black-box form (seir_exposure.jl:52-64 without its input scaling)."""
     chain: FastChain
@@ -236,7 +260,7 @@ class UDESolver:
         for i, a in enumerate(chain.acts):
             d.acts[i] = _ACT_CODE[a]
         d.n_prefix = getattr(f, "trainable_rates", 0)
-        d.n_suffix = 0
+        d.n_suffix = getattr(f, "n_suffix", 0)
         cs = f.consts()
         d.n_consts = len(cs)
         for i, c in enumerate(cs):
