@@ -82,6 +82,7 @@ extern "C" {
 /* per-trajectory status words written by b200ude_forward */
 #define B200UDE_TRAJ_OK 0
 #define B200UDE_TRAJ_NONFINITE 1
+#define B200UDE_TRAJ_MAXSTEPS 2 /* adaptive: more than max_steps accepted steps needed */
 
 /* error codes */
 #define B200UDE_OK 0
@@ -114,11 +115,14 @@ typedef struct b200ude_desc {
     double dt;            /* fixed step (adaptive = false); saveat = t0 + i*save_every*dt */
     int32_t n_steps;      /* number of steps; tspan[2] = t0 + n_steps*dt */
     int32_t save_every;   /* save the state every this many steps (and at t0) */
-    double abstol, reltol; /* reserved for adaptive stepping; ignored when dt > 0 */
+    double abstol, reltol; /* adaptive stepping tolerances (used when adaptive = 1) */
     int32_t n_loss_weights; /* 0 => all ones; else = state_dim */
     double loss_weights[16]; /* per-component weight of the fused L2 loss (seir_exposure.jl:146 uses rows 2:4) */
     uint64_t max_trajectories; /* capacity: scratch is sized for this many trajectories */
     uint32_t flags;
+    int32_t adaptive;   /* 0: fixed step dt (adaptive = false). 1: Tsit5 with OrdinaryDiffEq's PI controller, abstol / reltol;
+                           saveat = t0 + i*save_every*dt, i = 0..n_steps/save_every (dt only defines the save grid) */
+    int32_t max_steps;  /* adaptive: capacity of ACCEPTED steps per trajectory (status 2 when exceeded) */
     uint32_t reserved;
 } b200ude_desc;
 
@@ -141,7 +145,8 @@ int32_t b200ude_set_params(b200ude_handle *h, const void *theta, size_t P, int32
 /* FORWARD  (replaces: the UDE RHS closure + OrdinaryDiffEq perform_step! loop behind
  * concrete_solve(prob, Tsit5(), u0, p; saveat, ...), one trajectory per ensemble member).
  * u0 [d][N], out [n_save][d][N], status [N] (may be NULL): DEVICE pointers.
- * Also stores the dense output (stage derivatives) the adjoint interpolates. */
+ * Also stores the dense output (stage derivatives) the adjoint interpolates.  With adaptive = 1 `out` must stay valid
+ * until the matching adjoint call (the fused L2 adjoint reads the interpolated saved states from it). */
 int32_t b200ude_forward(b200ude_handle *h, const void *u0, size_t N, void *out, int32_t *status,
                         void *stream);
 

@@ -201,3 +201,49 @@ def vern7_constants():
     c = np.empty(58)
     lib().ude_vern7_constants(_p(c))
     return c
+
+
+def solve_adaptive_dense(m, theta, u0, saveat, abstol, reltol, max_steps=4096):
+    """Adaptive Tsit5 recording the accepted steps -> (out[n_save,d], rec) with rec = (tgrid, ustep, dense, nacc)."""
+    suf, ct = _dt(theta.dtype)
+    dtp = theta.dtype
+    u0 = np.ascontiguousarray(u0, dtype=dtp)
+    saveat = np.ascontiguousarray(saveat, dtype=dtp)
+    out = np.empty((len(saveat), m.d), dtype=dtp)
+    tgrid = np.empty(max_steps + 1, dtype=dtp)
+    ustep = np.empty((max_steps + 1, m.d), dtype=dtp)
+    dense = np.empty((max_steps, 7, m.d), dtype=dtp)
+    f = getattr(lib(), "ude_solve_adaptive_dense" + suf)
+    f.restype = C.c_int
+    nacc = f(C.byref(m), _p(np.ascontiguousarray(theta)), _p(u0), _p(saveat), len(saveat), ct(abstol), ct(reltol), max_steps,
+             _p(out), _p(tgrid), _p(ustep), _p(dense))
+    if nacc < 0:
+        raise FloatingPointError("oracle: adaptive dense solve failed")
+    return out, (tgrid, ustep, dense, nacc)
+
+
+def adjoint_replay(m, theta, saveat, rec, dLdout):
+    suf, ct = _dt(theta.dtype)
+    tgrid, ustep, dense, nacc = rec
+    g = np.zeros(num_params(m), dtype=theta.dtype)
+    gu = np.empty(m.d, dtype=theta.dtype)
+    saveat = np.ascontiguousarray(saveat, dtype=theta.dtype)
+    getattr(lib(), "ude_adjoint_replay" + suf)(C.byref(m), _p(np.ascontiguousarray(theta)), _p(saveat), len(saveat), _p(tgrid), _p(ustep),
+                                               _p(dense), nacc, _p(np.ascontiguousarray(dLdout, dtype=theta.dtype)), _p(g), _p(gu))
+    return g, gu
+
+
+def adjoint_adaptive(m, theta, saveat, rec, dLdout, abstol, reltol):
+    """Reference-style error-controlled backward solve of [lambda; mu]; returns grad_theta, grad_u0, n_backward_steps."""
+    suf, ct = _dt(theta.dtype)
+    tgrid, ustep, dense, nacc = rec
+    g = np.zeros(num_params(m), dtype=theta.dtype)
+    gu = np.empty(m.d, dtype=theta.dtype)
+    saveat = np.ascontiguousarray(saveat, dtype=theta.dtype)
+    f = getattr(lib(), "ude_adjoint_adaptive" + suf)
+    f.restype = C.c_int
+    ns = f(C.byref(m), _p(np.ascontiguousarray(theta)), _p(saveat), len(saveat), _p(tgrid), _p(ustep), _p(dense), nacc,
+           _p(np.ascontiguousarray(dLdout, dtype=theta.dtype)), ct(abstol), ct(reltol), _p(g), _p(gu))
+    if ns < 0:
+        raise FloatingPointError("oracle: adaptive adjoint failed")
+    return g, gu, ns

@@ -123,6 +123,25 @@ double ude_ensemble_loss_grad_f32(const ude_model *m, const float *theta, const 
                                   int n_steps, int save_every, float *out, float *grad_theta,
                                   float *grad_u0, int n_threads);
 
+/* adaptive Tsit5 forward that records every accepted step (tgrid[nacc+1], ustep[(nacc+1)*d], dense[nacc*7*d]);
+ * returns nacc or -1.  The two adjoints below consume that record:
+ *   replay   -- one backward Tsit5 step per accepted forward step, split at the save times (what the GPU does);
+ *   adaptive -- reference-style error-controlled backward solve of [lambda; mu] with tstops at the save times. */
+int ude_solve_adaptive_dense_f64(const ude_model *m, const double *theta, const double *u0, const double *saveat, int n_save,
+                                  double abstol, double reltol, int max_steps, double *out, double *tgrid, double *ustep, double *dense);
+void ude_adjoint_replay_f64(const ude_model *m, const double *theta, const double *saveat, int n_save, const double *tgrid,
+                             const double *ustep, const double *dense, int nacc, const double *dLdout, double *grad_theta, double *grad_u0);
+int ude_adjoint_adaptive_f64(const ude_model *m, const double *theta, const double *saveat, int n_save, const double *tgrid,
+                              const double *ustep, const double *dense, int nacc, const double *dLdout, double abstol, double reltol,
+                              double *grad_theta, double *grad_u0);
+int ude_solve_adaptive_dense_f32(const ude_model *m, const float *theta, const float *u0, const float *saveat, int n_save,
+                                  float abstol, float reltol, int max_steps, float *out, float *tgrid, float *ustep, float *dense);
+void ude_adjoint_replay_f32(const ude_model *m, const float *theta, const float *saveat, int n_save, const float *tgrid,
+                             const float *ustep, const float *dense, int nacc, const float *dLdout, float *grad_theta, float *grad_u0);
+int ude_adjoint_adaptive_f32(const ude_model *m, const float *theta, const float *saveat, int n_save, const float *tgrid,
+                              const float *ustep, const float *dense, int nacc, const float *dLdout, float abstol, float reltol,
+                              float *grad_theta, float *grad_u0);
+
 /* tableau access for the known-answer test against OrdinaryDiffEq's serialized constants */
 void ude_tsit5_constants(double *c56);  /* same order as the .jld2 block: c1..c6,a21..a76,bt1..7,r11..r74 */
 void ude_vern7_constants(double *c58);  /* c2..c8, nonzero a_ij row by row, b1,b4..b9, bt1,bt4..bt10 */

@@ -502,6 +502,272 @@ void FN(ude_adjoint_fixed)(const ude_model *m, const REAL *th, const REAL *out, 
     free(ustart);
 }
 
+/* ---------------------------------------------- adaptive forward with dense output ---- */
+/* Adaptive Tsit5 (same controller as ude_solve_adaptive) that also records every ACCEPTED step:
+ * tgrid[0..nacc], ustep[(nacc+1) x d], dense[nacc x 7 x d] -- what InterpolatingAdjoint interpolates.
+ * saveat values are produced by the interpolant.  Returns the number of accepted steps or -1
+ * (non-finite state, or more than max_steps steps). */
+int FN(ude_solve_adaptive_dense)(const ude_model *m, const REAL *th, const REAL *u0, const REAL *saveat,
+                                 int n_save, REAL abstol, REAL reltol, int max_steps, REAL *out,
+                                 REAL *tgrid, REAL *ustep, REAL *dense)
+{
+    const ude_tableau *tb = ude_get_tableau(UDE_TSIT5);
+    const int d = m->d, s = 7, order = 5;
+    const REAL t0 = saveat[0], t1 = saveat[n_save - 1];
+    const REAL gamma = (REAL)0.9, qmin = (REAL)0.2, qmax = (REAL)10;
+    const REAL beta2 = (REAL)2 / ((REAL)5 * order), beta1 = (REAL)7 / ((REAL)10 * order);
+    REAL qold = (REAL)1e-4;
+    REAL u[UDE_MAX_STATE], un[UDE_MAX_STATE], err[UDE_MAX_STATE], f0[UDE_MAX_STATE], f1[UDE_MAX_STATE];
+    REAL ks[UDE_MAX_STAGES * UDE_MAX_STATE], kf[UDE_MAX_STATE];
+    for (int k = 0; k < d; ++k) { u[k] = u0[k]; out[k] = u[k]; ustep[k] = u[k]; }
+    tgrid[0] = t0;
+    int isave = 1, nacc = 0;
+    REAL dt;
+    {
+        FN(ude_rhs)(m, th, u, f0);
+        REAL d0 = 0, d1 = 0, d2 = 0;
+        for (int k = 0; k < d; ++k) {
+            const REAL sk = abstol + reltol * R_FABS(u[k]);
+            d0 += (u[k] / sk) * (u[k] / sk);
+            d1 += (f0[k] / sk) * (f0[k] / sk);
+        }
+        d0 = R_SQRT(d0 / d); d1 = R_SQRT(d1 / d);
+        REAL dt0 = (d0 < (REAL)1e-5 || d1 < (REAL)1e-5) ? (REAL)1e-6 : (REAL)0.01 * d0 / d1;
+        if (dt0 > t1 - t0) dt0 = t1 - t0;
+        for (int k = 0; k < d; ++k) un[k] = u[k] + dt0 * f0[k];
+        FN(ude_rhs)(m, th, un, f1);
+        for (int k = 0; k < d; ++k) {
+            const REAL sk = abstol + reltol * R_FABS(u[k]);
+            const REAL e = (f1[k] - f0[k]) / sk;
+            d2 += e * e;
+        }
+        d2 = R_SQRT(d2 / d) / dt0;
+        const REAL dm = d1 > d2 ? d1 : d2;
+        REAL dt1 = dm <= (REAL)1e-15 ? (dt0 * (REAL)1e-3 > (REAL)1e-6 ? dt0 * (REAL)1e-3 : (REAL)1e-6)
+                                     : R_POW((REAL)10, -((REAL)2 + R_LOG10(dm)) / (REAL)order);
+        dt = (REAL)100 * dt0 < dt1 ? (REAL)100 * dt0 : dt1;
+        if (dt > t1 - t0) dt = t1 - t0;
+    }
+    memcpy(kf, f0, sizeof(REAL) * d);
+    REAL t = t0;
+    int guard = 0;
+    while (isave < n_save && guard++ < 100000000) {
+        REAL h = dt;
+        int clipped = 0;
+        if (t + h >= t1 - (REAL)1e-7 * R_FABS(t1)) { h = t1 - t; clipped = 1; }
+        FN(rk_step)(m, th, tb, u, h, kf, ks, un, err);
+        const REAL EEst = FN(eest)(err, u, un, d, abstol, reltol);
+        if (!isfinite((double)EEst)) return -1;
+        const REAL q11 = R_POW(EEst, beta1);
+        REAL q = q11 / R_POW(qold, beta2);
+        q = q / gamma;
+        if (q < (REAL)1 / qmax) q = (REAL)1 / qmax;
+        if (q > (REAL)1 / qmin) q = (REAL)1 / qmin;
+        if (EEst <= (REAL)1) {
+            if (nacc >= max_steps) return -1;
+            const REAL tn = clipped ? t1 : t + h;
+            memcpy(dense + (size_t)nacc * s * d, ks, sizeof(REAL) * (size_t)s * d);
+            while (isave < n_save && saveat[isave] <= tn + (REAL)1e-7 * R_FABS(tn)) {
+                REAL Th = (saveat[isave] - t) / h, bw[7];
+                if (Th > 1) Th = 1;
+                FN(tsit5_bTheta)(Th, bw);
+                for (int k = 0; k < d; ++k) {
+                    REAL acc = 0;
+                    for (int i = 0; i < 7; ++i) acc += bw[i] * ks[(size_t)i * d + k];
+                    out[(size_t)isave * d + k] = u[k] + h * acc;
+                }
+                ++isave;
+            }
+            qold = EEst > (REAL)1e-4 ? EEst : (REAL)1e-4;
+            if (q >= (REAL)1 && q <= (REAL)1.2) q = 1;
+            if (!clipped || h >= dt) dt = h / q;
+            else { const REAL prop = h / q; if (prop > dt) dt = prop; }
+            t = tn;
+            ++nacc;
+            tgrid[nacc] = t;
+            for (int k = 0; k < d; ++k) { u[k] = un[k]; ustep[(size_t)nacc * d + k] = u[k]; }
+            memcpy(kf, ks + (size_t)(s - 1) * d, sizeof(REAL) * d);
+        } else {
+            REAL qr = q11 / gamma;
+            if (qr > (REAL)1 / qmin) qr = (REAL)1 / qmin;
+            dt = h / qr;
+            memcpy(kf, ks, sizeof(REAL) * d);
+        }
+    }
+    return isave == n_save ? nacc : -1;
+}
+
+/* u(t) from the recorded dense output; *hint is the last step index used (monotone search) */
+static void FN(dense_eval)(const REAL *tgrid, const REAL *ustep, const REAL *dense, int nacc, int d, REAL t,
+                           int *hint, REAL *uu)
+{
+    int n = *hint;
+    if (n < 0) n = 0;
+    if (n >= nacc) n = nacc - 1;
+    while (n > 0 && t < tgrid[n]) --n;
+    while (n < nacc - 1 && t > tgrid[n + 1]) ++n;
+    *hint = n;
+    const REAL h = tgrid[n + 1] - tgrid[n];
+    REAL Th = (t - tgrid[n]) / h, bw[7];
+    if (Th < 0) Th = 0;
+    if (Th > 1) Th = 1;
+    FN(tsit5_bTheta)(Th, bw);
+    const REAL *ks = dense + (size_t)n * 7 * d;
+    for (int k = 0; k < d; ++k) {
+        REAL acc = 0;
+        for (int j = 0; j < 7; ++j) acc += bw[j] * ks[(size_t)j * d + k];
+        uu[k] = ustep[(size_t)n * d + k] + h * acc;
+    }
+}
+
+/* Interpolating adjoint that REPLAYS the accepted forward steps backwards: each forward step
+ * [t_n, t_n+1] is one backward Tsit5 step, split at the save times that fall strictly inside it (the
+ * loss jumps are tstops of the backward solve).  This is what the GPU kernels do for adaptive solves;
+ * ude_adjoint_adaptive below is the reference-style error-controlled backward solve it is checked against. */
+void FN(ude_adjoint_replay)(const ude_model *m, const REAL *th, const REAL *saveat, int n_save,
+                            const REAL *tgrid, const REAL *ustep, const REAL *dense, int nacc,
+                            const REAL *dLdout, REAL *grad_theta, REAL *grad_u0)
+{
+    const ude_tableau *tb = ude_get_tableau(UDE_TSIT5);
+    const int d = m->d;
+    REAL lam[UDE_MAX_STATE], g[UDE_MAX_STATE], uu[UDE_MAX_STATE], kl[7 * UDE_MAX_STATE];
+    int isave = n_save - 1;
+    for (int k = 0; k < d; ++k) lam[k] = dLdout[(size_t)isave * d + k];
+    --isave;
+    for (int n = nacc - 1; n >= 0; --n) {
+        const REAL tn = tgrid[n], tn1 = tgrid[n + 1], hn = tn1 - tn;
+        const REAL *ks = dense + (size_t)n * 7 * d;
+        const REAL eps = (REAL)1e-6 * hn;
+        REAL cur = tn1;
+        while (cur > tn + eps) {
+            REAL ta = tn;
+            if (isave >= 0 && saveat[isave] > tn + eps) ta = saveat[isave];
+            const REAL h = cur - ta;
+            for (int i = 0; i < 6; ++i) {
+                REAL Th = (cur - (REAL)tb->c[i] * h - tn) / hn, bw[7];
+                if (Th < 0) Th = 0;
+                if (Th > 1) Th = 1;
+                FN(tsit5_bTheta)(Th, bw);
+                for (int k = 0; k < d; ++k) {
+                    REAL acc = 0;
+                    for (int j = 0; j < 7; ++j) acc += bw[j] * ks[(size_t)j * d + k];
+                    uu[k] = ustep[(size_t)n * d + k] + hn * acc;
+                }
+                for (int k = 0; k < d; ++k) {
+                    REAL acc = 0;
+                    for (int j = 0; j < i; ++j) {
+                        const REAL a = (REAL)tb->A[i][j];
+                        if (a != 0) acc += a * kl[(size_t)j * d + k];
+                    }
+                    g[k] = lam[k] + h * acc;
+                }
+                FN(ude_rhs_vjp)(m, th, uu, g, kl + (size_t)i * d, grad_theta, h * (REAL)tb->A[6][i]);
+            }
+            for (int k = 0; k < d; ++k) {
+                REAL acc = 0;
+                for (int j = 0; j < 6; ++j) acc += (REAL)tb->A[6][j] * kl[(size_t)j * d + k];
+                lam[k] += h * acc;
+            }
+            cur = ta;
+            if (isave >= 0 && R_FABS(saveat[isave] - ta) <= eps) {
+                for (int k = 0; k < d; ++k) lam[k] += dLdout[(size_t)isave * d + k];
+                --isave;
+            }
+        }
+    }
+    for (int k = 0; k < d; ++k) grad_u0[k] = lam[k];
+}
+
+/* Reference-style backward solve: the augmented state [lambda; mu] (d + P entries) is integrated from T to t0
+ * with adaptive Tsit5 (same tolerances, PI controller, error norm over all d + P components), tstops at the
+ * save times where dL/du(t_i) is added to lambda; u(t) from the forward dense output.  grad_theta is SET. */
+int FN(ude_adjoint_adaptive)(const ude_model *m, const REAL *th, const REAL *saveat, int n_save,
+                             const REAL *tgrid, const REAL *ustep, const REAL *dense, int nacc,
+                             const REAL *dLdout, REAL abstol, REAL reltol, REAL *grad_theta, REAL *grad_u0)
+{
+    const ude_tableau *tb = ude_get_tableau(UDE_TSIT5);
+    const int d = m->d, order = 5;
+    const size_t P = ude_num_params(m), S = (size_t)d + P;
+    const REAL gamma = (REAL)0.9, qmin = (REAL)0.2, qmax = (REAL)10;
+    const REAL beta2 = (REAL)2 / ((REAL)5 * order), beta1 = (REAL)7 / ((REAL)10 * order);
+    REAL qold = (REAL)1e-4;
+    REAL *y = (REAL *)calloc(S, sizeof(REAL)), *yn = (REAL *)calloc(S, sizeof(REAL));
+    REAL *K = (REAL *)calloc(7 * S, sizeof(REAL)), *gs = (REAL *)calloc(S, sizeof(REAL));
+    REAL uu[UDE_MAX_STATE];
+    int hint = nacc - 1, isave = n_save - 1, nsteps = 0;
+    for (int k = 0; k < d; ++k) y[k] = dLdout[(size_t)isave * d + k];
+    --isave;
+    REAL t = saveat[n_save - 1];
+    REAL dt = (saveat[n_save - 1] - saveat[0]) * (REAL)0.01;   /* backward step magnitude */
+    int have_k1 = 0;
+    while (isave >= 0) {
+        const REAL tstop = saveat[isave];
+        REAL h = dt;
+        int clipped = 0;
+        if (t - h <= tstop + (REAL)1e-7 * R_FABS(tstop)) { h = t - tstop; clipped = 1; }
+        /* stages in reverse time: y' = +F(y, t - c h) with F = [J_u^T lam; J_theta^T lam] */
+        for (int i = 0; i < 7; ++i) {
+            if (i == 0 && have_k1) continue;
+            for (size_t q = 0; q < S; ++q) {
+                REAL acc = 0;
+                for (int j = 0; j < i; ++j) {
+                    const REAL a = (REAL)tb->A[i][j];
+                    if (a != 0) acc += a * K[(size_t)j * S + q];
+                }
+                gs[q] = y[q] + h * acc;
+            }
+            FN(dense_eval)(tgrid, ustep, dense, nacc, d, t - (REAL)tb->c[i] * h, &hint, uu);
+            REAL *Ki = K + (size_t)i * S;
+            for (size_t q = d; q < S; ++q) Ki[q] = 0;
+            FN(ude_rhs_vjp)(m, th, uu, gs, Ki, Ki + d, (REAL)1);
+            if (i == 5) for (size_t q = 0; q < S; ++q) {   /* y_new = stage-7 argument (row 7 = b) */
+                REAL acc = 0;
+                for (int j = 0; j < 6; ++j) acc += (REAL)tb->A[6][j] * K[(size_t)j * S + q];
+                yn[q] = y[q] + h * acc;
+            }
+        }
+        REAL ee = 0;
+        for (size_t q = 0; q < S; ++q) {
+            REAL e = 0;
+            for (int j = 0; j < 7; ++j) e += (REAL)tb->bt[j] * K[(size_t)j * S + q];
+            e *= h;
+            const REAL a = R_FABS(y[q]), b = R_FABS(yn[q]);
+            const REAL sc = abstol + reltol * (a > b ? a : b);
+            ee += (e / sc) * (e / sc);
+        }
+        const REAL EEst = R_SQRT(ee / (REAL)S);
+        if (!isfinite((double)EEst) || ++nsteps > 10000000) { free(y); free(yn); free(K); free(gs); return -1; }
+        const REAL q11 = R_POW(EEst, beta1);
+        REAL q = q11 / R_POW(qold, beta2) / gamma;
+        if (q < (REAL)1 / qmax) q = (REAL)1 / qmax;
+        if (q > (REAL)1 / qmin) q = (REAL)1 / qmin;
+        if (EEst <= (REAL)1) {
+            qold = EEst > (REAL)1e-4 ? EEst : (REAL)1e-4;
+            if (q >= (REAL)1 && q <= (REAL)1.2) q = 1;
+            if (!clipped || h >= dt) dt = h / q;
+            else { const REAL prop = h / q; if (prop > dt) dt = prop; }
+            t = clipped ? tstop : t - h;
+            for (size_t qq = 0; qq < S; ++qq) y[qq] = yn[qq];
+            memcpy(K, K + 6 * S, sizeof(REAL) * S);   /* FSAL */
+            have_k1 = 1;
+            if (clipped) {
+                for (int k = 0; k < d; ++k) y[k] += dLdout[(size_t)isave * d + k];
+                --isave;
+                have_k1 = 0;                          /* the jump invalidates FSAL */
+            }
+        } else {
+            REAL qr = q11 / gamma;
+            if (qr > (REAL)1 / qmin) qr = (REAL)1 / qmin;
+            dt = h / qr;
+            have_k1 = 1;                              /* K[0] is still F(y, t) */
+        }
+    }
+    for (int k = 0; k < d; ++k) grad_u0[k] = y[k];
+    for (size_t q = 0; q < P; ++q) grad_theta[q] = y[d + q];
+    free(y); free(yn); free(K); free(gs);
+    return nsteps;
+}
+
 double FN(ude_ensemble_loss_grad)(const ude_model *m, const REAL *th, const REAL *u0, const REAL *y,
                                   const REAL *wmask, size_t N, REAL dt, int n_steps, int save_every,
                                   REAL *out, REAL *grad_theta, REAL *grad_u0, int n_threads)

@@ -330,3 +330,46 @@ def test_fisher_kpp_golden_forward(golden, O):
     assert (status == 0).all()
     assert np.abs(out[:, :, 0].T - g["Xhat"]).max() <= 5e-4
     solver.close()
+
+
+def test_adaptive_tsit5_forward_and_adjoint_vs_oracle(golden, O):
+    """abstol / reltol path (scenario_1.jl:85: abstol = reltol = 1e-6): PI-controlled Tsit5 per trajectory with saveat by
+    interpolation, and the interpolating adjoint replaying the accepted steps.  fp32 round-off can flip single
+    accept/reject decisions, so values are compared, not step sequences; tolerances = a few x the solver tolerance."""
+    ude = _ude()
+    g = golden["scenario_1"]
+    chain = ude.FastChain(ude.FastDense(2, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 2))
+    f = ude.LotkaVolterraUDE(chain)
+    theta = g["theta_trained"].astype(np.float32)
+    rng = np.random.default_rng(1)
+    N = 70
+    u0 = (g["X"][:, :1] * rng.uniform(0.8, 1.2, (2, N))).astype(np.float32)
+    ts = np.linspace(0.0, 3.0, 31)
+    tol = 1e-5
+    m = O.lv_model((2, 5, 5, 5, 2), ("rbf", "rbf", "rbf", "identity"))
+    y = rng.normal(size=(31, 2, N)).astype(np.float32)
+    solver = ude.UDESolver(f, 0.0, 0.1, 30, 1, max_trajectories=N, adaptive=True, abstol=tol, reltol=tol, max_steps=256)
+    out, loss, gth, gu, status = _run(solver, theta, u0, y)
+    assert (status == 0).all()
+    l_ref, g_ref, gu_ref = 0.0, np.zeros(87), np.zeros((2, N))
+    for k in range(N):
+        o64, rec = O.solve_adaptive_dense(m, theta.astype(np.float64), u0[:, k].astype(np.float64), ts, tol, tol)
+        assert np.abs(out[:, :, k] - o64).max() <= 50 * tol * (1 + np.abs(o64).max())
+        dl = 2 * (o64 - y[:, :, k])
+        l_ref += ((o64 - y[:, :, k]) ** 2).sum()
+        gk, guk = O.adjoint_replay(m, theta.astype(np.float64), ts, rec, dl)
+        g_ref += gk
+        gu_ref[:, k] = guk
+    assert abs(loss - l_ref) <= 1e-3 * abs(l_ref)
+    assert np.linalg.norm(gth - g_ref) <= 5e-3 * np.linalg.norm(g_ref)
+    assert np.abs(gu - gu_ref).max() <= 5e-3 * np.abs(gu_ref).max()
+    # the golden X-hat of the reference (Vern7 @ 1e-6) is reproduced by the adaptive GPU solve from the reference's own start
+    solver2 = ude.UDESolver(f, 0.0, 0.05, 60, 1, max_trajectories=2, adaptive=True, abstol=1e-6, reltol=1e-6, max_steps=512)
+    o2, st2 = solver2.solve_host(theta, np.repeat(g["X"][:, :1].astype(np.float32), 2, axis=1))
+    assert (st2 == 0).all() and np.abs(o2[:, :, 0].T - g["Xhat"]).max() <= 2e-4
+    # step budget exhausted -> status 2, no crash
+    solver3 = ude.UDESolver(f, 0.0, 0.1, 30, 1, max_trajectories=2, adaptive=True, abstol=1e-6, reltol=1e-6, max_steps=3)
+    _, st3 = solver3.solve_host(theta, u0[:, :2].copy())
+    assert (st3 == 2).all()
+    for sv in (solver, solver2, solver3):
+        sv.close()

@@ -37,8 +37,6 @@ def test_grid_from_saveat():
 def test_unsupported_requests_fail_loudly():
     chain = ude.FastChain(ude.FastDense(2, 32, ude.tanh), ude.FastDense(32, 32, ude.tanh), ude.FastDense(32, 2))
     prob = ude.ODEProblem(ude.LotkaVolterraUDE(chain), np.zeros(2), (0.0, 3.0), np.zeros(1218, np.float32))
-    with pytest.raises(NotImplementedError):
-        ude.concrete_solve(prob, ude.Tsit5(), saveat=0.1, adaptive=True)
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             ude.UDESolver(prob.f, 0.0, 0.1, 30)

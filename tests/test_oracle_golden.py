@@ -208,3 +208,26 @@ def test_fp32_oracle_close_to_fp64(O):
     l32, g32, gu32 = O.ensemble_loss_grad(m, theta, u0, y, np.ones(2, np.float32), 0.1, 30)
     assert abs(l32 - l64) < 1e-5 * l64
     assert np.linalg.norm(g32 - g64) < 1e-4 * np.linalg.norm(g64)
+
+
+def test_replay_adjoint_matches_error_controlled_backward_solve(O, golden):
+    """Adaptive solves: the adjoint that replays the accepted forward steps (what the GPU kernels do) agrees with a
+    reference-style error-controlled backward solve of the augmented state [lambda; mu] (tstops at the save times)
+    and with a fine fixed-grid adjoint, at the level of the solver tolerance."""
+    g = golden["scenario_1"]
+    m = O.lv_model((2, 5, 5, 5, 2), RBF3)
+    th = theta_scenario1_init(g)
+    X, ts = g["X"], g["t"]
+    sub = 32
+    out, dense = O.solve_fixed(m, th, X[:, 0], 0.1 / sub, 30 * sub, save_every=sub, want_dense=True)
+    g_true, gu_true = O.adjoint_fixed(m, th, out, dense, 0.1 / sub, 30 * sub, 2 * (out - X.T), save_every=sub)
+    n = np.linalg.norm
+    for tol, bound in ((1e-6, 5e-7), (1e-8, 2e-8)):
+        outa, rec = O.solve_adaptive_dense(m, th, X[:, 0], ts, tol, tol)
+        assert np.abs(outa - out).max() < 20 * tol
+        dl = 2 * (outa - X.T)
+        g_rep, gu_rep = O.adjoint_replay(m, th, ts, rec, dl)
+        g_ada, gu_ada, nback = O.adjoint_adaptive(m, th, ts, rec, dl, tol, tol)
+        assert nback > rec[3]                      # the backward solve takes its own (more) steps
+        assert n(g_rep - g_ada) < bound * n(g_ada) and n(g_rep - g_true) < bound * n(g_true)
+        assert n(gu_rep - gu_ada) < bound * n(gu_ada)

@@ -44,7 +44,8 @@ class Desc(C.Structure):
         ("t0", C.c_double), ("dt", C.c_double), ("n_steps", C.c_int32), ("save_every", C.c_int32),
         ("abstol", C.c_double), ("reltol", C.c_double),
         ("n_loss_weights", C.c_int32), ("loss_weights", C.c_double * 16),
-        ("max_trajectories", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("max_trajectories", C.c_uint64), ("flags", C.c_uint32), ("adaptive", C.c_int32), ("max_steps", C.c_int32),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -64,6 +64,12 @@ struct b200ude_handle {
     float *d_dense = nullptr;
     float *d_partial = nullptr;
     size_t partial_blocks = 0;
+    // adaptive stepping
+    bool adaptive = false;
+    float *d_tgrid = nullptr, *d_cot = nullptr, *d_block_loss = nullptr;
+    int *d_nacc = nullptr;
+    const float *last_out = nullptr;
+    AdaptiveGrid ag{};
     // host-buffer path
     float *d_u0 = nullptr, *d_out = nullptr, *d_data = nullptr, *d_gu0 = nullptr, *d_grad = nullptr, *d_loss = nullptr;
     int32_t *d_status = nullptr;
@@ -151,6 +157,14 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
     p.u0 = u0; p.out = out; p.ustep = h->d_ustep; p.dense = h->d_dense; p.status = status; p.theta = h->d_theta;
     p.N = (int)N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P; p.dt = (float)h->desc.dt;
     cudaError_t e = cudaSuccess;
+    if (h->adaptive) {
+        e = launch_fwd_adaptive(h->gen, h->tab, p, h->ag, st);
+        CUDA_TRY(h, e);
+        h->N = N;
+        h->have_forward = true;
+        h->last_out = out;
+        return B200UDE_OK;
+    }
     switch (h->kid) {
     case K_LV32: e = launch_fwd_lv32(h->var, h->tab, p, st); break;
     case K_LV5P0: e = launch_fwd_lv5(0, h->var, h->tab, p, st); break;
@@ -178,6 +192,17 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     p.dt = (float)h->desc.dt;
     cudaError_t e = cudaSuccess;
     int grid = 0;
+    if (h->adaptive) {
+        if (l2) {   // form the cotangent 2 w (out - data) from the interpolated saved states of the last forward
+            CUDA_TRY(h, launch_l2_cot(h->tab, h->last_out, cot, h->d_cot, h->d_block_loss, h->D, h->N, h->n_save, st));
+            p.cot = h->d_cot;
+            p.fused_l2 = 0;
+        }
+        CUDA_TRY(h, launch_adj_adaptive(h->gen, h->tab, p, h->ag, st, &grid));
+        CUDA_TRY(h, launch_reduce(h->d_partial, grid, h->P + 1, grad_theta, loss, st));
+        if (l2 && loss) CUDA_TRY(h, launch_l2_finish(h->d_block_loss, loss, st));
+        return B200UDE_OK;
+    }
     switch (h->kid) {
     case K_LV32: e = launch_adj_lv32(h->var, h->tab, p, st, &grid); break;
     case K_LV5P0: e = launch_adj_lv5(0, h->var, h->tab, p, st, &grid); break;
@@ -215,7 +240,14 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         return fail(nullptr, B200UDE_EINVAL, "create: need dt>0, n_steps>=1, save_every>=1 dividing n_steps");
     if (d->max_trajectories == 0 || d->max_trajectories > (1ull << 26)) return fail(nullptr, B200UDE_EINVAL, "create: max_trajectories out of range");
     if (d->n_loss_weights != 0 && d->n_loss_weights != d->state_dim) return fail(nullptr, B200UDE_EINVAL, "create: n_loss_weights must be 0 or state_dim");
-    const KernelId kid = pick_kernel(*d);
+    KernelId kid = pick_kernel(*d);
+    if (d->adaptive) {
+        if (!(d->abstol > 0) || !(d->reltol > 0) || d->max_steps < 1)
+            return fail(nullptr, B200UDE_EINVAL, "create: adaptive stepping needs abstol > 0, reltol > 0, max_steps >= 1");
+        if (!generic_ok(*d) || d->model == B200UDE_MODEL_FKPP)
+            return fail(nullptr, B200UDE_EUNSUPPORTED, "create: adaptive stepping is implemented for the LV / SEIR / NODE forms (chain widths <= 64)");
+        kid = K_GENERIC;   // adaptive solves run on the runtime-shape kernels
+    }
     if (kid == K_NONE)
         return fail(nullptr, B200UDE_EUNSUPPORTED,
                     "create: no sm_100a kernel for this model/chain (built: LV 2-32-32-2 tanh; LV 2-5-5-5-2; generic LV/SEIR/NODE chains with widths <= 64, <= 5 layers)");
@@ -239,6 +271,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->n_save = d->n_steps / d->save_every + 1;
     h->cap = (size_t)d->max_trajectories;
     h->sm_count = prop.multiProcessorCount;
+    h->adaptive = d->adaptive != 0;
     h->P = kernel_num_params(kid);
     if (kid == K_GENERIC || kid == K_FKPP) {
         int P = d->n_prefix + d->n_suffix;
@@ -263,8 +296,15 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : adj_grid_lv5((int)N));
     bool ok = true;
     ok = ok && dalloc(h, &h->d_theta, (size_t)((h->P + 3) / 4) * 4) == cudaSuccess;
-    ok = ok && dalloc(h, &h->d_ustep, (size_t)(d->n_steps + 1) * D * N) == cudaSuccess;
-    ok = ok && dalloc(h, &h->d_dense, (size_t)(d->n_steps * 6 + 1) * D * N) == cudaSuccess;
+    const size_t rec_steps = h->adaptive ? (size_t)d->max_steps : (size_t)d->n_steps;   // capacity of the step record
+    ok = ok && dalloc(h, &h->d_ustep, (rec_steps + 1) * D * N) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_dense, (rec_steps * 6 + 1) * D * N) == cudaSuccess;
+    if (h->adaptive) {
+        ok = ok && dalloc(h, &h->d_tgrid, (rec_steps + 1) * N) == cudaSuccess;
+        ok = ok && dalloc(h, &h->d_nacc, N) == cudaSuccess;
+        ok = ok && dalloc(h, &h->d_cot, (size_t)h->n_save * D * N) == cudaSuccess;
+        ok = ok && dalloc(h, &h->d_block_loss, (size_t)L2_BLOCKS) == cudaSuccess;
+    }
     ok = ok && dalloc(h, &h->d_partial, h->partial_blocks * (size_t)(h->P + 1)) == cudaSuccess;
     ok = ok && dalloc(h, &h->d_grad, (size_t)h->P) == cudaSuccess;
     ok = ok && dalloc(h, &h->d_loss, 1) == cudaSuccess;
@@ -284,6 +324,8 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         return B200UDE_ENOMEM;
     }
     h->tab.serial = ++g_serial;
+    h->ag.t0 = (float)d->t0; h->ag.save_dt = (float)(d->dt * d->save_every); h->ag.abstol = (float)d->abstol; h->ag.reltol = (float)d->reltol;
+    h->ag.n_save = h->n_save; h->ag.max_steps = d->max_steps; h->ag.tgrid = h->d_tgrid; h->ag.nacc = h->d_nacc;
     h->tab.d_theta = h->d_theta;
     h->tab.P = h->P;
     for (int i = 0; i < 16; ++i) {
@@ -301,6 +343,7 @@ void b200ude_destroy(b200ude_handle *h)
     cudaFree(h->d_theta); cudaFree(h->d_ustep); cudaFree(h->d_dense); cudaFree(h->d_partial);
     cudaFree(h->d_u0); cudaFree(h->d_out); cudaFree(h->d_data); cudaFree(h->d_gu0); cudaFree(h->d_grad);
     cudaFree(h->d_loss); cudaFree(h->d_status);
+    cudaFree(h->d_tgrid); cudaFree(h->d_nacc); cudaFree(h->d_cot); cudaFree(h->d_block_loss);
     if (h->h_loss) cudaFreeHost(h->h_loss);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);

@@ -60,6 +60,15 @@ struct GenericShape {
     int acts[8];
 };
 
+// adaptive stepping: save grid + tolerances + the per-trajectory record of accepted steps
+struct AdaptiveGrid {
+    float t0, save_dt, abstol, reltol;
+    int n_save, max_steps;
+    float *tgrid;   // [max_steps+1][N]
+    int *nacc;      // [N]
+};
+constexpr int L2_BLOCKS = 296;
+
 // launchers (one translation unit per kernel family; each owns its constant-bank symbols)
 cudaError_t launch_fwd_lv32(const Variant &, const ConstTables &, const FwdParams &, cudaStream_t);
 cudaError_t launch_adj_lv32(const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *grid_out);
@@ -70,6 +79,10 @@ int adj_grid_lv5(int N);
 cudaError_t launch_fwd_generic(const GenericShape &, const ConstTables &, const FwdParams &, cudaStream_t);
 cudaError_t launch_adj_generic(const GenericShape &, const ConstTables &, const AdjParams &, cudaStream_t, int *rows_out);
 int adj_rows_generic(int N);
+cudaError_t launch_fwd_adaptive(const GenericShape &, const ConstTables &, const FwdParams &, const AdaptiveGrid &, cudaStream_t);
+cudaError_t launch_adj_adaptive(const GenericShape &, const ConstTables &, const AdjParams &, const AdaptiveGrid &, cudaStream_t, int *rows_out);
+cudaError_t launch_l2_cot(const ConstTables &, const float *out, const float *data, float *cot, float *block_loss, int D, size_t N, int n_save, cudaStream_t);
+cudaError_t launch_l2_finish(const float *block_loss, float *loss, cudaStream_t);
 cudaError_t launch_fwd_fkpp(const GenericShape &, const ConstTables &, const FwdParams &, cudaStream_t);
 cudaError_t launch_adj_fkpp(const GenericShape &, const ConstTables &, const AdjParams &, cudaStream_t, int *rows_out);
 int adj_rows_fkpp(int N, int Nx);

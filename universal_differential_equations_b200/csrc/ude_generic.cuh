@@ -288,6 +288,231 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
 }
 
 // =====================================================================================================
+// Adaptive stepping (abstol / reltol as every reference call passes them: scenario_1.jl:85, seir_exposure.jl:139):
+// Tsit5 with OrdinaryDiffEq's default PI controller (gamma 0.9, qmin 1/5, qmax 10, beta1 7/50, beta2 2/25,
+// steady band [1, 1.2], Hairer initial step), one trajectory per thread with its own dt; saveat values come from
+// the free 4th-order interpolant and do not alter the steps.  Every ACCEPTED step is recorded
+// (tgrid, ustep, dense) so that the interpolating adjoint can replay the steps backwards, splitting them at
+// the save times where the loss cotangent jumps in (oracle: ude_adjoint_replay; validated there against an
+// error-controlled backward solve of [lambda; mu]).
+// =====================================================================================================
+struct AdaptParams {
+    float t0, save_dt, abstol, reltol;
+    int n_save, max_steps;
+    float *tgrid;     // [max_steps+1][N]
+    int *nacc;        // [N]
+};
+
+__device__ __forceinline__ void tsit5_bw_rt(float Th, float *bw)
+{
+    bw[0] = Th * ((float)Tsit5::r(0, 1) + Th * ((float)Tsit5::r(0, 2) + Th * ((float)Tsit5::r(0, 3) + Th * (float)Tsit5::r(0, 4))));
+#pragma unroll
+    for (int j = 1; j < 7; ++j) bw[j] = Th * Th * ((float)Tsit5::r(j, 2) + Th * ((float)Tsit5::r(j, 3) + Th * (float)Tsit5::r(j, 4)));
+}
+__device__ __forceinline__ float tsit5_btilde(int j)
+{
+    return j == 0 ? -0.001780011052225777f : j == 1 ? -0.0008164344596567469f : j == 2 ? 0.007880878010261995f
+         : j == 3 ? -0.1447110071732629f : j == 4 ? 0.5823571654525552f : j == 5 ? -0.45808210592918697f : 0.015151515151515152f;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) adaptive_forward_kernel(FwdParams p, AdaptParams ap)
+{
+    const int D = c_gen.D;
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    if (gid >= p.N) return;
+    const size_t n = (size_t)gid;
+    const float t0 = ap.t0, t1 = ap.t0 + ap.save_dt * (float)(ap.n_save - 1);
+    const float abstol = ap.abstol, reltol = ap.reltol;
+    const float gamma = 0.9f, qmin = 0.2f, qmax = 10.0f, beta1 = 7.0f / 50.0f, beta2 = 2.0f / 25.0f;
+    float u[MAXD], un[MAXD], g[MAXD], k[7][MAXD];
+    for (int c = 0; c < D; ++c) u[c] = __ldg(p.u0 + (size_t)c * N + n);
+    auto store = [&](float *base, int row, const float *v) {
+        for (int c = 0; c < D; ++c) base[((size_t)row * D + c) * N + n] = v[c];
+    };
+    store(p.out, 0, u);
+    store(p.ustep, 0, u);
+    ap.tgrid[n] = t0;
+    model_rhs(u, k[0]);
+    store(p.dense, 0, k[0]);
+    // initial step: Hairer-Norsett-Wanner as in OrdinaryDiffEq
+    float dt;
+    {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        for (int c = 0; c < D; ++c) {
+            const float sk = abstol + reltol * fabsf(u[c]);
+            d0 += (u[c] / sk) * (u[c] / sk);
+            d1 += (k[0][c] / sk) * (k[0][c] / sk);
+        }
+        d0 = sqrtf(d0 / D); d1 = sqrtf(d1 / D);
+        float dt0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+        dt0 = fminf(dt0, t1 - t0);
+        for (int c = 0; c < D; ++c) g[c] = fmaf(dt0, k[0][c], u[c]);
+        model_rhs(g, un);
+        for (int c = 0; c < D; ++c) {
+            const float sk = abstol + reltol * fabsf(u[c]);
+            const float e = (un[c] - k[0][c]) / sk;
+            d2 += e * e;
+        }
+        d2 = sqrtf(d2 / D) / dt0;
+        const float dm = fmaxf(d1, d2);
+        const float dt1 = dm <= 1e-15f ? fmaxf(1e-6f, dt0 * 1e-3f) : exp10f(-(2.0f + log10f(dm)) / 5.0f);
+        dt = fminf(fminf(100.0f * dt0, dt1), t1 - t0);
+    }
+    float t = t0, qold = 1e-4f;
+    int nacc = 0, isave = 1, bad = 0;
+    while (isave < ap.n_save) {
+        float h = dt;
+        bool clipped = false;
+        if (t + h >= t1 - 1e-6f * fabsf(t1)) { h = t1 - t; clipped = true; }
+#pragma unroll
+        for (int i = 1; i < 7; ++i) {
+            for (int c = 0; c < D; ++c) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                    if (Tsit5::a(i, j) != 0.0) acc = fmaf((float)Tsit5::a(i, j), k[j][c], acc);
+                g[c] = fmaf(h, acc, u[c]);
+            }
+            if (i == 6) for (int c = 0; c < D; ++c) un[c] = g[c];
+            model_rhs(g, k[i]);
+        }
+        float ee = 0.0f;
+        for (int c = 0; c < D; ++c) {
+            float e = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) e = fmaf(tsit5_btilde(j), k[j][c], e);
+            e *= h;
+            const float sc = abstol + reltol * fmaxf(fabsf(u[c]), fabsf(un[c]));
+            ee += (e / sc) * (e / sc);
+        }
+        const float EEst = sqrtf(ee / D);
+        if (!(EEst <= 3.0e38f)) { bad = 1; break; }   // NaN / Inf
+        const float q11 = powf(EEst, beta1);
+        float q = fminf(fmaxf(q11 / powf(qold, beta2) / gamma, 1.0f / qmax), 1.0f / qmin);
+        if (EEst <= 1.0f) {
+            if (nacc >= ap.max_steps) { bad = 2; break; }
+            const float tn = clipped ? t1 : t + h;
+            // dense record of this step: k_1..k_6 at rows nacc*6 + i, k_7 at (nacc+1)*6 (= k_1 of the next step)
+            for (int i = 1; i < 7; ++i) store(p.dense, nacc * 6 + i, k[i]);
+            while (isave < ap.n_save) {
+                const float ts = t0 + ap.save_dt * (float)isave;
+                if (ts > tn + 1e-6f * fabsf(tn)) break;
+                float bw[7];
+                tsit5_bw_rt(fminf((ts - t) / h, 1.0f), bw);
+                for (int c = 0; c < D; ++c) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc = fmaf(bw[j], k[j][c], acc);
+                    p.out[((size_t)isave * D + c) * N + n] = fmaf(h, acc, u[c]);
+                }
+                ++isave;
+            }
+            qold = fmaxf(EEst, 1e-4f);
+            if (q >= 1.0f && q <= 1.2f) q = 1.0f;
+            if (!clipped || h >= dt) dt = h / q;
+            else dt = fmaxf(dt, h / q);
+            t = tn;
+            ++nacc;
+            ap.tgrid[(size_t)nacc * N + n] = t;
+            for (int c = 0; c < D; ++c) { u[c] = un[c]; k[0][c] = k[6][c]; }
+            store(p.ustep, nacc, u);
+        } else {
+            dt = h / fminf(1.0f / qmin, q11 / gamma);
+        }
+    }
+    ap.nacc[n] = nacc;
+    if (p.status) {
+        bool ok = true;
+        for (int c = 0; c < D; ++c) ok = ok && (fabsf(u[c]) <= 3.0e38f);
+        p.status[n] = bad == 2 ? 2 : ((bad || !ok) ? 1 : 0);
+    }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) adaptive_adjoint_kernel(AdjParams p, AdaptParams ap)
+{
+    extern __shared__ __align__(16) float s_g[];   // [BLOCK/32][P+1]
+    const int D = c_gen.D, P = c_gen.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *gw = s_g + (size_t)warp * (P + 1);
+    for (int q = lane; q < P + 1; q += 32) gw[q] = 0.0f;
+    __syncwarp();
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = gid < p.N;
+    const size_t n = live ? (size_t)gid : (size_t)(p.N - 1);
+    const int nacc = ap.nacc[n];
+    int nmax = live ? nacc : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    float lam[MAXD], x[MAXD], g[MAXD], kl[6][MAXD], un_[MAXD];
+    float loss = 0.0f;
+    for (int c = 0; c < D; ++c) lam[c] = 0.0f;
+    int isave = ap.n_save - 1;
+    auto jump = [&](int is) {
+        for (int c = 0; c < D; ++c) {
+            const size_t idx = ((size_t)is * D + c) * N + n;
+            lam[c] += __ldg(p.cot + idx);
+        }
+    };
+    if (live) jump(isave);
+    --isave;
+    for (int s = nmax - 1; s >= 0; --s) {
+        const bool act_s = live && s < nacc;
+        const int sc_ = act_s ? s : 0;                 // inactive lanes shadow step 0 (finite data), weight 0
+        const float tn = ap.tgrid[(size_t)sc_ * N + n], tn1 = ap.tgrid[(size_t)(sc_ + 1) * N + n], hn = tn1 - tn;
+        const float eps = 1e-5f * hn;
+        for (int c = 0; c < D; ++c) un_[c] = __ldg(p.ustep + ((size_t)sc_ * D + c) * N + n);
+        float cur = tn1;
+        while (true) {
+            const bool has = act_s && cur > tn + eps;
+            if (!__any_sync(0xffffffffu, has)) break;
+            float ta = tn;
+            const float ts = ap.t0 + ap.save_dt * (float)isave;
+            if (has && isave >= 0 && ts > tn + eps) ta = ts;
+            const float h = has ? cur - ta : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                float bw[7];
+                const float Th = fminf(fmaxf((cur - (float)Tsit5::c(i) * h - tn) / hn, 0.0f), 1.0f);
+                tsit5_bw_rt(Th, bw);
+                for (int c = 0; c < D; ++c) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc = fmaf(bw[j], __ldg(p.dense + ((size_t)(sc_ * 6 + j) * D + c) * N + n), acc);
+                    x[c] = fmaf(hn, acc, un_[c]);
+                    float a2 = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < i; ++j)
+                        if (Tsit5::a(i, j) != 0.0) a2 = fmaf((float)Tsit5::a(i, j), kl[j][c], a2);
+                    g[c] = fmaf(h, a2, lam[c]);
+                }
+                model_vjp(x, g, h * (float)Tsit5::b(i), has ? 1.0f : 0.0f, kl[i], gw, lane);
+            }
+            if (has) {
+                for (int c = 0; c < D; ++c) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) acc = fmaf((float)Tsit5::b(j), kl[j][c], acc);
+                    lam[c] = fmaf(h, acc, lam[c]);
+                }
+                cur = ta;
+                if (isave >= 0 && fabsf(ts - ta) <= eps) { jump(isave); --isave; }
+            }
+        }
+    }
+    if (p.grad_u0 && live)
+        for (int c = 0; c < D; ++c) p.grad_u0[(size_t)c * N + n] = lam[c];
+    if (lane == 0) gw[P] = 0.0f;   // the adaptive path takes a generic cotangent; no fused loss
+    (void)loss;
+    __syncwarp();
+    float *dst = p.partial + ((size_t)blockIdx.x * (BLOCK / 32) + warp) * (P + 1);
+    for (int q = lane; q < P + 1; q += 32) dst[q] = gw[q];
+}
+
+// =====================================================================================================
 // Fisher-KPP UPDE (FisherKPP/Fisher-KPP-CNN.jl:111-126, LotkaVolterra/scenario_3.jl:103-114):
 //   du_i = NN(u_i) + D0 * (w1 u_{i-1} + w2 u_i + w3 u_{i+1}),  periodic, theta = [chain | w1 w2 w3 b | D0].
 // One thread per grid point; a CTA holds `tpc` whole trajectories (tpc * Nx threads, rounded up to a warp

@@ -235,7 +235,8 @@ class UDESolver:
     """One C-ABI handle: a UDE form, a fixed Tsit5 grid and a capacity of trajectories."""
 
     def __init__(self, f, t0, dt, n_steps, save_every=1, max_trajectories=1, device=None,
-                 loss_weights=None, alg=None, sensealg=None, approx_tanh=False):
+                 loss_weights=None, alg=None, sensealg=None, approx_tanh=False, adaptive=False, abstol=1e-6, reltol=1e-3,
+                 max_steps=512):
         alg = alg or Tsit5()
         sensealg = sensealg or InterpolatingAdjoint()
         if isinstance(sensealg, ForwardDiffSensitivity):
@@ -274,6 +275,9 @@ class UDESolver:
                 d.loss_weights[i] = float(w)
         d.max_trajectories = int(max_trajectories)
         d.flags = _lib.FLAG_APPROX_TANH if approx_tanh else 0
+        # adaptive = true: OrdinaryDiffEq's defaults abstol = 1e-6, reltol = 1e-3 when the kwargs are omitted (Fisher-KPP-CNN.jl:136)
+        d.adaptive = 1 if adaptive else 0
+        d.abstol, d.reltol, d.max_steps = float(abstol), float(reltol), int(max_steps)
         self._L = _lib.lib()
         h = C.c_void_p()
         rc = self._L.b200ude_create(C.byref(d), C.byref(h))
@@ -409,18 +413,17 @@ def _grid_from(tspan, saveat, dt):
     return t0, float(dt), n_steps, save_every
 
 
-def concrete_solve(prob, alg, u0=None, p=None, *, saveat=None, dt=None, adaptive=False, abstol=None, reltol=None,
-                   sensealg=None, loss_weights=None):
+def concrete_solve(prob, alg, u0=None, p=None, *, saveat=None, dt=None, adaptive=None, abstol=None, reltol=None,
+                   sensealg=None, loss_weights=None, max_steps=512):
     """Array(concrete_solve(prob, Tsit5(), u0, p; saveat, sensealg=InterpolatingAdjoint(...))).
 
     `prob` may be an ODEProblem (u0[d] -> d x n_save, like Julia's Array(sol)) or an
     EnsembleProblem (u0s[d, N] -> n_save x d x N).  Differentiable w.r.t. p and u0.
-    Only adaptive=false (fixed dt) is implemented on the device in this version.
+    adaptive defaults to true when no dt is given (as in OrdinaryDiffEq): Tsit5 with the PI controller and
+    abstol / reltol (defaults 1e-6 / 1e-3); pass dt= for adaptive=false.
     """
     ens = isinstance(prob, EnsembleProblem)
     base = prob.prob if ens else prob
-    if adaptive:
-        raise NotImplementedError("adaptive stepping is not implemented on the device yet; pass dt= (adaptive=false)")
     u0 = (prob.u0s if ens else base.u0) if u0 is None else u0
     p = base.p if p is None else p
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -432,13 +435,18 @@ def concrete_solve(prob, alg, u0=None, p=None, *, saveat=None, dt=None, adaptive
         pt = pt.to(dev, torch.float32)
     t0, dtv, n_steps, save_every = _grid_from(base.tspan, saveat, dt)
     N = u0t.shape[1]
-    key = (id(base.f), t0, dtv, n_steps, save_every, type(alg).__name__, dev.index, tuple(loss_weights) if loss_weights else None)
+    if adaptive is None:
+        adaptive = dt is None
+    abstol = 1e-6 if abstol is None else abstol
+    reltol = 1e-3 if reltol is None else reltol
+    key = (id(base.f), t0, dtv, n_steps, save_every, type(alg).__name__, dev.index, tuple(loss_weights) if loss_weights else None,
+           bool(adaptive), abstol, reltol, max_steps)
     solver = _SOLVERS.get(key)
     if solver is None or solver.capacity < N:
         if solver is not None:
             solver.close()
         solver = UDESolver(base.f, t0, dtv, n_steps, save_every, max_trajectories=max(N, 1), device=dev, alg=alg,
-                           sensealg=sensealg, loss_weights=loss_weights)
+                           sensealg=sensealg, loss_weights=loss_weights, adaptive=adaptive, abstol=abstol, reltol=reltol, max_steps=max_steps)
         _SOLVERS[key] = solver
     out = _SolveFn.apply(pt, u0t, solver)
     return out if ens else out[:, :, 0].transpose(0, 1)
