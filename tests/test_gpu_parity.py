@@ -127,7 +127,7 @@ def test_autograd_concrete_solve_matches_adjoint(O):
     f = _lv32(ude)
     prob = ude.EnsembleProblem(ude.ODEProblem(f, None, (0.0, 3.0), None), torch.from_numpy(u0).cuda())
     p = torch.from_numpy(theta).cuda().requires_grad_(True)
-    pred = ude.concrete_solve(prob, ude.Tsit5(), p=p, saveat=0.1, sensealg=ude.InterpolatingAdjoint(autojacvec=ude.ReverseDiffVJP()))
+    pred = ude.concrete_solve(prob, ude.Tsit5(), p=p, saveat=0.1, dt=0.1, sensealg=ude.InterpolatingAdjoint(autojacvec=ude.ReverseDiffVJP()))
     loss = ((pred - torch.from_numpy(y).cuda()) ** 2).sum()
     loss.backward()
     m = O.lv_model()
