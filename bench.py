@@ -267,7 +267,7 @@ def main():
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
         "traffic": 131.5e6 * (n / 65536.0),
         "traffic_source": "ncu --set full capture of this kernel at N=65536: dram read 127.5 MB + write 4.0 MB (profiles/r01_ncu_kernel_summaries.txt); algorithmic bytes %.1f MB" % (65536 * BYTES_ADJ / 1e6),
-        "note": "the path is FP32-FMA-bound by construction (SURVEY.md 8d): see roofline_fp32 for the binding roofline",
+        "note": "the path is compute-bound by construction (SURVEY.md 8d, ~430 FLOP/B): roofline_fp32 (CUDA-core FP32 peak, which the tensor-core kernels bypass for the 32x32 layers) and roofline_xu (MUFU, the nearest bound of the tensor-core forward kernel) are the informative ones",
     }
     roofline_fp32 = {
         "kernel_adjoint": {"achieved": n * FLOP_ADJ / (adj_ms * 1e-3) / 1e12, "ms": adj_ms},
@@ -278,6 +278,15 @@ def main():
         "frac_step": n * (FLOP_FWD + FLOP_ADJ) / (float(np.mean(t_step)) * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
         "peak_source": "measured FFMA2 issue peak, tools/microbench/pipes.cu on this pool (profiles/r01_pipes_microbench.txt)",
         "flop_per_trajectory": FLOP_FWD + FLOP_ADJ,
+    }
+    # MUFU (XU pipe) roofline: 2 MUFU per tanh, 64 tanh per chain evaluation; measured peak 16 lanes/clk/SM
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    xu_peak = 148 * 16 * sm_clock * 1e6
+    roofline_xu = {
+        "forward": {"achieved": n * 128.0 * (1 + 6 * N_STEPS) / (fwd_ms * 1e-3), "frac": n * 128.0 * (1 + 6 * N_STEPS) / (fwd_ms * 1e-3) / xu_peak},
+        "adjoint": {"achieved": n * 128.0 * 6 * N_STEPS / (adj_ms * 1e-3), "frac": n * 128.0 * 6 * N_STEPS / (adj_ms * 1e-3) / xu_peak},
+        "peak": xu_peak, "unit": "MUFU op/s",
+        "peak_source": "16 MUFU lanes/clk/SM measured by tools/microbench/pipes.cu (profiles/r01_pipes_microbench.txt) x 148 SMs x sampled SM clock",
     }
     cpu = None
     if not a.no_cpu_baseline:
@@ -296,7 +305,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "b200ude_loss_gradient_host: pinned host theta/u0/data -> H2D -> kernels -> D2H grad+loss, wall clock"},
         "gpu_launches": 3 * a.steps, "kernels_per_step": ["lv32::tc::forward_kernel", "lv32::tc::adjoint_kernel", "ude_reduce_kernel"],
-        "clocks": clocks, "roofline": roofline, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "roofline_fp32": roofline_fp32, "roofline_xu": roofline_xu, "cpu_baseline": cpu,
         "kernel_ms": {"forward": fwd_ms, "adjoint_plus_reduce": adj_ms, "step": float(np.mean(t_step))},
     }
     print(json.dumps(line))
