@@ -373,3 +373,26 @@ def test_adaptive_tsit5_forward_and_adjoint_vs_oracle(golden, O):
     assert (st3 == 2).all()
     for sv in (solver, solver2, solver3):
         sv.close()
+
+
+def test_vern7_fixed_step_forward_vs_oracle(golden, O):
+    """solve(prob, Vern7(); saveat, adaptive=false): 9-stage 7th-order steps on the generic kernels vs the oracle's
+    Vern7 (tableau = OrdinaryDiffEq's serialized constants, KAT-7); the adjoint of a Vern7 handle is rejected."""
+    ude = _ude()
+    from universal_differential_equations_b200._lib import B200UDEError, EUNSUPPORTED
+    g = golden["scenario_1"]
+    chain = ude.FastChain(ude.FastDense(2, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 2))
+    f = ude.LotkaVolterraUDE(chain)
+    theta = g["theta_trained"].astype(np.float32)
+    solver = ude.UDESolver(f, 0.0, 0.05, 60, 1, max_trajectories=8, alg=ude.Vern7())
+    u0 = np.repeat(g["X"][:, :1].astype(np.float32), 5, axis=1)
+    out, status = solver.solve_host(theta, u0)
+    m = O.lv_model((2, 5, 5, 5, 2), ("rbf", "rbf", "rbf", "identity"))
+    ref = O.solve_fixed(m, g["theta_trained"], g["X"][:, 0], 0.05, 60, solver=O.VERN7)
+    assert (status == 0).all()
+    assert np.abs(out[:, :, 0] - ref).max() <= 2e-5 * (1 + np.abs(ref).max())
+    assert np.abs(out[:, :, 0].T - g["Xhat"]).max() <= 2e-4      # the reference's own Vern7 solution
+    with pytest.raises(B200UDEError) as e:
+        solver.adjoint(torch.zeros(61, 2, 5, device="cuda"))
+    assert e.value.code == EUNSUPPORTED
+    solver.close()

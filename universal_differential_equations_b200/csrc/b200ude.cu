@@ -157,6 +157,12 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
     p.u0 = u0; p.out = out; p.ustep = h->d_ustep; p.dense = h->d_dense; p.status = status; p.theta = h->d_theta;
     p.N = (int)N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P; p.dt = (float)h->desc.dt;
     cudaError_t e = cudaSuccess;
+    if (h->desc.solver == B200UDE_VERN7) {
+        CUDA_TRY(h, launch_fwd_vern7(h->gen, h->tab, p, st));
+        h->N = N;
+        h->have_forward = false;   // no dense output is recorded: the adjoint of a Vern7 solve is not available
+        return B200UDE_OK;
+    }
     if (h->adaptive) {
         e = launch_fwd_adaptive(h->gen, h->tab, p, h->ag, st);
         CUDA_TRY(h, e);
@@ -183,6 +189,8 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
 int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, float *grad_theta,
                    float *grad_u0, cudaStream_t st)
 {
+    if (h->desc.solver == B200UDE_VERN7)
+        return fail(h, B200UDE_EUNSUPPORTED, "adjoint: the interpolating adjoint needs Vern7's dense output, which this build does not have; use Tsit5");
     if (!h->have_forward) return fail(h, B200UDE_ESTATE, "adjoint: no stored forward solution (call b200ude_forward first)");
     if (!cot || !grad_theta) return fail(h, B200UDE_EINVAL, "adjoint: null pointer");
     AdjParams p;
@@ -234,13 +242,18 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         return fail(nullptr, B200UDE_EINVAL, "create: struct_size %u != %zu (ABI mismatch)", d->struct_size, sizeof(b200ude_desc));
     if (d->dtype != B200UDE_F32) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only B200UDE_F32 kernels exist in this build");
     if (d->n_layers < 1 || d->n_layers > B200UDE_MAX_LAYERS) return fail(nullptr, B200UDE_EINVAL, "create: n_layers=%d out of range", d->n_layers);
-    if (d->solver != B200UDE_TSIT5) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only Tsit5 has a kernel in this build");
+    if (d->solver != B200UDE_TSIT5 && d->solver != B200UDE_VERN7) return fail(nullptr, B200UDE_EINVAL, "create: unknown solver %d", d->solver);
     if (d->sensealg != B200UDE_INTERPOLATING_ADJOINT) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: unknown sensealg %d", d->sensealg);
     if (!(d->dt > 0) || d->n_steps < 1 || d->save_every < 1 || d->n_steps % d->save_every != 0)
         return fail(nullptr, B200UDE_EINVAL, "create: need dt>0, n_steps>=1, save_every>=1 dividing n_steps");
     if (d->max_trajectories == 0 || d->max_trajectories > (1ull << 26)) return fail(nullptr, B200UDE_EINVAL, "create: max_trajectories out of range");
     if (d->n_loss_weights != 0 && d->n_loss_weights != d->state_dim) return fail(nullptr, B200UDE_EINVAL, "create: n_loss_weights must be 0 or state_dim");
     KernelId kid = pick_kernel(*d);
+    if (d->solver == B200UDE_VERN7) {
+        if (d->adaptive || !generic_ok(*d) || d->model == B200UDE_MODEL_FKPP)
+            return fail(nullptr, B200UDE_EUNSUPPORTED, "create: Vern7 has a fixed-step forward kernel for the LV / SEIR / NODE forms only");
+        kid = K_GENERIC;
+    }
     if (d->adaptive) {
         if (!(d->abstol > 0) || !(d->reltol > 0) || d->max_steps < 1)
             return fail(nullptr, B200UDE_EINVAL, "create: adaptive stepping needs abstol > 0, reltol > 0, max_steps >= 1");

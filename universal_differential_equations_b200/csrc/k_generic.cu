@@ -51,6 +51,16 @@ cudaError_t launch_adj_generic(const GenericShape &g, const ConstTables &t, cons
     return cudaGetLastError();
 }
 
+cudaError_t launch_fwd_vern7(const GenericShape &g, const ConstTables &t, const FwdParams &p, cudaStream_t st)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    e = upload_gen(g, st);
+    if (e != cudaSuccess) return e;
+    generic::vern7_forward_kernel<GEN_BLOCK><<<(p.N + GEN_BLOCK - 1) / GEN_BLOCK, GEN_BLOCK, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 // ---- adaptive stepping ----
 cudaError_t launch_fwd_adaptive(const GenericShape &g, const ConstTables &t, const FwdParams &p, const AdaptiveGrid &ag, cudaStream_t st)
 {

@@ -10,6 +10,7 @@
 // kernels are ~10-30x slower per FLOP than lv32::tc and are reported as such.
 #pragma once
 #include "ude_adjoint.cuh"
+#include "vern7.cuh"
 
 namespace b200ude {
 namespace generic {
@@ -137,6 +138,55 @@ __global__ void __launch_bounds__(BLOCK, 1) forward_kernel(FwdParams p)
         store(p.ustep, s + 1, u);
         if ((s + 1) % p.save_every == 0) { store(p.out, isave, u); ++isave; }
         for (int c = 0; c < D; ++c) k[0][c] = k[6][c];
+    }
+    if (p.status) {
+        bool ok = true;
+        for (int c = 0; c < D; ++c) ok = ok && (fabsf(u[c]) <= 3.0e38f);
+        p.status[n] = ok ? 0 : 1;
+    }
+}
+
+// Vern7 fixed-step forward solve (solve(prob, Vern7(); saveat, adaptive = false)): 9 stages per step, no FSAL.
+// Forward only: the interpolating adjoint of a Vern7 solve needs Vern7's lazy 7th-order dense output, whose
+// coefficients are not recoverable from the reference's artefacts, so the adjoint call on a
+// Vern7 handle is rejected with B200UDE_EUNSUPPORTED.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) vern7_forward_kernel(FwdParams p)
+{
+    const int D = c_gen.D;
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    if (gid >= p.N) return;
+    const size_t n = (size_t)gid;
+    const float dt = p.dt;
+    float u[MAXD], g[MAXD], k[9][MAXD];
+    for (int c = 0; c < D; ++c) u[c] = __ldg(p.u0 + (size_t)c * N + n);
+    for (int c = 0; c < D; ++c) p.out[(size_t)c * N + n] = u[c];
+    int isave = 1;
+    for (int s = 0; s < p.n_steps; ++s) {
+        model_rhs(u, k[0]);
+#pragma unroll
+        for (int i = 1; i < 9; ++i) {
+            for (int c = 0; c < D; ++c) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                    if (Vern7::a(i, j) != 0.0) acc = fmaf((float)Vern7::a(i, j), k[j][c], acc);
+                g[c] = fmaf(dt, acc, u[c]);
+            }
+            model_rhs(g, k[i]);
+        }
+        for (int c = 0; c < D; ++c) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (Vern7::b(j) != 0.0) acc = fmaf((float)Vern7::b(j), k[j][c], acc);
+            u[c] = fmaf(dt, acc, u[c]);
+        }
+        if ((s + 1) % p.save_every == 0) {
+            for (int c = 0; c < D; ++c) p.out[((size_t)isave * D + c) * N + n] = u[c];
+            ++isave;
+        }
     }
     if (p.status) {
         bool ok = true;
