@@ -288,6 +288,40 @@ def test_seir_exposure_ude_vs_oracle(O):
     solver.close()
 
 
+@pytest.mark.parametrize("N", [1, 129, 300, 1000])
+def test_seir_tensor_core_vs_runtime_shape_kernels(N, monkeypatch):
+    """The tuned SEIR kernels (k_seir.cu: tcgen05 3xTF32 sweeps, two 128-trajectory groups per CTA) against the
+    runtime-shape kernels (k_generic.cu) on ragged ensemble sizes, incl. a non-trivial cotangent path (adjoint with
+    an explicit dL/dout) and grad_u0.  Both are fp32; they differ only in summation order / the 3xTF32 split."""
+    ude = _ude()
+    rng = np.random.default_rng(N)
+    chain = ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1))
+    f = ude.SEIRExposureUDE(chain)
+    theta = glorot_theta((3, 64, 64, 1), seed=5)
+    S0 = 14e6
+    u0 = np.zeros((7, N), np.float32)
+    u0[0] = 0.9 * S0 * rng.uniform(0.9, 1.0, N)
+    u0[1:4] = rng.uniform(0, 50, (3, N)); u0[4] = S0; u0[5] = rng.uniform(0, 10, N); u0[6] = rng.uniform(0, 100, N)
+    y = rng.uniform(0, 100, (8, 7, N)).astype(np.float32)
+    cot = rng.standard_normal((8, 7, N)).astype(np.float32)
+    res = []
+    for tc in ("1", "0"):
+        monkeypatch.setenv("B200UDE_SEIR_TC", tc)
+        solver = ude.UDESolver(f, 0.0, 0.25, 28, 4, max_trajectories=N, loss_weights=[0, 1, 1, 1, 0, 0, 0])
+        out, loss, g, gu, status = _run(solver, theta, u0, y)
+        g2, gu2 = solver.adjoint(torch.from_numpy(cot).cuda(), want_grad_u0=True)
+        torch.cuda.synchronize()
+        res.append((out, loss, g, gu, g2.cpu().numpy(), gu2.cpu().numpy()))
+        assert (status == 0).all()
+        solver.close()
+    a, b = res
+    scale = np.abs(b[0]).max(axis=(0, 2), keepdims=True)
+    assert np.all(np.abs(a[0] - b[0]) <= 2e-6 * scale + 1e-4)
+    assert abs(a[1] - b[1]) <= 1e-5 * abs(b[1])
+    for k in (2, 3, 4, 5):
+        assert np.linalg.norm(a[k] - b[k]) <= 2e-4 * np.linalg.norm(b[k]), k
+
+
 @pytest.mark.parametrize("widths,acts,nx,N", [((1, 10, 20, 10, 1), ("tanh", "tanh", "tanh", "identity"), 26, 37),
                                              ((1, 5, 5, 5, 1), ("rbf", "rbf", "rbf", "identity"), 26, 5),
                                              ((1, 16, 16, 1), ("tanh", "tanh", "identity"), 256, 3)])

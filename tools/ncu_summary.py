@@ -17,16 +17,20 @@ WANT = [
 ]
 STALL = "smsp__pcsamp_warps_issue_stalled_"
 
-for rep in sys.argv[1:]:
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    h, units, v = rows[0], rows[1], rows[-1]
-    print(f"== {rep}")
-    name_i = h.index("Kernel Name")
-    print("kernel:", v[name_i])
+
+def summarise(h, units, v):
+    print("kernel:", v[h.index("Kernel Name")])
     for i, n in enumerate(h):
         if n in WANT:
             print(f"  {n:75s} {v[i]:>18s} {units[i]}")
     stalls = {n[len(STALL):]: int(float(v[i])) for i, n in enumerate(h) if n.startswith(STALL) and not n.endswith("_not_issued")}
     tot = sum(stalls.values()) or 1
     print("  warp-state samples (share):", ", ".join(f"{k} {100 * c / tot:.1f}%" for k, c in sorted(stalls.items(), key=lambda x: -x[1]) if c > 0.01 * tot))
+
+
+for rep in sys.argv[1:]:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    print(f"== {rep}")
+    for v in rows[2:]:
+        summarise(rows[0], rows[1], v)

@@ -1,0 +1,540 @@
+// seir_tc.cuh -- tensor-core kernels of the SEIR exposure UDE (SEIR_exposure/seir_exposure.jl:114-130):
+// 7 states (S, E, I, R, N, D, C), chain 3 -> 64 -> 64 -> 1 (tanh, tanh, linear) on [S/N, I, D/N], P = 4481.
+//
+// Same building block as lv32_tc.cuh, one size up: the 64 x 64 layer of the 128 trajectories of a GROUP is a
+// [128 x 64] x [64 x 64] tcgen05 GEMM with the 3xTF32 split (24 UTCHMMA of N = 64), activations written to / read
+// from tensor memory by the thread that owns the trajectory.  A CTA holds TWO independent groups (256 threads)
+// that share the 64 KB of staged weights (W2 hi/lo in both orientations); each group has its own TMEM columns
+// (accumulator 64 + A_hi 64 + A_lo 64), mbarrier, named barrier and staging buffers.  One CTA per SM
+// (204 KB shared memory, all 512 TMEM columns).
+// Adjoint: the two sweeps (chain forward, W2^T q2) on the tensor core; the ensemble-summed dW2 += q2 (x) h1
+// (64 x 64 outputs, K = the group's 128 trajectories) is an FFMA2 outer-product GEMM over conflict-free 128-bit
+// shared-memory rows with an 8 x 4 register tile per thread, run while the second sweep's MMAs are in flight;
+// the thin layers are thread-owned column sums.  Deterministic: per-group partials, fixed-order final reduce.
+#pragma once
+#include "lv32_tc.cuh"
+
+namespace b200ude {
+namespace seir {
+
+using lv32::ldw4;
+using lv32::bc;
+using lv32::fma2;
+using namespace lv32::tc;   // low-level tcgen05 helpers (mma_ts, make_desc, tf32_rna, mbar_wait, fences, ...)
+
+constexpr int D = 7, DIN = 3, HS = 64;
+constexpr int OFF_W1 = 0;               // W1[j, m] at m*64 + j
+constexpr int OFF_B1 = 3 * HS;          // 192
+constexpr int OFF_W2 = OFF_B1 + HS;     // 256, W2[j, i] at i*64 + j
+constexpr int OFF_B2 = OFF_W2 + HS * HS; // 4352
+constexpr int OFF_W3 = OFF_B2 + HS;     // 4416, W3[0, j] at j
+constexpr int OFF_B3 = OFF_W3 + HS;     // 4480
+constexpr int PS = OFF_B3 + 1;          // 4481
+
+constexpr uint32_t LBO64 = 128, SBO64 = (HS / 4) * 128;   // weights tile [n/8][k/4][n%8][k%4], 16 K-chunks per row group
+constexpr uint32_t IDESC64 = make_idesc(128, HS);
+constexpr int GROUP = 128, GROUPS = 2, BLOCK = GROUP * GROUPS;
+constexpr int TMEM_PER_GROUP = 3 * HS;   // D | A_hi | A_lo
+constexpr int TMEM_ALLOC = 512;
+
+template <bool BWD>
+__device__ __forceinline__ void stage_weights64(const float *__restrict__ theta, float *sBhi, float *sBlo, int tid, int nthreads)
+{
+    for (int e = tid; e < HS * HS; e += nthreads) {
+        const int n = e >> 6, k = e & 63;
+        const float x = BWD ? theta[OFF_W2 + n * HS + k] : theta[OFF_W2 + k * HS + n];
+        const float hi = tf32_rna(x);
+        const int off = (n >> 3) * (SBO64 / 4) + (k >> 2) * (LBO64 / 4) + (n & 7) * 4 + (k & 3);
+        sBhi[off] = hi;
+        sBlo[off] = x - hi;
+    }
+}
+
+struct GrpCtx {
+    uint32_t tmem;       // this group's first TMEM column
+    uint32_t lane_base;  // (warp % 4) * 32 << 16
+    uint32_t bar;        // mbarrier of this group
+    uint32_t parity;
+    int bar_id;          // named barrier of this group (1 + group)
+};
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(GROUP) : "memory"); }
+
+// write this thread's 64-wide row (hi/lo split) into TMEM, group barrier, elected thread issues 24 MMAs + commit
+__device__ __forceinline__ void tc_issue64(GrpCtx &c, const float (&a)[HS], const float *sBhi, const float *sBlo, bool issuer)
+{
+#pragma unroll
+    for (int q = 0; q < HS / 8; ++q) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float h = tf32_rna(a[8 * q + k]);
+            hi[k] = __float_as_uint(h);
+            lo[k] = __float_as_uint(a[8 * q + k] - h);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(c.tmem + HS + 8 * q + c.lane_base),
+                     "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(c.tmem + 2 * HS + 8 * q + c.lane_base),
+                     "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    group_sync(c.bar_id);
+    if (issuer) {
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < HS / 8; ++kb) {
+            const uint64_t dbh = make_desc(smem_u32(sBhi) + kb * 2 * LBO64, LBO64, SBO64);
+            const uint64_t dbl = make_desc(smem_u32(sBlo) + kb * 2 * LBO64, LBO64, SBO64);
+            mma_ts(c.tmem, c.tmem + HS + kb * 8, dbh, IDESC64, kb > 0);
+            mma_ts(c.tmem, c.tmem + 2 * HS + kb * 8, dbh, IDESC64, 1);
+            mma_ts(c.tmem, c.tmem + HS + kb * 8, dbl, IDESC64, 1);
+        }
+        mma_commit(c.bar);
+    }
+}
+__device__ __forceinline__ void tc_collect64(GrpCtx &c, float (&d)[HS])
+{
+    mbar_wait(c.bar, c.parity);
+    c.parity ^= 1;
+    tc_fence_after();
+    float lo[32], hi[32];
+    tmem_ld32(c.tmem + c.lane_base, lo);
+    tmem_ld32(c.tmem + 32 + c.lane_base, hi);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { d[k] = lo[k]; d[32 + k] = hi[k]; }
+}
+
+__device__ __forceinline__ GrpCtx cta_setup(uint64_t *mbars, uint32_t *tmem_slot)
+{
+    const int warp = threadIdx.x >> 5, group = threadIdx.x / GROUP;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_ALLOC) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < GROUPS; ++g) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbars[g])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    GrpCtx c;
+    c.tmem = *tmem_slot + group * TMEM_PER_GROUP;
+    c.lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    c.bar = smem_u32(&mbars[group]);
+    c.parity = 0;
+    c.bar_id = 1 + group;
+    return c;
+}
+__device__ __forceinline__ void cta_teardown(uint32_t tmem_base)
+{
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC) : "memory");
+}
+
+struct State7 {
+    float v[D];
+};
+
+// chain input [S/N, I, D/N] (seir_exposure.jl:120)
+__device__ __forceinline__ void seir_inputs(const float (&u)[D], float (&x)[3])
+{
+    const float invN = 1.0f / u[4];
+    x[0] = u[0] * invN;
+    x[1] = u[2];
+    x[2] = u[5] * invN;
+}
+
+// ---- UDE right-hand side (seir_exposure.jl:117-130), the 64 x 64 layer on the tensor core ----
+template <int TM>
+__device__ __noinline__ State7 rhs_seir(GrpCtx *cp, const float *sWhi, const float *sWlo, State7 us, int zsel, bool issuer)
+{
+    GrpCtx c = *cp;
+    const int zb = lv32::c_zero[zsel & 7] << 2;
+    float x[3];
+    seir_inputs(us.v, x);
+    float h[HS];
+#pragma unroll
+    for (int j4 = 0; j4 < HS; j4 += 4) {
+        const float4 wb = ldw4(zb + OFF_B1 + j4), w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
+        const float b_[4] = {wb.x, wb.y, wb.z, wb.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[j4 + k] = tanh_dev<TM>(fmaf(w2_[k], x[2], fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k]))));
+    }
+    tc_issue64(c, h, sWhi, sWlo, issuer);
+    tc_collect64(c, h);
+    float z = c_theta[zb + OFF_B3];
+#pragma unroll
+    for (int j4 = 0; j4 < HS; j4 += 4) {
+        const float4 b2 = ldw4(zb + OFF_B2 + j4), w3 = ldw4(zb + OFF_W3 + j4);
+        const float b_[4] = {b2.x, b2.y, b2.z, b2.w}, w3_[4] = {w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z = fmaf(w3_[k], tanh_dev<TM>(h[j4 + k] + b_[k]), z);
+    }
+    cp->parity = c.parity;
+    // consts = F, beta0, alpha, kappa, mu, sigma, gamma, d, lambda (seir_exposure.jl:33)
+    const float F = c_consts[0], b0 = c_consts[1], mu = c_consts[4], sg = c_consts[5], gm = c_consts[6], dd = c_consts[7], lm = c_consts[8];
+    const float S = us.v[0], E = us.v[1], I = us.v[2], R = us.v[3], N = us.v[4], Dd = us.v[5];
+    const float inf = b0 * S * F / N;
+    State7 du;
+    du.v[0] = -inf - z - mu * S;
+    du.v[1] = inf + z - (sg + mu) * E;
+    du.v[2] = sg * E - (gm + mu) * I;
+    du.v[3] = gm * I - mu * R;
+    du.v[4] = -mu * N;
+    du.v[5] = dd * gm * I - lm * Dd;
+    du.v[6] = sg * E;
+    return du;
+}
+
+// ---- forward kernel --------------------------------------------------------------------------------------
+template <int TM>
+__global__ void __launch_bounds__(BLOCK, 1) forward_kernel(FwdParams p)
+{
+    extern __shared__ __align__(1024) float s_dyn[];
+    float *sWf_hi = s_dyn, *sWf_lo = s_dyn + HS * HS;
+    __shared__ __align__(8) uint64_t mbars[GROUPS];
+    __shared__ uint32_t tmem_slot;
+    GrpCtx c = cta_setup(mbars, &tmem_slot);
+    const uint32_t tmem_base = tmem_slot;
+    stage_weights64<false>(p.theta, sWf_hi, sWf_lo, threadIdx.x, BLOCK);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const bool issuer = (threadIdx.x % GROUP) == 0;
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = gid < p.N;
+    const size_t n = live ? (size_t)gid : (size_t)(p.N - 1);
+    const float dt = p.dt;
+    State7 u;
+#pragma unroll
+    for (int cc = 0; cc < D; ++cc) u.v[cc] = __ldg(p.u0 + (size_t)cc * N + n);
+    auto store = [&](float *base, int row, const State7 &v) {
+        if (live) {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) base[((size_t)row * D + cc) * N + n] = v.v[cc];
+        }
+    };
+    store(p.out, 0, u);
+    store(p.ustep, 0, u);
+    State7 k[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) k[j].v[cc] = 0.0f;
+    int isave = 1;
+#pragma unroll 1
+    for (int s = 0; s < p.n_steps; ++s) {
+#pragma unroll 1
+        for (int i = (s == 0 ? 0 : 1); i < 7; ++i) {
+            State7 g;
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) g.v[cc] = 0.0f;
+#define B200UDE_SEIR_COMB(I)                                                              \
+    case I: {                                                                             \
+        _Pragma("unroll") for (int j = 0; j < I; ++j) if (Tsit5::a(I, j) != 0.0) {        \
+            _Pragma("unroll") for (int cc = 0; cc < D; ++cc)                              \
+                g.v[cc] = fmaf((float)Tsit5::a(I, j), k[j].v[cc], g.v[cc]);               \
+        }                                                                                 \
+    } break;
+            switch (i) {
+                B200UDE_SEIR_COMB(1)
+                B200UDE_SEIR_COMB(2)
+                B200UDE_SEIR_COMB(3)
+                B200UDE_SEIR_COMB(4)
+                B200UDE_SEIR_COMB(5)
+                B200UDE_SEIR_COMB(6)
+            default: break;
+            }
+#undef B200UDE_SEIR_COMB
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) g.v[cc] = fmaf(dt, g.v[cc], u.v[cc]);
+            if (i == 6) u = g;   // stage 7's argument is u_{n+1} (row 7 = b, FSAL)
+            const State7 kk = rhs_seir<TM>(&c, sWf_hi, sWf_lo, g, i, issuer);
+            switch (i) {
+            case 0: k[0] = kk; break;
+            case 1: k[1] = kk; break;
+            case 2: k[2] = kk; break;
+            case 3: k[3] = kk; break;
+            case 4: k[4] = kk; break;
+            case 5: k[5] = kk; break;
+            default: k[6] = kk; break;
+            }
+            store(p.dense, s * 6 + i, kk);
+        }
+        store(p.ustep, s + 1, u);
+        if ((s + 1) % p.save_every == 0) {
+            store(p.out, isave, u);
+            ++isave;
+        }
+        k[0] = k[6];
+    }
+    if (p.status && live) {
+        bool ok = true;
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) ok = ok && (fabsf(u.v[cc]) <= 3.0e38f);
+        p.status[n] = ok ? 0 : 1;
+    }
+    cta_teardown(tmem_base);
+}
+
+// ---- adjoint kernel --------------------------------------------------------------------------------------
+constexpr int SLD64 = 68;   // staged row stride (floats): 64 + 4
+struct __align__(16) GroupStage {
+    float B1[GROUP * SLD64];   // h2 rows, then q2 rows, then q1 rows   [trajectory][j]
+    float B2[GROUP * SLD64];   // h1 rows                                [trajectory][i]
+    float SG[GROUP];           // scaled, masked chain-output cotangent
+    float U[GROUP * 4];        // chain input [x0, x1, x2, -]
+    float RED[GROUP];          // loss reduction scratch
+};
+
+template <int TM>
+__global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
+{
+    extern __shared__ __align__(1024) float s_dyn[];
+    float *sWf_hi = s_dyn, *sWf_lo = s_dyn + HS * HS, *sWb_hi = s_dyn + 2 * HS * HS, *sWb_lo = s_dyn + 3 * HS * HS;
+    __shared__ __align__(8) uint64_t mbars[GROUPS];
+    __shared__ uint32_t tmem_slot;
+    GrpCtx c = cta_setup(mbars, &tmem_slot);
+    const uint32_t tmem_base = tmem_slot;
+    stage_weights64<false>(p.theta, sWf_hi, sWf_lo, threadIdx.x, BLOCK);
+    stage_weights64<true>(p.theta, sWb_hi, sWb_lo, threadIdx.x, BLOCK);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int group = threadIdx.x / GROUP, tg = threadIdx.x % GROUP;
+    const bool issuer = tg == 0;
+    GroupStage *st = reinterpret_cast<GroupStage *>(s_dyn + 4 * HS * HS) + group;
+    float *const rowB1 = st->B1 + tg * SLD64, *const rowB2 = st->B2 + tg * SLD64;
+    const int jt = tg >> 4, it = tg & 15;        // dW2 tile: j = jt*8 + jj, i = it*4 + {0,1},{2,3}
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = gid < p.N;
+    const size_t n = live ? (size_t)gid : (size_t)(p.N - 1);
+    const float lv = live ? 1.0f : 0.0f;
+    const float dt = p.dt, inv_dt = 1.0f / dt;
+    const float F = c_consts[0], b0 = c_consts[1], mu = c_consts[4], sgm = c_consts[5], gm = c_consts[6], dd = c_consts[7], lm = c_consts[8];
+
+    float2 acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = bc(0.0f);
+    // thin layers: thread tg owns column j = tg % 64 over the staged rows [64 * (tg / 64), +64) of its group:
+    // a_w3 (dW3[j]), a_b2 (db2[j]), a_b3 (db3), a_w1[m] (dW1[j][m]), a_b1 (db1[j]); the two halves are added at the end
+    float a_w3 = 0.f, a_b2 = 0.f, a_b3 = 0.f, a_w10 = 0.f, a_w11 = 0.f, a_w12 = 0.f, a_b1 = 0.f;
+    const int jc = tg & 63, tlo = (tg >> 6) * 64;
+
+    float lam[D];
+#pragma unroll
+    for (int cc = 0; cc < D; ++cc) lam[cc] = 0.0f;
+    float loss = 0.0f;
+    const int n_save = p.n_steps / p.save_every + 1;
+    loss_jump<D>(p, n_save - 1, n, N, lam, loss);
+
+#pragma unroll 1
+    for (int s = p.n_steps - 1; s >= 0; --s) {
+        float kl[6][D];
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) kl[j][cc] = 0.0f;
+#pragma unroll 1
+        for (int stage = 0; stage < 6; ++stage) {
+            float u[D], g[D], sc, isc;
+#define B200UDE_SEIR_PRE(I)                                        \
+    case I: {                                                      \
+        interp_state<D, I>(p, s, n, N, dt, u);                     \
+        stage_arg<D, I>(lam, kl, dt, g);                           \
+        sc = dt * (float)Tsit5::b(I);                              \
+        isc = inv_dt * (float)(1.0 / Tsit5::b(I));                 \
+    } break;
+            switch (stage) {
+                B200UDE_SEIR_PRE(0)
+                B200UDE_SEIR_PRE(1)
+                B200UDE_SEIR_PRE(2)
+                B200UDE_SEIR_PRE(3)
+                B200UDE_SEIR_PRE(4)
+            default:
+                B200UDE_SEIR_PRE(5)
+            }
+#undef B200UDE_SEIR_PRE
+            const int zb = lv32::c_zero[stage] << 2;
+            float x[3];
+            seir_inputs(u, x);
+            const float sg = lv * sc * (g[1] - g[0]);   // z enters dS with -, dE with +
+            group_sync(c.bar_id);                       // the previous stage's column passes are done with SG / U / B1
+            st->SG[tg] = sg;
+            *reinterpret_cast<float4 *>(&st->U[tg * 4]) = make_float4(x[0], x[1], x[2], 0.0f);
+
+            // ---- chain forward ----
+            float v[HS];
+#pragma unroll
+            for (int j4 = 0; j4 < HS; j4 += 4) {
+                const float4 wb = ldw4(zb + OFF_B1 + j4), w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
+                const float b_[4] = {wb.x, wb.y, wb.z, wb.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[j4 + k] = tanh_dev<TM>(fmaf(w2_[k], x[2], fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k]))));
+                *reinterpret_cast<float4 *>(rowB2 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // h1 row
+            }
+            tc_issue64(c, v, sWf_hi, sWf_lo, issuer);
+            tc_collect64(c, v);   // v = W2 h1
+            // h2 = tanh(. + b2) -> B1 row;  q2 = W3 * sg * (1 - h2^2) stays in v
+#pragma unroll
+            for (int j4 = 0; j4 < HS; j4 += 4) {
+                const float4 b2 = ldw4(zb + OFF_B2 + j4), w3 = ldw4(zb + OFF_W3 + j4);
+                const float b_[4] = {b2.x, b2.y, b2.z, b2.w}, w3_[4] = {w3.x, w3.y, w3.z, w3.w};
+                float h2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    h2[k] = tanh_dev<TM>(v[j4 + k] + b_[k]);
+                    v[j4 + k] = w3_[k] * sg * fmaf(-h2[k], h2[k], 1.0f);
+                }
+                *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+            }
+            group_sync(c.bar_id);
+            // column pass A: dW3[j] += sum_t SG[t] h2[t][j];  db3 += sum_t SG[t]
+#pragma unroll 8
+            for (int t = tlo; t < tlo + 64; ++t) {
+                const float sgt = st->SG[t];
+                a_w3 = fmaf(sgt, st->B1[t * SLD64 + jc], a_w3);
+                a_b3 += sgt;
+            }
+            group_sync(c.bar_id);
+#pragma unroll
+            for (int j4 = 0; j4 < HS; j4 += 4) *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // q2 row
+            // ---- W2^T q2 on the tensor core; gradient GEMM of the group while the MMAs are in flight ----
+            tc_issue64(c, v, sWb_hi, sWb_lo, issuer);
+            {
+                float4 G0[2], G1[2], Hh[2];
+                auto load_row = [&](int t, int b) {
+                    const float *r1 = st->B1 + t * SLD64, *r2 = st->B2 + t * SLD64;
+                    G0[b] = *reinterpret_cast<const float4 *>(r1 + jt * 8);
+                    G1[b] = *reinterpret_cast<const float4 *>(r1 + jt * 8 + 4);
+                    Hh[b] = *reinterpret_cast<const float4 *>(r2 + it * 4);
+                };
+                auto use_row = [&](int b) {
+                    const float gj[8] = {G0[b].x, G0[b].y, G0[b].z, G0[b].w, G1[b].x, G1[b].y, G1[b].z, G1[b].w};
+                    const float2 h01 = make_float2(Hh[b].x, Hh[b].y), h23 = make_float2(Hh[b].z, Hh[b].w);
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        acc[2 * jj] = fma2(bc(gj[jj]), h01, acc[2 * jj]);
+                        acc[2 * jj + 1] = fma2(bc(gj[jj]), h23, acc[2 * jj + 1]);
+                    }
+                };
+                load_row(0, 0);
+#pragma unroll 1
+                for (int t = 0; t < GROUP; t += 2) {
+                    load_row(t + 1, 1);
+                    use_row(0);
+                    if (t + 2 < GROUP) load_row(t + 2, 0);
+                    use_row(1);
+                }
+#pragma unroll 8
+                for (int t = tlo; t < tlo + 64; ++t) a_b2 += st->B1[t * SLD64 + jc];   // db2[j] += sum_t q2[t][j]
+            }
+            tc_collect64(c, v);   // v = W2^T q2
+            group_sync(c.bar_id);  // everyone is done reading q2 / h1 rows
+            float dx0 = 0.0f, dx1 = 0.0f, dx2 = 0.0f;
+#pragma unroll
+            for (int j4 = 0; j4 < HS; j4 += 4) {
+                const float4 hh = *reinterpret_cast<const float4 *>(rowB2 + j4);
+                const float4 w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
+                const float h_[4] = {hh.x, hh.y, hh.z, hh.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[j4 + k] *= fmaf(-h_[k], h_[k], 1.0f);   // q1
+                    dx0 = fmaf(w0_[k], v[j4 + k], dx0);
+                    dx1 = fmaf(w1_[k], v[j4 + k], dx1);
+                    dx2 = fmaf(w2_[k], v[j4 + k], dx2);
+                }
+                *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // q1 row
+            }
+            dx0 *= isc; dx1 *= isc; dx2 *= isc;   // cotangent of the chain input, quadrature weight removed
+            // (df/du)^T g: physics Jacobian of seir_exposure.jl:117-130 plus the chain-input map [S/N, I, D/N]
+            {
+                const float S = u[0], Nn = u[4], Dd = u[5];
+                const float cS = b0 * F / Nn, cN = -b0 * S * F / (Nn * Nn), invN = 1.0f / Nn;
+                float kn[D];
+                kn[0] = g[0] * (-cS - mu) + g[1] * cS + dx0 * invN;
+                kn[1] = g[1] * (-(sgm + mu)) + g[2] * sgm + g[6] * sgm;
+                kn[2] = g[2] * (-(gm + mu)) + g[3] * gm + g[5] * dd * gm + dx1;
+                kn[3] = g[3] * (-mu);
+                kn[4] = g[0] * (-cN) + g[1] * cN + g[4] * (-mu) - dx0 * S * invN * invN - dx2 * Dd * invN * invN;
+                kn[5] = g[5] * (-lm) + dx2 * invN;
+                kn[6] = 0.0f;
+                switch (stage) {
+#define B200UDE_SEIR_SETKL(I) case I: _Pragma("unroll") for (int cc = 0; cc < D; ++cc) kl[I][cc] = kn[cc]; break;
+                    B200UDE_SEIR_SETKL(0)
+                    B200UDE_SEIR_SETKL(1)
+                    B200UDE_SEIR_SETKL(2)
+                    B200UDE_SEIR_SETKL(3)
+                    B200UDE_SEIR_SETKL(4)
+                default:
+#pragma unroll
+                    for (int cc = 0; cc < D; ++cc) kl[5][cc] = kn[cc];
+#undef B200UDE_SEIR_SETKL
+                }
+            }
+            group_sync(c.bar_id);
+            // column pass B: dW1[j][m] += sum_t q1[t][j] x[t][m];  db1[j] += sum_t q1[t][j]
+#pragma unroll 8
+            for (int t = tlo; t < tlo + 64; ++t) {
+                const float qq = st->B1[t * SLD64 + jc];
+                const float4 u4 = *reinterpret_cast<const float4 *>(&st->U[t * 4]);
+                a_w10 = fmaf(qq, u4.x, a_w10);
+                a_w11 = fmaf(qq, u4.y, a_w11);
+                a_w12 = fmaf(qq, u4.z, a_w12);
+                a_b1 += qq;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a = fmaf((float)Tsit5::b(j), kl[j][cc], a);
+            lam[cc] = fmaf(dt, a, lam[cc]);
+        }
+        if (s % p.save_every == 0) loss_jump<D>(p, s / p.save_every, n, N, lam, loss);
+    }
+    if (p.grad_u0 && live) {
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) p.grad_u0[(size_t)cc * N + n] = lam[cc];
+    }
+    // ---- this group's partial gradient ----
+    group_sync(c.bar_id);
+    st->RED[tg] = loss * lv;
+    if (tg >= 64) {   // upper half of the staged rows: hand the column sums to the lower-half owner of the same column
+        float *x = st->B1 + jc * 8;
+        x[0] = a_w3; x[1] = a_b2; x[2] = a_b3; x[3] = a_w10; x[4] = a_w11; x[5] = a_w12; x[6] = a_b1;
+    }
+    group_sync(c.bar_id);
+    float *dst = p.partial + ((size_t)blockIdx.x * GROUPS + group) * (PS + 1);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        dst[OFF_W2 + (it * 4 + 0) * HS + (jt * 8 + jj)] = acc[2 * jj].x;
+        dst[OFF_W2 + (it * 4 + 1) * HS + (jt * 8 + jj)] = acc[2 * jj].y;
+        dst[OFF_W2 + (it * 4 + 2) * HS + (jt * 8 + jj)] = acc[2 * jj + 1].x;
+        dst[OFF_W2 + (it * 4 + 3) * HS + (jt * 8 + jj)] = acc[2 * jj + 1].y;
+    }
+    if (tg < 64) {
+        const float *x = st->B1 + jc * 8;
+        dst[OFF_W3 + jc] = a_w3 + x[0];
+        dst[OFF_B2 + jc] = a_b2 + x[1];
+        dst[OFF_W1 + jc] = a_w10 + x[3];
+        dst[OFF_W1 + HS + jc] = a_w11 + x[4];
+        dst[OFF_W1 + 2 * HS + jc] = a_w12 + x[5];
+        dst[OFF_B1 + jc] = a_b1 + x[6];
+        if (tg == 0) {
+            dst[OFF_B3] = a_b3 + x[2];
+            float ls = 0.0f;
+            for (int t = 0; t < GROUP; ++t) ls += st->RED[t];   // fixed order
+            dst[PS] = ls;
+        }
+    }
+    cta_teardown(tmem_base);
+}
+
+}  // namespace seir
+}  // namespace b200ude
