@@ -32,7 +32,8 @@
  *    seir_exposure.jl:115, Flux.destructure Fisher-KPP-CNN.jl:106).
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls taking a
  *    stream are asynchronous with respect to the host unless stated otherwise.
- *  - a handle is not thread-safe; use one handle per host thread and device.
+ *  - a handle is not thread-safe; use one handle per host thread and device.  Kernels read the active handle's theta and
+ *    tables from the constant bank, so work of DIFFERENT handles on one device must be stream-ordered (not concurrent).
  */
 #ifndef B200UDE_H
 #define B200UDE_H
@@ -171,6 +172,34 @@ int32_t b200ude_solve_host(b200ude_handle *h, const void *theta, const void *u0,
 int32_t b200ude_loss_gradient_host(b200ude_handle *h, const void *theta, const void *u0,
                                    const void *data, size_t N, double *loss, void *grad_theta,
                                    void *grad_u0 /* may be NULL */);
+
+/* ON-DEVICE OPTIMISER  (replaces the ADAM phase of DiffEqFlux.sciml_train(loss, theta, ADAM(eta); cb, maxiters)
+ * seir_exposure.jl:160, Fisher-KPP-CNN.jl:236, Optimization.solve(optprob, ADAM(0.1); maxiters) scenario_1.jl:114,
+ * for the trajectory-matching loss  L = loss_scale * sum w (u - data)^2 + l2_reg * sum theta^2
+ * (scenario_1.jl:91-94; scenario_2.jl:113-116 divides by the number of points and adds the L2 term).
+ * The update is Flux.ADAM: m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2,
+ * theta -= eta * (m / (1 - b1^t)) / (sqrt(v / (1 - b2^t)) + eps); the moments and t live in the handle. */
+typedef struct b200ude_adam {
+    uint32_t struct_size; /* = sizeof(b200ude_adam) */
+    uint32_t reserved;
+    double eta, beta1, beta2, eps; /* Flux defaults: 0.001, 0.9, 0.999, 1e-8 */
+    double loss_scale;             /* 0 is read as 1 */
+    double l2_reg;
+} b200ude_adam;
+
+/* the handle's current theta -> theta[P] (host: synchronises the stream; device: asynchronous) */
+int32_t b200ude_get_params(b200ude_handle *h, void *theta, size_t P, int32_t mem, void *stream);
+/* zero the ADAM moments and the step counter */
+int32_t b200ude_adam_reset(b200ude_handle *h, void *stream);
+/* one ADAM update of the handle's theta with a caller-supplied DEVICE gradient [P] (e.g. after an all-reduce over GPUs);
+ * loss_scale / l2_reg are applied to it as above */
+int32_t b200ude_adam_step(b200ude_handle *h, const b200ude_adam *opt, const void *grad_theta, void *stream);
+/* `iters` full iterations without a host round trip: forward, fused-L2 adjoint, fixed-order reduce, ADAM update -- the first
+ * launched directly, the rest as replays of one captured CUDA graph.  u0 [d][N], data [n_save][d][N]: DEVICE pointers.
+ * loss_history: DEVICE float[iters] or NULL; slot i = loss at the pre-update theta of iteration i (what the reference's
+ * callback records).  stream NULL = the handle's own stream, synchronised before returning. */
+int32_t b200ude_train_adam(b200ude_handle *h, const b200ude_adam *opt, const void *u0, const void *data, size_t N,
+                           int32_t iters, void *loss_history, void *stream);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,6 @@ from . import _lib  # noqa: F401
 from .sciml import (  # noqa: F401
     ADAM, BFGS, Chain, Dense, EnsembleProblem, FastChain, FastDense, FisherKPPUDE, ForwardDiffSensitivity,
     InterpolatingAdjoint, LotkaVolterraUDE, NeuralODE, ODEProblem, SEIRExposureUDE, ReverseDiffVJP, Tsit5, UDESolver, Vern7,
-    concrete_solve, identity, initial_params, rbf, remake, sciml_train, solve, tanh,
+    concrete_solve, identity, initial_params, rbf, remake, sciml_train, sciml_train_l2, solve, tanh,
 )
 from .dist import shard_range, allreduce_loss_grad  # noqa: F401

@@ -28,7 +28,7 @@ EXPORTS = [
     "b200ude_version", "b200ude_last_error", "b200ude_create", "b200ude_destroy",
     "b200ude_num_params", "b200ude_num_save", "b200ude_device_bytes", "b200ude_set_params",
     "b200ude_forward", "b200ude_adjoint", "b200ude_adjoint_l2", "b200ude_solve_host",
-    "b200ude_loss_gradient_host",
+    "b200ude_loss_gradient_host", "b200ude_get_params", "b200ude_adam_reset", "b200ude_adam_step", "b200ude_train_adam",
 ]
 
 
@@ -46,6 +46,15 @@ class Desc(C.Structure):
         ("n_loss_weights", C.c_int32), ("loss_weights", C.c_double * 16),
         ("max_trajectories", C.c_uint64), ("flags", C.c_uint32), ("adaptive", C.c_int32), ("max_steps", C.c_int32),
         ("reserved", C.c_uint32),
+    ]
+
+
+class Adam(C.Structure):
+    """struct b200ude_adam"""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("reserved", C.c_uint32),
+        ("eta", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+        ("loss_scale", C.c_double), ("l2_reg", C.c_double),
     ]
 
 
@@ -98,6 +107,14 @@ def lib():
     L.b200ude_solve_host.argtypes = [vp, vp, vp, sz, vp, vp]
     L.b200ude_loss_gradient_host.restype = i32
     L.b200ude_loss_gradient_host.argtypes = [vp, vp, vp, vp, sz, C.POINTER(C.c_double), vp, vp]
+    L.b200ude_get_params.restype = i32
+    L.b200ude_get_params.argtypes = [vp, vp, sz, i32, vp]
+    L.b200ude_adam_reset.restype = i32
+    L.b200ude_adam_reset.argtypes = [vp, vp]
+    L.b200ude_adam_step.restype = i32
+    L.b200ude_adam_step.argtypes = [vp, C.POINTER(Adam), vp, vp]
+    L.b200ude_train_adam.restype = i32
+    L.b200ude_train_adam.argtypes = [vp, C.POINTER(Adam), vp, vp, sz, i32, vp, vp]
     if L.b200ude_version() != ABI_VERSION:
         raise RuntimeError("libb200ude.so ABI version mismatch")
     _lib = L

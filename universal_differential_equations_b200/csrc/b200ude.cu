@@ -79,6 +79,10 @@ struct b200ude_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-buffer path: the data upload overlaps the forward kernel
     cudaEvent_t data_ready = nullptr;
+    // on-device optimiser (b200ude_adam_*, b200ude_train_adam)
+    float *d_adam_m = nullptr, *d_adam_v = nullptr, *d_train_out = nullptr;
+    int *d_adam_t = nullptr;
+    int adam_t = 0;   // host mirror of the step counter
     size_t dev_bytes = 0;
     std::string err;
 };
@@ -233,6 +237,85 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     return B200UDE_OK;
 }
 
+
+// ---- ADAM on the device (Flux.ADAM(eta, (beta1, beta2)), eps = 1e-8: scenario_1.jl:114, seir_exposure.jl:160) ----
+// One CTA: L = loss_scale * L_data + l2_reg * sum theta^2, g = loss_scale * grad + 2 l2_reg theta, then the
+// bias-corrected update of theta in place.  The step counter lives in device memory so that the launch arguments
+// do not change from iteration to iteration (the training loop is replayed as a CUDA graph).
+struct AdamArgs {
+    float *theta, *m, *v;
+    const float *grad, *loss;   // loss may be null
+    float *loss_history;        // [..] or null; slot (t - 1 - t_base) receives the pre-update loss
+    int *t;
+    int P, t_base;
+    float eta, beta1, beta2, eps, loss_scale, l2_reg;
+};
+
+__global__ void __launch_bounds__(1024, 1) adam_kernel(AdamArgs a)
+{
+    __shared__ float red[32];
+    __shared__ int s_t;
+    if (threadIdx.x == 0) s_t = *a.t + 1;
+    float sq = 0.0f;
+    if (a.l2_reg != 0.0f)
+        for (int i = threadIdx.x; i < a.P; i += blockDim.x) sq = fmaf(a.theta[i], a.theta[i], sq);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    const int t = s_t;
+    if (threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];   // fixed order
+        if (a.loss_history && a.loss) a.loss_history[t - 1 - a.t_base] = fmaf(a.loss_scale, *a.loss, a.l2_reg * tot);
+        *a.t = t;
+    }
+    const float c1 = (float)(1.0 / (1.0 - pow((double)a.beta1, (double)t)));
+    const float c2 = (float)(1.0 / (1.0 - pow((double)a.beta2, (double)t)));
+    for (int i = threadIdx.x; i < a.P; i += blockDim.x) {
+        const float th = a.theta[i];
+        const float g = fmaf(a.loss_scale, a.grad[i], 2.0f * a.l2_reg * th);
+        const float m = fmaf(a.beta1, a.m[i], (1.0f - a.beta1) * g);
+        const float v = fmaf(a.beta2, a.v[i], (1.0f - a.beta2) * g * g);
+        a.m[i] = m;
+        a.v[i] = v;
+        a.theta[i] = th - a.eta * (m * c1) / (sqrtf(v * c2) + a.eps);
+    }
+}
+
+int32_t ensure_adam(b200ude_handle *h)
+{
+    if (h->d_adam_m) return B200UDE_OK;
+    bool ok = dalloc(h, &h->d_adam_m, (size_t)h->P) == cudaSuccess && dalloc(h, &h->d_adam_v, (size_t)h->P) == cudaSuccess &&
+              dalloc(h, &h->d_adam_t, 1) == cudaSuccess;
+    if (!ok) return fail(h, B200UDE_ENOMEM, "adam: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaMemset(h->d_adam_m, 0, sizeof(float) * h->P);
+    cudaMemset(h->d_adam_v, 0, sizeof(float) * h->P);
+    cudaMemset(h->d_adam_t, 0, sizeof(int));
+    h->adam_t = 0;
+    return B200UDE_OK;
+}
+
+int32_t check_adam(b200ude_handle *h, const b200ude_adam *o)
+{
+    if (!o || o->struct_size != sizeof(b200ude_adam)) return fail(h, B200UDE_EINVAL, "adam: bad options struct");
+    if (!(o->eta > 0) || !(o->beta1 >= 0 && o->beta1 < 1) || !(o->beta2 >= 0 && o->beta2 < 1) || !(o->eps > 0))
+        return fail(h, B200UDE_EINVAL, "adam: need eta > 0, 0 <= beta < 1, eps > 0");
+    if (!h->have_theta) return fail(h, B200UDE_ESTATE, "adam: no parameters set (call b200ude_set_params first)");
+    return ensure_adam(h);
+}
+
+cudaError_t launch_adam(b200ude_handle *h, const b200ude_adam *o, const float *grad, const float *loss, float *hist, int t_base, cudaStream_t st)
+{
+    AdamArgs a;
+    a.theta = h->d_theta; a.m = h->d_adam_m; a.v = h->d_adam_v; a.grad = grad; a.loss = loss; a.loss_history = hist;
+    a.t = h->d_adam_t; a.P = h->P; a.t_base = t_base;
+    a.eta = (float)o->eta; a.beta1 = (float)o->beta1; a.beta2 = (float)o->beta2; a.eps = (float)o->eps;
+    a.loss_scale = (float)(o->loss_scale == 0.0 ? 1.0 : o->loss_scale); a.l2_reg = (float)o->l2_reg;
+    adam_kernel<<<1, 1024, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 // ---- exported entry points ------------------------------------------------------------------------
@@ -364,6 +447,7 @@ void b200ude_destroy(b200ude_handle *h)
     cudaFree(h->d_theta); cudaFree(h->d_ustep); cudaFree(h->d_dense); cudaFree(h->d_partial);
     cudaFree(h->d_u0); cudaFree(h->d_out); cudaFree(h->d_data); cudaFree(h->d_gu0); cudaFree(h->d_grad);
     cudaFree(h->d_loss); cudaFree(h->d_status);
+    cudaFree(h->d_adam_m); cudaFree(h->d_adam_v); cudaFree(h->d_adam_t); cudaFree(h->d_train_out);
     cudaFree(h->d_tgrid); cudaFree(h->d_nacc); cudaFree(h->d_cot); cudaFree(h->d_block_loss);
     if (h->h_loss) cudaFreeHost(h->h_loss);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -469,6 +553,87 @@ int32_t b200ude_loss_gradient_host(b200ude_handle *h, const void *theta, const v
     if (grad_u0) CUDA_TRY(h, cudaMemcpyAsync(grad_u0, h->d_gu0, sizeof(float) * D * N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
     if (loss) *loss = (double)*h->h_loss;
+    return B200UDE_OK;
+}
+
+// ---- on-device optimiser ---------------------------------------------------------------------------
+int32_t b200ude_get_params(b200ude_handle *h, void *theta, size_t P, int32_t mem, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (!theta || P != (size_t)h->P) return fail(h, B200UDE_EINVAL, "get_params: P=%zu, expected %d", P, h->P);
+    CUDA_TRY(h, cudaMemcpyAsync(theta, h->d_theta, sizeof(float) * P,
+                                mem == B200UDE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (mem != B200UDE_DEVICE) CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return B200UDE_OK;
+}
+
+int32_t b200ude_adam_reset(b200ude_handle *h, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    int32_t rc = ensure_adam(h);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_adam_m, 0, sizeof(float) * h->P, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_adam_v, 0, sizeof(float) * h->P, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_adam_t, 0, sizeof(int), st));
+    h->adam_t = 0;
+    return B200UDE_OK;
+}
+
+int32_t b200ude_adam_step(b200ude_handle *h, const b200ude_adam *opt, const void *grad_theta, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (!grad_theta) return fail(h, B200UDE_EINVAL, "adam_step: null gradient");
+    int32_t rc = check_adam(h, opt);
+    if (rc) return rc;
+    CUDA_TRY(h, launch_adam(h, opt, (const float *)grad_theta, nullptr, nullptr, h->adam_t, (cudaStream_t)stream));
+    h->adam_t += 1;
+    return B200UDE_OK;
+}
+
+int32_t b200ude_train_adam(b200ude_handle *h, const b200ude_adam *opt, const void *u0, const void *data, size_t N,
+                           int32_t iters, void *loss_history, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (!u0 || !data || iters < 1) return fail(h, B200UDE_EINVAL, "train_adam: null pointer or iters < 1");
+    if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "train_adam: N=%zu outside (0, %zu]", N, h->cap);
+    int32_t rc = check_adam(h, opt);
+    if (rc) return rc;
+    if (!h->d_train_out && dalloc(h, &h->d_train_out, (size_t)h->n_save * (size_t)h->D * h->cap) != cudaSuccess)
+        return fail(h, B200UDE_ENOMEM, "train_adam: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;   // the legacy default stream cannot be captured
+    const int t_base = h->adam_t;
+    auto one_iteration = [&]() -> int32_t {
+        int32_t r = do_forward(h, (const float *)u0, N, h->d_train_out, nullptr, st);
+        if (r) return r;
+        r = do_adjoint(h, true, (const float *)data, h->d_loss, h->d_grad, nullptr, st);
+        if (r) return r;
+        CUDA_TRY(h, launch_adam(h, opt, h->d_grad, h->d_loss, (float *)loss_history, t_base, st));
+        return B200UDE_OK;
+    };
+    // iteration 1 eagerly (one-time function attributes, constant tables), the rest as replays of one captured graph
+    rc = one_iteration();
+    if (rc) return rc;
+    if (iters > 1) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool graphed = false;
+        if (env_int("B200UDE_TRAIN_GRAPH", 1) && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int32_t r = one_iteration();
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (r == B200UDE_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) graphed = true;
+            else cudaGetLastError();
+        }
+        for (int it = 1; it < iters; ++it) {
+            if (graphed) CUDA_TRY(h, cudaGraphLaunch(exec, st));
+            else if ((rc = one_iteration()) != 0) break;   // same kernels, launched one by one
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc) return rc;
+    }
+    h->adam_t = t_base + iters;
+    if (!stream) CUDA_TRY(h, cudaStreamSynchronize(st));
     return B200UDE_OK;
 }
 

@@ -370,6 +370,42 @@ class UDESolver:
         return loss.value, grad_theta, grad_u0
 
 
+    # -- on-device optimiser ----------------------------------------------------------------
+    @staticmethod
+    def _adam_struct(opt, loss_scale=1.0, l2_reg=0.0):
+        a = _lib.Adam()
+        a.struct_size = C.sizeof(_lib.Adam)
+        a.eta, (a.beta1, a.beta2), a.eps = opt.eta, opt.beta, opt.eps
+        a.loss_scale, a.l2_reg = loss_scale, l2_reg
+        return a
+
+    def get_params(self) -> torch.Tensor:
+        th = torch.empty(self.P, device=self.device, dtype=torch.float32)
+        _lib.check(self._h, self._L.b200ude_get_params(self._h, th.data_ptr(), self.P, _lib.DEVICE, _stream_ptr(self.device)))
+        return th
+
+    def adam_reset(self):
+        _lib.check(self._h, self._L.b200ude_adam_reset(self._h, _stream_ptr(self.device)))
+
+    def adam_step(self, opt, grad_theta: torch.Tensor, loss_scale=1.0, l2_reg=0.0):
+        """One ADAM update of the handle's theta with a device gradient (e.g. all-reduced over ranks)."""
+        a = self._adam_struct(opt, loss_scale, l2_reg)
+        grad_theta = grad_theta.contiguous()
+        _lib.check(self._h, self._L.b200ude_adam_step(self._h, C.byref(a), grad_theta.data_ptr(), _stream_ptr(self.device)))
+
+    def train_adam(self, opt, u0: torch.Tensor, data: torch.Tensor, iters: int, loss_scale=1.0, l2_reg=0.0,
+                   loss_history: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`iters` iterations of forward + fused-L2 adjoint + ADAM on the device (one CUDA graph replayed); returns the
+        per-iteration pre-update losses (device float32[iters])."""
+        a = self._adam_struct(opt, loss_scale, l2_reg)
+        u0, data = u0.contiguous(), data.contiguous()
+        if loss_history is None:
+            loss_history = torch.empty(iters, device=self.device, dtype=torch.float32)
+        _lib.check(self._h, self._L.b200ude_train_adam(self._h, C.byref(a), u0.data_ptr(), data.data_ptr(), u0.shape[1], iters,
+                                                     loss_history.data_ptr(), _stream_ptr(self.device)))
+        return loss_history
+
+
 class _SolveFn(torch.autograd.Function):
     """concrete_solve with its reverse rule: backward = InterpolatingAdjoint on the stored forward."""
 
@@ -475,6 +511,7 @@ class TrainResult:
     minimizer: torch.Tensor
     minimum: float
     iterations: int
+    final: Optional[torch.Tensor] = None   # theta after the last update (sciml_train_l2)
 
 
 def _loss_and_grad(loss: Callable, theta: torch.Tensor):
@@ -554,3 +591,32 @@ def sciml_train(loss: Callable, theta0, opt, cb: Optional[Callable] = None, maxi
             best, best_th = l, th.clone()
         return TrainResult(best_th, best, it)
     raise TypeError(f"unknown optimiser {opt!r}")
+
+
+def sciml_train_l2(solver: "UDESolver", theta0, u0: torch.Tensor, data: torch.Tensor, opt: "ADAM", cb: Optional[Callable] = None,
+                   maxiters: int = 100, chunk: int = 50, loss_scale: float = 1.0, l2_reg: float = 0.0) -> TrainResult:
+    """sciml_train(loss, theta, ADAM(eta); cb, maxiters) for the trajectory-matching loss
+    loss_scale * sum w (u - data)^2 + l2_reg * sum theta^2 (scenario_1.jl:91-94,111-114; scenario_2.jl:113-116) with the whole
+    iteration -- forward, adjoint, reduce, ADAM -- on the device (b200ude_train_adam).  The host looks in every `chunk`
+    iterations: cb(theta_at_chunk_start, l) is called for each recorded loss of the chunk and can halt the run at that
+    boundary; the returned minimizer is the best (theta, loss) pair seen at a chunk start.  chunk = 1 reproduces the
+    reference's per-iteration callback and best-so-far bookkeeping exactly.  `.final` holds the last theta."""
+    th = torch.as_tensor(theta0, dtype=torch.float32).to(solver.device)
+    solver.set_params(th)
+    solver.adam_reset()
+    best, best_th, it, halted = float("inf"), th.clone(), 0, False
+    while it < maxiters and not halted:
+        k = min(chunk, maxiters - it)
+        start = solver.get_params()
+        losses = solver.train_adam(opt, u0, data, k, loss_scale, l2_reg).cpu().numpy()
+        it += k
+        if float(losses[0]) < best:
+            best, best_th = float(losses[0]), start
+        if cb is not None:
+            for l in losses:
+                if cb(start, float(l)):
+                    halted = True
+                    break
+    res = TrainResult(best_th, best, it)
+    res.final = solver.get_params()
+    return res
