@@ -411,9 +411,10 @@ def test_adaptive_tsit5_forward_and_adjoint_vs_oracle(golden, O):
 
 def test_vern7_fixed_step_forward_vs_oracle(golden, O):
     """solve(prob, Vern7(); saveat, adaptive=false): 9-stage 7th-order steps on the generic kernels vs the oracle's
-    Vern7 (tableau = OrdinaryDiffEq's serialized constants, KAT-7); the adjoint of a Vern7 handle is rejected."""
+    Vern7 (tableau = OrdinaryDiffEq's serialized constants, KAT-7).  The interpolating adjoint of a Vern7 handle runs
+    over a Tsit5 re-solve with the same step (Vern7's dense output is not available): its gradient is compared with the
+    oracle's Tsit5 interpolating adjoint."""
     ude = _ude()
-    from universal_differential_equations_b200._lib import B200UDEError, EUNSUPPORTED
     g = golden["scenario_1"]
     chain = ude.FastChain(ude.FastDense(2, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 2))
     f = ude.LotkaVolterraUDE(chain)
@@ -426,9 +427,52 @@ def test_vern7_fixed_step_forward_vs_oracle(golden, O):
     assert (status == 0).all()
     assert np.abs(out[:, :, 0] - ref).max() <= 2e-5 * (1 + np.abs(ref).max())
     assert np.abs(out[:, :, 0].T - g["Xhat"]).max() <= 2e-4      # the reference's own Vern7 solution
-    with pytest.raises(B200UDEError) as e:
-        solver.adjoint(torch.zeros(61, 2, 5, device="cuda"))
-    assert e.value.code == EUNSUPPORTED
+    # gradient through the Vern7 handle
+    rng = np.random.default_rng(3)
+    y = (out + rng.normal(scale=0.1, size=out.shape)).astype(np.float32)
+    out2, loss, gth, gu, st = _run(solver, theta, u0, y)
+    l64, g64, gu64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.05, 60)
+    assert np.array_equal(out2, out)
+    assert abs(loss - l64) <= 1e-4 * abs(l64)
+    assert np.linalg.norm(gth - g64) <= 2e-3 * np.linalg.norm(g64)
+    assert np.abs(gu - gu64).max() <= 2e-3 * np.abs(gu64).max()
+    solver.close()
+
+
+def test_vern7_adaptive_forward_vs_oracle_and_reference(golden, O):
+    """The reference's own call, solve(prob, Vern7(); saveat = 0:0.05:3, abstol = reltol = 1e-6) (scenario_1.jl:41,84-85),
+    on the GPU: PI-controlled Vern7 with the save times as step end points (as the oracle's Vern7 path), from the reference's
+    start and trained parameters, against the oracle and against the reference's stored X-hat; gradient via the adaptive
+    Tsit5 re-solve."""
+    ude = _ude()
+    g = golden["scenario_1"]
+    chain = ude.FastChain(ude.FastDense(2, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 2))
+    f = ude.LotkaVolterraUDE(chain)
+    theta = g["theta_trained"].astype(np.float32)
+    rng = np.random.default_rng(5)
+    N = 40
+    u0 = (g["X"][:, :1] * rng.uniform(0.8, 1.2, (2, N))).astype(np.float32)
+    u0[:, 0] = g["X"][:, 0]
+    ts = np.linspace(0.0, 3.0, 61)
+    tol = 1e-5
+    m = O.lv_model((2, 5, 5, 5, 2), ("rbf", "rbf", "rbf", "identity"))
+    solver = ude.UDESolver(f, 0.0, 0.05, 60, 1, max_trajectories=N, alg=ude.Vern7(), adaptive=True, abstol=tol, reltol=tol, max_steps=512)
+    y = rng.normal(size=(61, 2, N)).astype(np.float32)
+    out, loss, gth, gu, status = _run(solver, theta, u0, y)
+    assert (status == 0).all()
+    for k in range(0, N, 7):
+        o64, _, _ = O.solve_adaptive(m, theta.astype(np.float64), u0[:, k].astype(np.float64), ts, tol, tol, solver=O.VERN7)
+        assert np.abs(out[:, :, k] - o64).max() <= 50 * tol * (1 + np.abs(o64).max())
+    assert np.abs(out[:, :, 0].T - g["Xhat"]).max() <= 3e-4
+    # gradient: adaptive Tsit5 interpolating adjoint at the same tolerances
+    l_ref, g_ref = 0.0, np.zeros(87)
+    for k in range(N):
+        o64, rec = O.solve_adaptive_dense(m, theta.astype(np.float64), u0[:, k].astype(np.float64), ts, tol, tol)
+        l_ref += ((o64 - y[:, :, k]) ** 2).sum()
+        gk, _ = O.adjoint_replay(m, theta.astype(np.float64), ts, rec, 2 * (o64 - y[:, :, k]))
+        g_ref += gk
+    assert abs(loss - l_ref) <= 1e-3 * abs(l_ref)
+    assert np.linalg.norm(gth - g_ref) <= 5e-3 * np.linalg.norm(g_ref)
     solver.close()
 
 

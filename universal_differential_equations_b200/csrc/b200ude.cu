@@ -80,6 +80,8 @@ struct b200ude_handle {
     cudaStream_t copy_stream = nullptr;   // host-buffer path: the data upload overlaps the forward kernel
     cudaEvent_t data_ready = nullptr;
     // on-device optimiser (b200ude_adam_*, b200ude_train_adam)
+    float *d_u0_keep = nullptr, *d_aux_out = nullptr;   // Vern7: u0 of the last forward, saved states of the Tsit5 re-solve
+    bool vern7_pending = false;
     float *d_adam_m = nullptr, *d_adam_v = nullptr, *d_train_out = nullptr;
     int *d_adam_t = nullptr;
     int adam_t = 0;   // host mirror of the step counter
@@ -158,26 +160,16 @@ KernelId pick_kernel(const b200ude_desc &d)
 }
 
 
-int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int32_t *status, cudaStream_t st)
+// Tsit5 forward solve with the dense record (stage derivatives) the interpolating adjoint reads
+int32_t tsit5_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int32_t *status, cudaStream_t st)
 {
-    if (!h->have_theta) return fail(h, B200UDE_ESTATE, "forward: set_params has not been called");
-    if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "forward: N=%zu outside (0, max_trajectories=%zu]", N, h->cap);
-    if (!u0 || !out) return fail(h, B200UDE_EINVAL, "forward: null pointer");
     FwdParams p;
     p.u0 = u0; p.out = out; p.ustep = h->d_ustep; p.dense = h->d_dense; p.status = status; p.theta = h->d_theta;
     p.N = (int)N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P; p.dt = (float)h->desc.dt;
     cudaError_t e = cudaSuccess;
-    if (h->desc.solver == B200UDE_VERN7) {
-        CUDA_TRY(h, launch_fwd_vern7(h->gen, h->tab, p, st));
-        h->N = N;
-        h->have_forward = false;   // no dense output is recorded: the adjoint of a Vern7 solve is not available
-        return B200UDE_OK;
-    }
     if (h->adaptive) {
         e = launch_fwd_adaptive(h->gen, h->tab, p, h->ag, st);
         CUDA_TRY(h, e);
-        h->N = N;
-        h->have_forward = true;
         h->last_out = out;
         return B200UDE_OK;
     }
@@ -192,6 +184,33 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
     default: return fail(h, B200UDE_EUNSUPPORTED, "forward: no kernel");
     }
     CUDA_TRY(h, e);
+    return B200UDE_OK;
+}
+
+int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int32_t *status, cudaStream_t st)
+{
+    if (!h->have_theta) return fail(h, B200UDE_ESTATE, "forward: set_params has not been called");
+    if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "forward: N=%zu outside (0, max_trajectories=%zu]", N, h->cap);
+    if (!u0 || !out) return fail(h, B200UDE_EINVAL, "forward: null pointer");
+    if (h->desc.solver == B200UDE_VERN7) {
+        // Vern7 writes the saved states only.  Its lazy dense output is not available, so the
+        // interpolating adjoint of a Vern7 solve runs over a Tsit5 re-solve from the same u0 with the same step /
+        // tolerances, launched by the first adjoint call (do_adjoint); u0 is kept for that.
+        FwdParams p;
+        p.u0 = u0; p.out = out; p.ustep = nullptr; p.dense = nullptr; p.status = status; p.theta = h->d_theta;
+        p.N = (int)N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P; p.dt = (float)h->desc.dt;
+        if (h->adaptive) CUDA_TRY(h, launch_fwd_vern7_adaptive(h->gen, h->tab, p, h->ag, st));
+        else CUDA_TRY(h, launch_fwd_vern7(h->gen, h->tab, p, st));
+        if (!h->d_u0_keep && dalloc(h, &h->d_u0_keep, (size_t)h->D * h->cap) != cudaSuccess)
+            return fail(h, B200UDE_ENOMEM, "forward: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_u0_keep, u0, sizeof(float) * (size_t)h->D * N, cudaMemcpyDeviceToDevice, st));
+        h->N = N;
+        h->have_forward = false;
+        h->vern7_pending = true;
+        return B200UDE_OK;
+    }
+    int32_t rc = tsit5_forward(h, u0, N, out, status, st);
+    if (rc) return rc;
     h->N = N;
     h->have_forward = true;
     return B200UDE_OK;
@@ -200,8 +219,14 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
 int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, float *grad_theta,
                    float *grad_u0, cudaStream_t st)
 {
-    if (h->desc.solver == B200UDE_VERN7)
-        return fail(h, B200UDE_EUNSUPPORTED, "adjoint: the interpolating adjoint needs Vern7's dense output, which this build does not have; use Tsit5");
+    if (h->desc.solver == B200UDE_VERN7 && h->vern7_pending) {
+        if (!h->d_aux_out && dalloc(h, &h->d_aux_out, (size_t)h->n_save * (size_t)h->D * h->cap) != cudaSuccess)
+            return fail(h, B200UDE_ENOMEM, "adjoint: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        int32_t rc = tsit5_forward(h, h->d_u0_keep, h->N, h->d_aux_out, nullptr, st);
+        if (rc) return rc;
+        h->vern7_pending = false;
+        h->have_forward = true;
+    }
     if (!h->have_forward) return fail(h, B200UDE_ESTATE, "adjoint: no stored forward solution (call b200ude_forward first)");
     if (!cot || !grad_theta) return fail(h, B200UDE_EINVAL, "adjoint: null pointer");
     AdjParams p;
@@ -341,8 +366,8 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     if (d->n_loss_weights != 0 && d->n_loss_weights != d->state_dim) return fail(nullptr, B200UDE_EINVAL, "create: n_loss_weights must be 0 or state_dim");
     KernelId kid = pick_kernel(*d);
     if (d->solver == B200UDE_VERN7) {
-        if (d->adaptive || !generic_ok(*d) || d->model == B200UDE_MODEL_FKPP)
-            return fail(nullptr, B200UDE_EUNSUPPORTED, "create: Vern7 has a fixed-step forward kernel for the LV / SEIR / NODE forms only");
+        if (!generic_ok(*d) || d->model == B200UDE_MODEL_FKPP)
+            return fail(nullptr, B200UDE_EUNSUPPORTED, "create: Vern7 kernels exist for the LV / SEIR / NODE forms only");
         kid = K_GENERIC;
     }
     if (d->adaptive) {
@@ -447,6 +472,7 @@ void b200ude_destroy(b200ude_handle *h)
     cudaFree(h->d_theta); cudaFree(h->d_ustep); cudaFree(h->d_dense); cudaFree(h->d_partial);
     cudaFree(h->d_u0); cudaFree(h->d_out); cudaFree(h->d_data); cudaFree(h->d_gu0); cudaFree(h->d_grad);
     cudaFree(h->d_loss); cudaFree(h->d_status);
+    cudaFree(h->d_u0_keep); cudaFree(h->d_aux_out);
     cudaFree(h->d_adam_m); cudaFree(h->d_adam_v); cudaFree(h->d_adam_t); cudaFree(h->d_train_out);
     cudaFree(h->d_tgrid); cudaFree(h->d_nacc); cudaFree(h->d_cot); cudaFree(h->d_block_loss);
     if (h->h_loss) cudaFreeHost(h->h_loss);

@@ -61,6 +61,17 @@ cudaError_t launch_fwd_vern7(const GenericShape &g, const ConstTables &t, const 
     return cudaGetLastError();
 }
 
+cudaError_t launch_fwd_vern7_adaptive(const GenericShape &g, const ConstTables &t, const FwdParams &p, const AdaptiveGrid &ag, cudaStream_t st)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    e = upload_gen(g, st);
+    if (e != cudaSuccess) return e;
+    generic::AdaptParams ap{ag.t0, ag.save_dt, ag.abstol, ag.reltol, ag.n_save, ag.max_steps, nullptr, nullptr};   // no step record
+    generic::vern7_adaptive_forward_kernel<GEN_BLOCK><<<(p.N + GEN_BLOCK - 1) / GEN_BLOCK, GEN_BLOCK, 0, st>>>(p, ap);
+    return cudaGetLastError();
+}
+
 // ---- adaptive stepping ----
 cudaError_t launch_fwd_adaptive(const GenericShape &g, const ConstTables &t, const FwdParams &p, const AdaptiveGrid &ag, cudaStream_t st)
 {

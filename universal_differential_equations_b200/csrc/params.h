@@ -80,6 +80,7 @@ cudaError_t launch_fwd_generic(const GenericShape &, const ConstTables &, const 
 cudaError_t launch_adj_generic(const GenericShape &, const ConstTables &, const AdjParams &, cudaStream_t, int *rows_out);
 int adj_rows_generic(int N);
 cudaError_t launch_fwd_vern7(const GenericShape &, const ConstTables &, const FwdParams &, cudaStream_t);
+cudaError_t launch_fwd_vern7_adaptive(const GenericShape &, const ConstTables &, const FwdParams &, const AdaptiveGrid &, cudaStream_t);
 cudaError_t launch_fwd_adaptive(const GenericShape &, const ConstTables &, const FwdParams &, const AdaptiveGrid &, cudaStream_t);
 cudaError_t launch_adj_adaptive(const GenericShape &, const ConstTables &, const AdjParams &, const AdaptiveGrid &, cudaStream_t, int *rows_out);
 cudaError_t launch_l2_cot(const ConstTables &, const float *out, const float *data, float *cot, float *block_loss, int D, size_t N, int n_save, cudaStream_t);

@@ -480,6 +480,112 @@ __global__ void __launch_bounds__(BLOCK, 1) adaptive_forward_kernel(FwdParams p,
     }
 }
 
+// Vern7 with OrdinaryDiffEq's PI controller (abstol / reltol; scenario_1.jl:84-85, seir_exposure.jl:138-139).  The lazy
+// 7th-order interpolant is not available (see above), so the save times are step end points (tstops), exactly as the
+// oracle's Vern7 path does; the step sequence between save points is the controller's own.  Forward solve only: no dense
+// record is written (the gradient of a Vern7 solve is taken over a Tsit5 re-solve, see b200ude.cu).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) vern7_adaptive_forward_kernel(FwdParams p, AdaptParams ap)
+{
+    const int D = c_gen.D;
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    if (gid >= p.N) return;
+    const size_t n = (size_t)gid;
+    const float t0 = ap.t0, t1 = ap.t0 + ap.save_dt * (float)(ap.n_save - 1);
+    const float abstol = ap.abstol, reltol = ap.reltol;
+    const float gamma = 0.9f, qmin = 0.2f, qmax = 10.0f, beta1 = 7.0f / 70.0f, beta2 = 2.0f / 35.0f;   // order 7
+    float u[MAXD], un[MAXD], g[MAXD], k[10][MAXD];
+    for (int c = 0; c < D; ++c) u[c] = __ldg(p.u0 + (size_t)c * N + n);
+    for (int c = 0; c < D; ++c) p.out[(size_t)c * N + n] = u[c];
+    model_rhs(u, k[0]);
+    float dt;
+    {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        for (int c = 0; c < D; ++c) {
+            const float sk = abstol + reltol * fabsf(u[c]);
+            d0 += (u[c] / sk) * (u[c] / sk);
+            d1 += (k[0][c] / sk) * (k[0][c] / sk);
+        }
+        d0 = sqrtf(d0 / D); d1 = sqrtf(d1 / D);
+        float dt0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+        dt0 = fminf(dt0, t1 - t0);
+        for (int c = 0; c < D; ++c) g[c] = fmaf(dt0, k[0][c], u[c]);
+        model_rhs(g, un);
+        for (int c = 0; c < D; ++c) {
+            const float sk = abstol + reltol * fabsf(u[c]);
+            const float e = (un[c] - k[0][c]) / sk;
+            d2 += e * e;
+        }
+        d2 = sqrtf(d2 / D) / dt0;
+        const float dm = fmaxf(d1, d2);
+        const float dt1 = dm <= 1e-15f ? fmaxf(1e-6f, dt0 * 1e-3f) : exp10f(-(2.0f + log10f(dm)) / 7.0f);
+        dt = fminf(fminf(100.0f * dt0, dt1), t1 - t0);
+    }
+    float t = t0, qold = 1e-4f;
+    int nacc = 0, isave = 1, bad = 0;
+    bool have_k1 = true;
+    while (isave < ap.n_save) {
+        const float tend = t0 + ap.save_dt * (float)isave;
+        float h = dt;
+        bool clipped = false;
+        if (t + h >= tend - 1e-6f * fabsf(tend)) { h = tend - t; clipped = true; }
+        if (!have_k1) model_rhs(u, k[0]);
+#pragma unroll
+        for (int i = 1; i < 10; ++i) {
+            for (int c = 0; c < D; ++c) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                    if (Vern7::a(i, j) != 0.0) acc = fmaf((float)Vern7::a(i, j), k[j][c], acc);
+                g[c] = fmaf(h, acc, u[c]);
+            }
+            model_rhs(g, k[i]);
+        }
+        float ee = 0.0f;
+        for (int c = 0; c < D; ++c) {
+            float acc = 0.0f, e = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                if (Vern7::b(j) != 0.0) acc = fmaf((float)Vern7::b(j), k[j][c], acc);
+                if (Vern7::bt(j) != 0.0) e = fmaf((float)Vern7::bt(j), k[j][c], e);
+            }
+            un[c] = fmaf(h, acc, u[c]);
+            e *= h;
+            const float sc = abstol + reltol * fmaxf(fabsf(u[c]), fabsf(un[c]));
+            ee += (e / sc) * (e / sc);
+        }
+        const float EEst = sqrtf(ee / D);
+        if (!(EEst <= 3.0e38f)) { bad = 1; break; }
+        const float q11 = powf(EEst, beta1);
+        float q = fminf(fmaxf(q11 / powf(qold, beta2) / gamma, 1.0f / qmax), 1.0f / qmin);
+        if (EEst <= 1.0f) {
+            if (nacc >= ap.max_steps) { bad = 2; break; }
+            ++nacc;
+            if (clipped) {
+                for (int c = 0; c < D; ++c) p.out[((size_t)isave * D + c) * N + n] = un[c];
+                ++isave;
+            }
+            qold = fmaxf(EEst, 1e-4f);
+            if (q >= 1.0f && q <= 1.2f) q = 1.0f;
+            if (!clipped || h >= dt) dt = h / q;
+            else dt = fmaxf(dt, h / q);
+            t = clipped ? tend : t + h;
+            for (int c = 0; c < D; ++c) u[c] = un[c];
+            have_k1 = false;   // not FSAL
+        } else {
+            dt = h / fminf(1.0f / qmin, q11 / gamma);
+            have_k1 = true;    // k_1 = f(u) is still valid after a rejection
+        }
+    }
+    if (ap.nacc) ap.nacc[n] = nacc;
+    if (p.status) {
+        bool ok = true;
+        for (int c = 0; c < D; ++c) ok = ok && (fabsf(u[c]) <= 3.0e38f);
+        p.status[n] = bad == 2 ? 2 : ((bad || !ok) ? 1 : 0);
+    }
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) adaptive_adjoint_kernel(AdjParams p, AdaptParams ap)
 {

@@ -42,6 +42,13 @@ struct Vern7 {
         case 8 * 16 + 5: return 2.0098622683770357;
         case 8 * 16 + 6: return 0.3487490460338272;
         case 8 * 16 + 7: return -0.27143900510483127;
+        // 10th stage: error estimate only
+        case 9 * 16 + 0: return -45.030072034298676;
+        case 9 * 16 + 2: return 187.3272437654589;
+        case 9 * 16 + 3: return -154.02882369350186;
+        case 9 * 16 + 4: return 18.56465306347536;
+        case 9 * 16 + 5: return -7.141809679295079;
+        case 9 * 16 + 6: return 1.3088085781613787;
         default: return 0.0;
         }
     }
@@ -55,6 +62,21 @@ struct Vern7 {
         case 6: return 0.4939969170032485;
         case 7: return -0.29430311714032503;
         case 8: return 0.08131747232495111;
+        default: return 0.0;
+        }
+    }
+    // error weights: err = dt * sum_j bt(j) k_j over the 10 stages
+    __host__ __device__ static constexpr double bt(int j)
+    {
+        switch (j) {
+        case 0: return 0.002547011879931045;
+        case 3: return -0.00965839487279575;
+        case 4: return 0.04206470975639691;
+        case 5: return -0.0666822437469301;
+        case 6: return 0.2650097464621281;
+        case 7: return -0.29430311714032503;
+        case 8: return 0.08131747232495111;
+        case 9: return -0.02029518466335628;
         default: return 0.0;
         }
     }
