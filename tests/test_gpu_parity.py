@@ -352,6 +352,39 @@ def test_fisher_kpp_upde_vs_oracle(O, widths, acts, nx, N):
     solver.close()
 
 
+@pytest.mark.parametrize("nx,N", [(26, 7), (100, 3), (256, 5)])
+def test_fisher_kpp_tuned_vs_runtime_shape_kernels(nx, N, monkeypatch):
+    """Tuned 1-16-16-1 Fisher-KPP kernels (k_fkpp.cu) against the runtime-shape kernels: partially filled CTAs
+    (7 trajectories at 4 per CTA), grids that are not a warp multiple, explicit cotangent and fused-L2 paths."""
+    ude = _ude()
+    rng = np.random.default_rng(nx)
+    widths = (1, 16, 16, 1)
+    layers = [ude.FastDense(1, 16, ude.tanh), ude.FastDense(16, 16, ude.tanh), ude.FastDense(16, 1)]
+    f = ude.FisherKPPUDE(ude.FastChain(*layers), nx)
+    theta = np.concatenate([glorot_theta(widths, seed=4), [1.1, -2.3, 0.9, 0.0, 0.01 * (nx - 1) ** 2]]).astype(np.float32)
+    x = np.linspace(0, 1, nx)
+    u0 = np.stack([0.5 * (np.tanh((x - (0.5 - d / 2)) / (d / 10)) - np.tanh((x - (0.5 + d / 2)) / (d / 10))) for d in rng.uniform(0.15, 0.5, N)], axis=1).astype(np.float32)
+    dt = 2.5 / (4 * 0.01 * (nx - 1) ** 2) / 4
+    n_steps, every = 40, 8
+    y = (np.repeat(u0[None], n_steps // every + 1, axis=0) + rng.normal(scale=0.05, size=(n_steps // every + 1, nx, N))).astype(np.float32)
+    cot = rng.standard_normal(y.shape).astype(np.float32)
+    res = []
+    for tuned in ("1", "0"):
+        monkeypatch.setenv("B200UDE_FKPP_TUNED", tuned)
+        solver = ude.UDESolver(f, 0.0, dt, n_steps, every, max_trajectories=N)
+        out, loss, g, gu, status = _run(solver, theta, u0, y)
+        g2, gu2 = solver.adjoint(torch.from_numpy(cot).cuda(), want_grad_u0=True)
+        torch.cuda.synchronize()
+        assert (status == 0).all()
+        res.append((out, loss, g, gu, g2.cpu().numpy(), gu2.cpu().numpy()))
+        solver.close()
+    a, b = res
+    assert np.abs(a[0] - b[0]).max() <= 2e-6 * (1 + np.abs(b[0]).max())
+    assert abs(a[1] - b[1]) <= 1e-5 * abs(b[1])
+    for k in (2, 3, 4, 5):
+        assert np.linalg.norm(a[k] - b[k]) <= 1e-4 * np.linalg.norm(b[k]), k
+
+
 def test_fisher_kpp_golden_forward(golden, O):
     """KAT-6 on the GPU: scenario_3's trained parameters reproduce its stored X-hat (26 x 11, Float32)."""
     ude = _ude()

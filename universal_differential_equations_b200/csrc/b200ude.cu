@@ -30,13 +30,15 @@ thread_local std::string g_create_error;
 //            coverage (seir_exposure.jl:114-130 shapes), not tuned
 //   K_FKPP     Fisher-KPP UPDE: pointwise chain 1 -> ... -> 1 + 3-tap periodic stencil (Fisher-KPP-CNN.jl:111-126)
 //   K_SEIR64   SEIR exposure UDE 3 -> 64 -> 64 -> 1 tanh, tensor-core kernels (k_seir.cu)      BASELINE config 3
-enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2, K_GENERIC, K_FKPP, K_SEIR64 };
+//   K_FKPP16   Fisher-KPP UPDE with the 1 -> 16 -> 16 -> 1 tanh reaction chain (k_fkpp.cu)                BASELINE config 4
+enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2, K_GENERIC, K_FKPP, K_SEIR64, K_FKPP16 };
 
 int kernel_num_params(KernelId k)
 {
     switch (k) {
     case K_LV32: return 2 * 32 + 32 + 32 * 32 + 32 + 32 * 2 + 2;
     case K_SEIR64: return 3 * 64 + 64 + 64 * 64 + 64 + 64 + 1;
+    case K_FKPP16: return 16 + 16 + 256 + 16 + 16 + 1 + 5;
     case K_LV5P0: return 87;
     case K_LV5P1: return 88;
     case K_LV5P2: return 89;
@@ -156,6 +158,9 @@ KernelId pick_kernel(const b200ude_desc &d)
     if (d.model == B200UDE_MODEL_SEIR && d.n_layers == 3 && d.widths[1] == 64 && d.widths[2] == 64 && d.acts[0] == B200UDE_ACT_TANH &&
         d.acts[1] == B200UDE_ACT_TANH && d.acts[2] == B200UDE_ACT_IDENTITY && d.n_suffix == 0 && env_int("B200UDE_SEIR_TC", 1))
         return K_SEIR64;
+    if (d.model == B200UDE_MODEL_FKPP && d.n_layers == 3 && d.widths[1] == 16 && d.widths[2] == 16 && d.acts[0] == B200UDE_ACT_TANH &&
+        d.acts[1] == B200UDE_ACT_TANH && d.acts[2] == B200UDE_ACT_IDENTITY && env_int("B200UDE_FKPP_TUNED", 1))
+        return K_FKPP16;
     return d.model == B200UDE_MODEL_FKPP ? K_FKPP : K_GENERIC;
 }
 
@@ -181,6 +186,7 @@ int32_t tsit5_forward(b200ude_handle *h, const float *u0, size_t N, float *out, 
     case K_GENERIC: e = launch_fwd_generic(h->gen, h->tab, p, st); break;
     case K_FKPP: e = launch_fwd_fkpp(h->gen, h->tab, p, st); break;
     case K_SEIR64: e = launch_fwd_seir(h->var, h->tab, p, st); break;
+    case K_FKPP16: e = launch_fwd_fkpp16(h->var, h->tab, p, h->D, st); break;
     default: return fail(h, B200UDE_EUNSUPPORTED, "forward: no kernel");
     }
     CUDA_TRY(h, e);
@@ -255,6 +261,7 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     case K_GENERIC: e = launch_adj_generic(h->gen, h->tab, p, st, &grid); break;
     case K_FKPP: e = launch_adj_fkpp(h->gen, h->tab, p, st, &grid); break;
     case K_SEIR64: e = launch_adj_seir(h->var, h->tab, p, st, &grid); break;
+    case K_FKPP16: e = launch_adj_fkpp16(h->var, h->tab, p, h->D, st, &grid); break;
     default: return fail(h, B200UDE_EUNSUPPORTED, "adjoint: no kernel");
     }
     CUDA_TRY(h, e);
@@ -422,7 +429,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->var.adj_tc = env_int("B200UDE_ADJ_TC", 1);
 
     const size_t N = h->cap, D = (size_t)h->D;
-    h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : kid == K_SEIR64 ? adj_rows_seir((int)N) : adj_grid_lv5((int)N));
+    h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : kid == K_SEIR64 ? adj_rows_seir((int)N) : kid == K_FKPP16 ? adj_rows_fkpp16((int)N, d->state_dim) : adj_grid_lv5((int)N));
     bool ok = true;
     ok = ok && dalloc(h, &h->d_theta, (size_t)((h->P + 3) / 4) * 4) == cudaSuccess;
     const size_t rec_steps = h->adaptive ? (size_t)d->max_steps : (size_t)d->n_steps;   // capacity of the step record

@@ -1,0 +1,398 @@
+// fkpp_tuned.cuh -- Fisher-KPP UPDE kernels for a compile-time reaction chain 1 -> H -> H -> 1 (tanh, tanh, identity):
+// BASELINE config 4 (256-point grid, 1 -> 16 -> 16 -> 1).  Replaces, per Runge-Kutta stage and for every grid point of every
+// ensemble member, the reference's `nn_ode` (FisherKPP/Fisher-KPP-CNN.jl:111-126; Lux twin scenario_3.jl:103-114):
+//     du_i = rx_nn([u_i]) + D0 * (w1 u_{i-1} + w2 u_i + w3 u_{i+1}),  periodic wrap,
+// theta = [chain | w1, w2, w3, conv bias (unused), D0] (Fisher-KPP-CNN.jl:106-109), and its interpolating adjoint.
+//
+// One thread per grid point, a CTA holds whole trajectories (same geometry and handle-internal point-fastest stores as the
+// runtime-shape kernels in ude_generic.cuh, which remain the path for every other chain shape).  What is tuned here:
+//   * chain weights are compile-time-indexed 128-bit constant-bank loads (uniform registers), the RHS is one function;
+//   * u and lambda neighbours travel through ONE double-buffered shared-memory exchange per stage (one barrier);
+//   * the ensemble-summed gradient of the H x H layer is a per-warp FFMA2 outer-product GEMM over the warp's 32 points
+//     (operands staged as conflict-free 128-bit rows, 2 x 4 register tile per lane), everything thin (first/last layer,
+//     biases, stencil weights, D0) accumulates in per-lane registers and is reduced once, at the end of the kernel, with
+//     a fixed shuffle tree and a fixed-order sum over the CTA's warps -> bitwise reproducible.
+#pragma once
+#include "lv32_packed.cuh"   // fma2 / bc / ldw4 / c_zero helpers
+#include "ude_adjoint.cuh"
+
+namespace b200ude {
+namespace fkpp {
+
+using lv32::bc;
+using lv32::fma2;
+using lv32::ldw4;
+
+struct Geom {
+    int Nx, tpc;   // grid points per trajectory, trajectories per CTA
+};
+
+template <int H>
+struct Off {
+    static constexpr int W1 = 0, B1 = H, W2 = 2 * H, B2 = 2 * H + H * H, W3 = 3 * H + H * H, B3 = 4 * H + H * H;
+    static constexpr int CHAIN = 4 * H + H * H + 1;
+    static constexpr int SX = CHAIN;          // w1, w2, w3, conv bias, D0
+    static constexpr int P = CHAIN + 5;
+};
+
+// reaction chain, value only
+template <int H, int TM>
+__device__ __noinline__ float chain_value(float g, int zsel)
+{
+    using O = Off<H>;
+    const int zb = lv32::c_zero[zsel & 7] << 2;
+    float h1[H];
+#pragma unroll
+    for (int j4 = 0; j4 < H; j4 += 4) {
+        const float4 w = ldw4(zb + O::W1 + j4), b = ldw4(zb + O::B1 + j4);
+        h1[j4 + 0] = tanh_dev<TM>(fmaf(w.x, g, b.x));
+        h1[j4 + 1] = tanh_dev<TM>(fmaf(w.y, g, b.y));
+        h1[j4 + 2] = tanh_dev<TM>(fmaf(w.z, g, b.z));
+        h1[j4 + 3] = tanh_dev<TM>(fmaf(w.w, g, b.w));
+    }
+    float a2[H];
+#pragma unroll
+    for (int j4 = 0; j4 < H; j4 += 4) {
+        const float4 b = ldw4(zb + O::B2 + j4);
+        a2[j4] = b.x; a2[j4 + 1] = b.y; a2[j4 + 2] = b.z; a2[j4 + 3] = b.w;
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4) {
+            const float4 w = ldw4(zb + O::W2 + i * H + j4);
+            a2[j4 + 0] = fmaf(w.x, h1[i], a2[j4 + 0]);
+            a2[j4 + 1] = fmaf(w.y, h1[i], a2[j4 + 1]);
+            a2[j4 + 2] = fmaf(w.z, h1[i], a2[j4 + 2]);
+            a2[j4 + 3] = fmaf(w.w, h1[i], a2[j4 + 3]);
+        }
+    }
+    float y0 = c_theta[zb + O::B3], y1 = 0.0f;
+#pragma unroll
+    for (int j4 = 0; j4 < H; j4 += 4) {
+        const float4 w = ldw4(zb + O::W3 + j4);
+        y0 = fmaf(w.x, tanh_dev<TM>(a2[j4 + 0]), y0);
+        y1 = fmaf(w.y, tanh_dev<TM>(a2[j4 + 1]), y1);
+        y0 = fmaf(w.z, tanh_dev<TM>(a2[j4 + 2]), y0);
+        y1 = fmaf(w.w, tanh_dev<TM>(a2[j4 + 3]), y1);
+    }
+    return y0 + y1;
+}
+
+// ---- forward ----------------------------------------------------------------------------------------------------------
+template <int H, int TM>
+__global__ void __launch_bounds__(256) forward_kernel(FwdParams p, Geom geo)
+{
+    using O = Off<H>;
+    extern __shared__ __align__(16) float s_dyn[];   // [2][slots] neighbour exchange, double buffered
+    const int Nx = geo.Nx, slots = geo.tpc * Nx;
+    const int slot = threadIdx.x;
+    const bool valid = slot < slots;
+    const int t_loc = valid ? slot / Nx : 0, i = valid ? slot % Nx : 0;
+    const int base = t_loc * Nx;
+    const int im = base + (i + Nx - 1) % Nx, ip = base + (i + 1) % Nx;
+    const int traj = blockIdx.x * geo.tpc + t_loc;
+    const bool live = valid && traj < p.N;
+    const size_t N = (size_t)p.N, n = (size_t)(live ? traj : p.N - 1);
+    const float dt = p.dt;
+    const float w1 = c_theta[O::SX], w2 = c_theta[O::SX + 1], w3 = c_theta[O::SX + 2], D0 = c_theta[O::SX + 4];
+    float u = __ldg(p.u0 + (size_t)i * N + n);
+    int flip = 0;
+    auto rhs = [&](float g, int zsel) {
+        float *sU = s_dyn + flip * slots;
+        flip ^= 1;
+        if (valid) sU[slot] = g;
+        __syncthreads();   // the buffer written two evaluations ago is free again: every thread passed this barrier since
+        const float gm = sU[im], gp = sU[ip];
+        const float y = chain_value<H, TM>(g, zsel);
+        return fmaf(D0, fmaf(w1, gm, fmaf(w2, g, w3 * gp)), y);
+    };
+    auto store_int = [&](float *b, int row, float v) { if (live) b[((size_t)row * N + n) * Nx + i] = v; };
+    auto store_abi = [&](float *b, int row, float v) { if (live) b[((size_t)row * Nx + i) * N + n] = v; };
+    store_abi(p.out, 0, u);
+    store_int(p.ustep, 0, u);
+    float k[7];
+    k[0] = rhs(u, 0);
+    store_int(p.dense, 0, k[0]);
+#pragma unroll
+    for (int j = 1; j < 7; ++j) k[j] = 0.0f;
+    int isave = 1;
+#pragma unroll 1
+    for (int s = 0; s < p.n_steps; ++s) {
+#pragma unroll 1
+        for (int st = 1; st < 7; ++st) {
+            float acc = 0.0f;
+#define B200UDE_FKPP_COMB(I)                                                                                  \
+    case I: {                                                                                                 \
+        _Pragma("unroll") for (int j = 0; j < I; ++j) if (Tsit5::a(I, j) != 0.0) acc = fmaf((float)Tsit5::a(I, j), k[j], acc); \
+    } break;
+            switch (st) {
+                B200UDE_FKPP_COMB(1)
+                B200UDE_FKPP_COMB(2)
+                B200UDE_FKPP_COMB(3)
+                B200UDE_FKPP_COMB(4)
+                B200UDE_FKPP_COMB(5)
+            default:
+                B200UDE_FKPP_COMB(6)
+            }
+#undef B200UDE_FKPP_COMB
+            const float g = fmaf(dt, acc, u);
+            if (st == 6) u = g;
+            const float kk = rhs(g, st);
+            switch (st) {
+            case 1: k[1] = kk; break;
+            case 2: k[2] = kk; break;
+            case 3: k[3] = kk; break;
+            case 4: k[4] = kk; break;
+            case 5: k[5] = kk; break;
+            default: k[6] = kk; break;
+            }
+            store_int(p.dense, s * 6 + st, kk);
+        }
+        store_int(p.ustep, s + 1, u);
+        if ((s + 1) % p.save_every == 0) { store_abi(p.out, isave, u); ++isave; }
+        k[0] = k[6];
+    }
+    if (p.status) {   // a trajectory is flagged when any of its points is non-finite
+        __syncthreads();
+        float *sU = s_dyn;
+        if (valid) sU[slot] = (fabsf(u) <= 3.0e38f) ? 0.0f : 1.0f;
+        __syncthreads();
+        if (live && i == 0) {
+            float any = 0.0f;
+            for (int q = 0; q < Nx; ++q) any += sU[base + q];
+            p.status[n] = any > 0.0f ? 1 : 0;
+        }
+    }
+}
+
+// ---- adjoint ----------------------------------------------------------------------------------------------------------
+template <int H>
+struct __align__(16) WarpRows {
+    static constexpr int LD = H + 4;   // 128-bit rows, conflict-free for the per-lane row stores and the tile loads
+    float Q[32 * LD];                  // q2 rows of the warp's 32 points
+    float A[32 * LD];                  // h1 rows
+};
+
+template <int H, int TM>
+__global__ void __launch_bounds__(256) adjoint_kernel(AdjParams p, Geom geo)
+{
+    using O = Off<H>;
+    static_assert(H == 16, "the 2 x 4 lane tile below covers a 16 x 16 layer with 32 lanes");
+    constexpr int P = O::P;
+    extern __shared__ __align__(16) float s_dyn[];
+    const int Nx = geo.Nx, slots = geo.tpc * Nx;
+    const int nwarp = blockDim.x >> 5;
+    float2 *sX = reinterpret_cast<float2 *>(s_dyn);                       // [2][slots] (x, g) exchange, double buffered
+    WarpRows<H> *rows = reinterpret_cast<WarpRows<H> *>(s_dyn + 4 * ((slots + 1) / 2) * 2);
+    const int slot = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpRows<H> &wr = rows[warp];
+    const bool valid = slot < slots;
+    const int t_loc = valid ? slot / Nx : 0, i = valid ? slot % Nx : 0;
+    const int base = t_loc * Nx;
+    const int im = base + (i + Nx - 1) % Nx, ip = base + (i + 1) % Nx;
+    const int traj = blockIdx.x * geo.tpc + t_loc;
+    const bool live = valid && traj < p.N;
+    const size_t N = (size_t)p.N, n = (size_t)(live ? traj : p.N - 1);
+    const float lv = live ? 1.0f : 0.0f;
+    const float dt = p.dt, inv_dt = 1.0f / dt;
+    const float w1 = c_theta[O::SX], w2 = c_theta[O::SX + 1], w3 = c_theta[O::SX + 2], D0 = c_theta[O::SX + 4];
+    const int jt = lane >> 2, it = lane & 3;   // dW2 tile: j = 2 jt + {0, 1}, i = 4 it + {0..3}
+
+    float2 acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = bc(0.0f);
+    float a_w3[H], a_b2[H], a_w1[H], a_b1[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) { a_w3[j] = 0.f; a_b2[j] = 0.f; a_w1[j] = 0.f; a_b1[j] = 0.f; }
+    float a_b3 = 0.f, a_s1 = 0.f, a_s2 = 0.f, a_s3 = 0.f, a_D0 = 0.f;
+
+    float lam = 0.0f, loss = 0.0f;
+    auto jump = [&](int isave) {
+        const size_t idx = ((size_t)isave * Nx + i) * N + n;   // ABI layout
+        if (p.fused_l2) {
+            const float r = __ldg(p.ustep + ((size_t)(isave * p.save_every) * N + n) * Nx + i) - __ldg(p.cot + idx);
+            loss = fmaf(r, r, loss);
+            lam = fmaf(2.0f, r, lam);
+        } else {
+            lam += __ldg(p.cot + idx);
+        }
+    };
+    const int n_save = p.n_steps / p.save_every + 1;
+    jump(n_save - 1);
+    int flip = 0;
+#pragma unroll 1
+    for (int s = p.n_steps - 1; s >= 0; --s) {
+        float kl[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) kl[j] = 0.0f;
+#pragma unroll 1
+        for (int st = 0; st < 6; ++st) {
+            float xa = 0.0f, ga = 0.0f, sc, isc;
+#define B200UDE_FKPP_PRE(I)                                                                                              \
+    case I: {                                                                                                            \
+        _Pragma("unroll") for (int j = 0; j < 7; ++j) if (Tsit5::bw(I, j) != 0.0)                                         \
+            xa = fmaf((float)Tsit5::bw(I, j), __ldg(p.dense + ((size_t)(s * 6 + j) * N + n) * Nx + i), xa);               \
+        _Pragma("unroll") for (int j = 0; j < I; ++j) if (Tsit5::a(I, j) != 0.0) ga = fmaf((float)Tsit5::a(I, j), kl[j], ga); \
+        sc = dt * (float)Tsit5::b(I);                                                                                    \
+        isc = inv_dt * (float)(1.0 / Tsit5::b(I));                                                                       \
+    } break;
+            switch (st) {
+                B200UDE_FKPP_PRE(0)
+                B200UDE_FKPP_PRE(1)
+                B200UDE_FKPP_PRE(2)
+                B200UDE_FKPP_PRE(3)
+                B200UDE_FKPP_PRE(4)
+            default:
+                B200UDE_FKPP_PRE(5)
+            }
+#undef B200UDE_FKPP_PRE
+            const float x = fmaf(dt, xa, __ldg(p.ustep + ((size_t)s * N + n) * Nx + i));
+            const float g = fmaf(dt, ga, lam);
+            const int zb = lv32::c_zero[st] << 2;
+            // neighbours of u (stencil-weight gradients) and of lambda (transposed stencil): one exchange
+            float2 *sx = sX + flip * slots;
+            flip ^= 1;
+            if (valid) sx[slot] = make_float2(x, g);
+            __syncthreads();
+            const float2 nm = sx[im], np = sx[ip];
+            const float sg = lv * sc * g;
+            // ---- chain forward, activations kept ----
+            float h1[H], v[H];
+#pragma unroll
+            for (int j4 = 0; j4 < H; j4 += 4) {
+                const float4 w = ldw4(zb + O::W1 + j4), b = ldw4(zb + O::B1 + j4);
+                h1[j4 + 0] = tanh_dev<TM>(fmaf(w.x, x, b.x));
+                h1[j4 + 1] = tanh_dev<TM>(fmaf(w.y, x, b.y));
+                h1[j4 + 2] = tanh_dev<TM>(fmaf(w.z, x, b.z));
+                h1[j4 + 3] = tanh_dev<TM>(fmaf(w.w, x, b.w));
+                *reinterpret_cast<float4 *>(&wr.A[lane * WarpRows<H>::LD + j4]) = make_float4(h1[j4], h1[j4 + 1], h1[j4 + 2], h1[j4 + 3]);
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < H; j4 += 4) {
+                const float4 b = ldw4(zb + O::B2 + j4);
+                v[j4] = b.x; v[j4 + 1] = b.y; v[j4 + 2] = b.z; v[j4 + 3] = b.w;
+            }
+#pragma unroll
+            for (int ii = 0; ii < H; ++ii) {
+#pragma unroll
+                for (int j4 = 0; j4 < H; j4 += 4) {
+                    const float4 w = ldw4(zb + O::W2 + ii * H + j4);
+                    v[j4 + 0] = fmaf(w.x, h1[ii], v[j4 + 0]);
+                    v[j4 + 1] = fmaf(w.y, h1[ii], v[j4 + 1]);
+                    v[j4 + 2] = fmaf(w.z, h1[ii], v[j4 + 2]);
+                    v[j4 + 3] = fmaf(w.w, h1[ii], v[j4 + 3]);
+                }
+            }
+            // h2 = tanh(v); output-layer gradients; q2 = W3 * sg * (1 - h2^2) -> v and the warp's Q rows
+            a_b3 += sg;
+#pragma unroll
+            for (int j4 = 0; j4 < H; j4 += 4) {
+                const float4 w = ldw4(zb + O::W3 + j4);
+                const float w_[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float h2 = tanh_dev<TM>(v[j4 + k]);
+                    a_w3[j4 + k] = fmaf(sg, h2, a_w3[j4 + k]);
+                    v[j4 + k] = w_[k] * sg * fmaf(-h2, h2, 1.0f);
+                    a_b2[j4 + k] += v[j4 + k];
+                }
+                *reinterpret_cast<float4 *>(&wr.Q[lane * WarpRows<H>::LD + j4]) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+            }
+            __syncwarp();
+            // ---- dW2 += q2 (x) h1 over the warp's 32 points ----
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) {
+                const float2 q = *reinterpret_cast<const float2 *>(&wr.Q[t * WarpRows<H>::LD + 2 * jt]);
+                const float4 hh = *reinterpret_cast<const float4 *>(&wr.A[t * WarpRows<H>::LD + 4 * it]);
+                const float2 h01 = make_float2(hh.x, hh.y), h23 = make_float2(hh.z, hh.w);
+                acc[0] = fma2(bc(q.x), h01, acc[0]);
+                acc[1] = fma2(bc(q.x), h23, acc[1]);
+                acc[2] = fma2(bc(q.y), h01, acc[2]);
+                acc[3] = fma2(bc(q.y), h23, acc[3]);
+            }
+            __syncwarp();
+            // ---- q1 = (W2^T q2) * (1 - h1^2); first-layer gradients; dx ----
+            float dx0 = 0.0f, dx1 = 0.0f;
+#pragma unroll
+            for (int ii = 0; ii < H; ++ii) {
+                float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                for (int j4 = 0; j4 < H; j4 += 4) {
+                    const float4 w = ldw4(zb + O::W2 + ii * H + j4);
+                    s0 = fmaf(w.x, v[j4 + 0], s0);
+                    s1 = fmaf(w.y, v[j4 + 1], s1);
+                    s0 = fmaf(w.z, v[j4 + 2], s0);
+                    s1 = fmaf(w.w, v[j4 + 3], s1);
+                }
+                const float q1 = (s0 + s1) * fmaf(-h1[ii], h1[ii], 1.0f);
+                a_b1[ii] += q1;
+                a_w1[ii] = fmaf(q1, x, a_w1[ii]);
+                const float wi = c_theta[zb + O::W1 + ii];
+                if (ii & 1) dx1 = fmaf(wi, q1, dx1);
+                else dx0 = fmaf(wi, q1, dx0);
+            }
+            const float dx = (dx0 + dx1) * isc;
+            // (J^T g)_i: w1 couples i+1 -> i, w3 couples i-1 -> i
+            const float kn = dx + D0 * fmaf(w2, g, fmaf(w1, np.y, w3 * nm.y));
+            switch (st) {
+            case 0: kl[0] = kn; break;
+            case 1: kl[1] = kn; break;
+            case 2: kl[2] = kn; break;
+            case 3: kl[3] = kn; break;
+            case 4: kl[4] = kn; break;
+            default: kl[5] = kn; break;
+            }
+            a_s1 = fmaf(sg * D0, nm.x, a_s1);
+            a_s2 = fmaf(sg * D0, x, a_s2);
+            a_s3 = fmaf(sg * D0, np.x, a_s3);
+            a_D0 = fmaf(sg, fmaf(w1, nm.x, fmaf(w2, x, w3 * np.x)), a_D0);
+        }
+        float a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a = fmaf((float)Tsit5::b(j), kl[j], a);
+        lam = fmaf(dt, a, lam);
+        if (s % p.save_every == 0) jump(s / p.save_every);
+    }
+    if (p.grad_u0 && live) p.grad_u0[(size_t)i * N + n] = lam;
+
+    // ---- reduction: lanes -> warp (fixed shuffle tree), warps -> CTA (fixed order) ----
+    __syncthreads();
+    float *gw = s_dyn + (size_t)warp * (P + 1);   // the staging area is free now: [nwarp][P+1]
+    auto wsum = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float r0 = wsum(a_w1[j]), r1 = wsum(a_b1[j]), r2 = wsum(a_b2[j]), r3 = wsum(a_w3[j]);
+        if (lane == 0) { gw[O::W1 + j] = r0; gw[O::B1 + j] = r1; gw[O::B2 + j] = r2; gw[O::W3 + j] = r3; }
+    }
+    {
+        const float r0 = wsum(a_b3), r1 = wsum(a_s1), r2 = wsum(a_s2), r3 = wsum(a_s3), r4 = wsum(a_D0), r5 = wsum(loss * lv);
+        if (lane == 0) {
+            gw[O::B3] = r0; gw[O::SX] = r1; gw[O::SX + 1] = r2; gw[O::SX + 2] = r3; gw[O::SX + 3] = 0.0f; gw[O::SX + 4] = r4;
+            gw[P] = r5;
+        }
+    }
+    gw[O::W2 + (4 * it + 0) * H + 2 * jt] = acc[0].x;
+    gw[O::W2 + (4 * it + 1) * H + 2 * jt] = acc[0].y;
+    gw[O::W2 + (4 * it + 2) * H + 2 * jt] = acc[1].x;
+    gw[O::W2 + (4 * it + 3) * H + 2 * jt] = acc[1].y;
+    gw[O::W2 + (4 * it + 0) * H + 2 * jt + 1] = acc[2].x;
+    gw[O::W2 + (4 * it + 1) * H + 2 * jt + 1] = acc[2].y;
+    gw[O::W2 + (4 * it + 2) * H + 2 * jt + 1] = acc[3].x;
+    gw[O::W2 + (4 * it + 3) * H + 2 * jt + 1] = acc[3].y;
+    __syncthreads();
+    float *dst = p.partial + (size_t)blockIdx.x * (P + 1);
+    for (int q = threadIdx.x; q < P + 1; q += blockDim.x) {
+        float tot = 0.0f;
+        for (int w = 0; w < nwarp; ++w) tot += s_dyn[(size_t)w * (P + 1) + q];
+        dst[q] = tot;
+    }
+}
+
+}  // namespace fkpp
+}  // namespace b200ude

@@ -1,0 +1,59 @@
+// k_fkpp.cu -- tuned Fisher-KPP UPDE kernels, reaction chain 1 -> 16 -> 16 -> 1 tanh (BASELINE config 4;
+// FisherKPP/Fisher-KPP-CNN.jl:111-126 with the chain widths of the config).
+#include "fkpp_tuned.cuh"
+
+namespace b200ude {
+
+static void geom16(int Nx, fkpp::Geom *g, int *threads)
+{
+    g->Nx = Nx;
+    g->tpc = Nx >= 128 ? 1 : 128 / Nx;
+    *threads = ((g->tpc * Nx + 31) / 32) * 32;
+}
+
+int adj_rows_fkpp16(int N, int Nx)
+{
+    fkpp::Geom g; int th;
+    geom16(Nx, &g, &th);
+    return (N + g.tpc - 1) / g.tpc;   // one partial row per CTA
+}
+
+template <int TM>
+static cudaError_t fwd(const FwdParams &p, int Nx, cudaStream_t st)
+{
+    fkpp::Geom g; int th;
+    geom16(Nx, &g, &th);
+    const int grid = (p.N + g.tpc - 1) / g.tpc;
+    fkpp::forward_kernel<16, TM><<<grid, th, sizeof(float) * 2 * g.tpc * g.Nx, st>>>(p, g);
+    return cudaGetLastError();
+}
+
+template <int TM>
+static cudaError_t adj(const AdjParams &p, int Nx, cudaStream_t st, int *rows_out)
+{
+    fkpp::Geom g; int th;
+    geom16(Nx, &g, &th);
+    const int grid = (p.N + g.tpc - 1) / g.tpc, slots = g.tpc * g.Nx, nwarp = th / 32;
+    size_t smem = sizeof(float) * 4 * (size_t)(((slots + 1) / 2) * 2) + (size_t)nwarp * sizeof(fkpp::WarpRows<16>);
+    const size_t red = sizeof(float) * (size_t)nwarp * (fkpp::Off<16>::P + 1);
+    if (red > smem) smem = red;
+    *rows_out = grid;
+    fkpp::adjoint_kernel<16, TM><<<grid, th, smem, st>>>(p, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_fkpp16(const Variant &v, const ConstTables &t, const FwdParams &p, int Nx, cudaStream_t st)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    return v.approx_tanh ? fwd<1>(p, Nx, st) : fwd<0>(p, Nx, st);
+}
+
+cudaError_t launch_adj_fkpp16(const Variant &v, const ConstTables &t, const AdjParams &p, int Nx, cudaStream_t st, int *rows_out)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    return v.approx_tanh ? adj<1>(p, Nx, st, rows_out) : adj<0>(p, Nx, st, rows_out);
+}
+
+}  // namespace b200ude
