@@ -426,7 +426,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->var.adj_smem = env_int("B200UDE_ADJ_SMEM", 0);
     // default: tcgen05 (3xTF32) kernels; B200UDE_FWD_TC=0 / B200UDE_ADJ_TC=0 select the FFMA2-packed CUDA-core kernels
     h->var.fwd_tc = env_int("B200UDE_FWD_TC", 1);
-    h->var.adj_tc = env_int("B200UDE_ADJ_TC", 1);
+    h->var.adj_tc = env_int("B200UDE_ADJ_TC", 2);   // 2: gradient GEMM on mma.sync (3xTF32), 1: on the FMA pipe (FFMA2)
 
     const size_t N = h->cap, D = (size_t)h->D;
     h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : kid == K_SEIR64 ? adj_rows_seir((int)N) : kid == K_FKPP16 ? adj_rows_fkpp16((int)N, d->state_dim) : adj_grid_lv5((int)N));

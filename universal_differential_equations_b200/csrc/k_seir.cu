@@ -32,10 +32,10 @@ static cudaError_t launch_fwd(const FwdParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int TM>
+template <int TM, int GEMM>
 static cudaError_t launch_adj(const AdjParams &p, cudaStream_t st)
 {
-    auto kern = seir::adjoint_kernel<TM>;
+    auto kern = seir::adjoint_kernel<TM, GEMM>;
     constexpr size_t smem = 4 * seir::HS * seir::HS * sizeof(float) + seir::GROUPS * sizeof(seir::GroupStage);
     static bool done = false;
     cudaError_t e = set_smem(kern, smem, &done);
@@ -56,7 +56,8 @@ cudaError_t launch_adj_seir(const Variant &v, const ConstTables &t, const AdjPar
     cudaError_t e = upload_tables(t, st);
     if (e != cudaSuccess) return e;
     *rows_out = adj_rows_seir(p.N);
-    return v.approx_tanh ? launch_adj<1>(p, st) : launch_adj<0>(p, st);
+    if (v.adj_tc == 1) return v.approx_tanh ? launch_adj<1, 0>(p, st) : launch_adj<0, 0>(p, st);   // B200UDE_ADJ_TC=1: FFMA2 gradient GEMM
+    return v.approx_tanh ? launch_adj<1, 1>(p, st) : launch_adj<0, 1>(p, st);
 }
 
 }  // namespace b200ude

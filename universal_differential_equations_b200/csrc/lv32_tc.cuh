@@ -87,7 +87,7 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 constexpr uint32_t LBO = 128, SBO = 1024;   // weights tile [n/8][k/4][n%8][k%4]: the 8 K-chunks of a row group are adjacent
-constexpr int TMEM_COLS = 128;              // D [0,32) | A_hi [32,64) | A_lo [64,96) | spare
+constexpr int TMEM_COLS = 128;              // D [0,32) | A_hi [32,64) | A_lo [64,96) | [96,128) running dW2 sums of the adjoint (tmem_flush32)
 constexpr uint32_t IDESC = make_idesc(128, 32);
 
 // per-CTA tensor-core context
@@ -317,7 +317,46 @@ struct __align__(16) WarpStageT {
     float U[32 * 2];      // chain input                            [lane][m]
 };
 
-template <int TM, int BLOCK, int MINB>
+// warp-level m16n8k8 TF32 MMA (legacy tensor-core path), D += A B
+__device__ __forceinline__ void mma_m16n8k8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+    const float h = tf32_rna(x);
+    hi = __float_as_uint(h);
+    lo = __float_as_uint(x - h);
+}
+
+// Running sums kept in spare tensor-memory columns (one 32-column row per thread): sum += m with ordinary round-to-nearest
+// adds, m = 0.  The tensor core adds into its accumulator with truncation, so a long mma accumulation chain drifts
+// (measured: 2.4e-5 relative on dW2 after the 2160 MMAs of a whole backward solve); short chains flushed through this
+// keep the error at the FFMA level without spending 32 more registers or any shared / global memory.
+__device__ __forceinline__ void tmem_flush32(uint32_t taddr, float (&m)[32], bool first)
+{
+    float r[32];
+    if (!first) {
+        tmem_ld32(taddr, r);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) r[q] += m[q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) r[q] = m[q];
+    }
+    tmem_st32(taddr, r);
+    tmem_st_wait();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) m[q] = 0.0f;
+}
+
+// GEMM = 0: the per-warp gradient GEMM dW2 += q2 (x) h1 on the FMA pipe (FFMA2, 8 x 4 register tile per lane);
+// GEMM = 1: the same product as 3xTF32 warp-level mma.sync.m16n8k8 (M = j, N = i, K = the warp's 32 trajectories):
+//           fragments are read straight from the staged rows; the contraction index inside a k-step is permuted
+//           (k = tig -> t = 2 tig, k = tig + 4 -> t = 2 tig + 1) so that every fragment load is bank-conflict free.
+template <int TM, int BLOCK, int MINB, int GEMM>
 __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
 {
     static_assert(BLOCK == 128, "one TMEM lane per thread: 128 trajectories per CTA");
@@ -347,6 +386,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
     float2 acc[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc[q] = bc(0.0f);
+    float macc[32];   // GEMM = 1: C fragments of the 2 x 4 (j x i) tiles, tile (mt, nt) at 16 mt + 4 nt
+#pragma unroll
+    for (int q = 0; q < 32; ++q) macc[q] = 0.0f;
+    const int fg = lane >> 2, tig = lane & 3;   // mma fragment coordinates (groupID, threadID_in_group)
     float g_w30 = 0.f, g_w31 = 0.f, g_b30 = 0.f, g_b31 = 0.f, g_b2 = 0.f, g_b1 = 0.f, g_w10 = 0.f, g_w11 = 0.f;
 
     float lam[2] = {0.0f, 0.0f};
@@ -427,7 +470,37 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
             // ---- W2^T q2 on the tensor core; the gradient GEMM of this warp runs while the MMAs are in flight ----
             tc_issue(c, v, sWb_hi, sWb_lo);
             __syncwarp();
-            {
+            if constexpr (GEMM == 1) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const float *q0 = st->B1 + (8 * ks + 2 * tig) * SLD + fg, *q1 = q0 + SLD;
+                    const float *h0 = st->B2 + (8 * ks + 2 * tig) * SLD + fg, *h1r = h0 + SLD;
+                    uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        split_tf32(q0[16 * mt], ah[mt][0], al[mt][0]);
+                        split_tf32(q0[16 * mt + 8], ah[mt][1], al[mt][1]);
+                        split_tf32(q1[16 * mt], ah[mt][2], al[mt][2]);
+                        split_tf32(q1[16 * mt + 8], ah[mt][3], al[mt][3]);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        split_tf32(h0[8 * nt], bh[nt][0], bl[nt][0]);
+                        split_tf32(h1r[8 * nt], bh[nt][1], bl[nt][1]);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            float (&cf)[4] = *reinterpret_cast<float (*)[4]>(&macc[16 * mt + 4 * nt]);
+                            mma_m16n8k8(cf, al[mt], bh[nt]);
+                            mma_m16n8k8(cf, ah[mt], bl[nt]);
+                            mma_m16n8k8(cf, ah[mt], bh[nt]);
+                        }
+                }
+#pragma unroll 8
+                for (int t = 0; t < 32; ++t) g_b2 += st->B1[t * SLD + lane];
+            } else {
                 float4 G0[2], G1[2], Hh[2];
                 float qc[2];
                 auto load_row = [&](int t, int b) {
@@ -502,6 +575,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
             lam[cc] = fmaf(dt, a, lam[cc]);
         }
         if (s % p.save_every == 0) loss_jump<2>(p, s / p.save_every, n, N, lam, loss);
+        if constexpr (GEMM == 1) tmem_flush32(c.tmem + 96 + c.lane_base, macc, s == p.n_steps - 1);   // per step: 72-MMA chains
     }
     if (p.grad_u0 && live) {
         p.grad_u0[n] = lam[0];
@@ -512,12 +586,26 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p)
     for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
     // this warp's partial gradient
     float *dst = p.partial + ((size_t)blockIdx.x * 4 + warp) * (P + 1);
+    if constexpr (GEMM == 1) {
+        tmem_ld32(c.tmem + 96 + c.lane_base, macc);
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-        dst[OFF_W2 + (it * 4 + 0) * H + (jt * 8 + jj)] = acc[2 * jj].x;
-        dst[OFF_W2 + (it * 4 + 1) * H + (jt * 8 + jj)] = acc[2 * jj].y;
-        dst[OFF_W2 + (it * 4 + 2) * H + (jt * 8 + jj)] = acc[2 * jj + 1].x;
-        dst[OFF_W2 + (it * 4 + 3) * H + (jt * 8 + jj)] = acc[2 * jj + 1].y;
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int j = 16 * mt + fg, i = 8 * nt + 2 * tig;
+                dst[OFF_W2 + i * H + j] = macc[16 * mt + 4 * nt + 0];
+                dst[OFF_W2 + (i + 1) * H + j] = macc[16 * mt + 4 * nt + 1];
+                dst[OFF_W2 + i * H + j + 8] = macc[16 * mt + 4 * nt + 2];
+                dst[OFF_W2 + (i + 1) * H + j + 8] = macc[16 * mt + 4 * nt + 3];
+            }
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            dst[OFF_W2 + (it * 4 + 0) * H + (jt * 8 + jj)] = acc[2 * jj].x;
+            dst[OFF_W2 + (it * 4 + 1) * H + (jt * 8 + jj)] = acc[2 * jj].y;
+            dst[OFF_W2 + (it * 4 + 2) * H + (jt * 8 + jj)] = acc[2 * jj + 1].x;
+            dst[OFF_W2 + (it * 4 + 3) * H + (jt * 8 + jj)] = acc[2 * jj + 1].y;
+        }
     }
     dst[OFF_W3 + lane * 2 + 0] = g_w30;
     dst[OFF_W3 + lane * 2 + 1] = g_w31;

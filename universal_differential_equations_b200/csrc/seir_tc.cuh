@@ -291,7 +291,10 @@ struct __align__(16) GroupStage {
     float RED[GROUP];          // loss reduction scratch
 };
 
-template <int TM>
+// GEMM = 1: the group's gradient GEMM dW2 += q2 (x) h1 (64 x 64 outputs, K = 128 trajectories) as 3xTF32 warp-level
+// mma.sync.m16n8k8 -- warp w of the group owns the 16 rows j = 16 w .. 16 w + 15 and all 8 column tiles; fragments are read
+// from the staged rows with the bank-conflict-free k permutation of lv32_tc.cuh.  GEMM = 0: FFMA2 8 x 4 register tiles.
+template <int TM, int GEMM>
 __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
 {
     extern __shared__ __align__(1024) float s_dyn[];
@@ -321,6 +324,11 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
     float2 acc[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc[q] = bc(0.0f);
+    float macc[32];   // GEMM = 1: C fragments of this warp's 8 column tiles, tile nt at 4 nt
+#pragma unroll
+    for (int q = 0; q < 32; ++q) macc[q] = 0.0f;
+    const uint32_t sum_taddr = tmem_base + GROUPS * TMEM_PER_GROUP + 32 * group + c.lane_base;   // spare columns [384, 448)
+    const int lane = threadIdx.x & 31, fg = lane >> 2, tig = lane & 3, wg = tg >> 5;
     // thin layers: thread tg owns column j = tg % 64 over the staged rows [64 * (tg / 64), +64) of its group:
     // a_w3 (dW3[j]), a_b2 (db2[j]), a_b3 (db3), a_w1[m] (dW1[j][m]), a_b1 (db1[j]); the two halves are added at the end
     float a_w3 = 0.f, a_b2 = 0.f, a_b3 = 0.f, a_w10 = 0.f, a_w11 = 0.f, a_w12 = 0.f, a_b1 = 0.f;
@@ -406,7 +414,37 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
             for (int j4 = 0; j4 < HS; j4 += 4) *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // q2 row
             // ---- W2^T q2 on the tensor core; gradient GEMM of the group while the MMAs are in flight ----
             tc_issue64(c, v, sWb_hi, sWb_lo, issuer);
-            {
+            if constexpr (GEMM == 1) {
+#pragma unroll 1
+                for (int ks = 0; ks < GROUP / 8; ++ks) {
+                    const float *q0 = st->B1 + (8 * ks + 2 * tig) * SLD64 + 16 * wg + fg, *q1 = q0 + SLD64;
+                    const float *h0 = st->B2 + (8 * ks + 2 * tig) * SLD64 + fg, *h1r = h0 + SLD64;
+                    uint32_t ah[4], al[4];
+                    lv32::tc::split_tf32(q0[0], ah[0], al[0]);
+                    lv32::tc::split_tf32(q0[8], ah[1], al[1]);
+                    lv32::tc::split_tf32(q1[0], ah[2], al[2]);
+                    lv32::tc::split_tf32(q1[8], ah[3], al[3]);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            lv32::tc::split_tf32(h0[8 * (4 * half + k)], bh[k][0], bl[k][0]);
+                            lv32::tc::split_tf32(h1r[8 * (4 * half + k)], bh[k][1], bl[k][1]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float (&cf)[4] = *reinterpret_cast<float (*)[4]>(&macc[4 * (4 * half + k)]);
+                            lv32::tc::mma_m16n8k8(cf, al, bh[k]);
+                            lv32::tc::mma_m16n8k8(cf, ah, bl[k]);
+                            lv32::tc::mma_m16n8k8(cf, ah, bh[k]);
+                        }
+                    }
+                }
+                lv32::tc::tmem_flush32(sum_taddr, macc, (s == p.n_steps - 1) && (stage == 0));   // per evaluation: 48-MMA chains
+#pragma unroll 8
+                for (int t = tlo; t < tlo + 64; ++t) a_b2 += st->B1[t * SLD64 + jc];   // db2[j] += sum_t q2[t][j]
+            } else {
                 float4 G0[2], G1[2], Hh[2];
                 auto load_row = [&](int t, int b) {
                     const float *r1 = st->B1 + t * SLD64, *r2 = st->B2 + t * SLD64;
@@ -511,12 +549,24 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
     }
     group_sync(c.bar_id);
     float *dst = p.partial + ((size_t)blockIdx.x * GROUPS + group) * (PS + 1);
+    if constexpr (GEMM == 1) {
+        lv32::tc::tmem_ld32(sum_taddr, macc);
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-        dst[OFF_W2 + (it * 4 + 0) * HS + (jt * 8 + jj)] = acc[2 * jj].x;
-        dst[OFF_W2 + (it * 4 + 1) * HS + (jt * 8 + jj)] = acc[2 * jj].y;
-        dst[OFF_W2 + (it * 4 + 2) * HS + (jt * 8 + jj)] = acc[2 * jj + 1].x;
-        dst[OFF_W2 + (it * 4 + 3) * HS + (jt * 8 + jj)] = acc[2 * jj + 1].y;
+        for (int nt = 0; nt < 8; ++nt) {
+            const int j = 16 * wg + fg, i = 8 * nt + 2 * tig;
+            dst[OFF_W2 + i * HS + j] = macc[4 * nt + 0];
+            dst[OFF_W2 + (i + 1) * HS + j] = macc[4 * nt + 1];
+            dst[OFF_W2 + i * HS + j + 8] = macc[4 * nt + 2];
+            dst[OFF_W2 + (i + 1) * HS + j + 8] = macc[4 * nt + 3];
+        }
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            dst[OFF_W2 + (it * 4 + 0) * HS + (jt * 8 + jj)] = acc[2 * jj].x;
+            dst[OFF_W2 + (it * 4 + 1) * HS + (jt * 8 + jj)] = acc[2 * jj].y;
+            dst[OFF_W2 + (it * 4 + 2) * HS + (jt * 8 + jj)] = acc[2 * jj + 1].x;
+            dst[OFF_W2 + (it * 4 + 3) * HS + (jt * 8 + jj)] = acc[2 * jj + 1].y;
+        }
     }
     if (tg < 64) {
         const float *x = st->B1 + jc * 8;
