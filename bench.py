@@ -165,6 +165,21 @@ def main():
     buf = torch.zeros(P + 1, device=dev)          # [grad_theta ; loss] -- the one all-reduced message
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     solver.set_params(th_d)
+    # multi-GPU: the sum over ranks of [grad_theta; loss] runs inside the final reduction kernel over NVLink peer memory
+    # (b200ude_adjoint_l2_allreduce); NCCL all-reduce only if the peer mapping cannot be set up on every rank
+    peer = None
+    if world > 1 and os.environ.get("B200UDE_PEER_ALLREDUCE", "1") != "0":
+        ok = torch.ones(1, device=dev)
+        try:
+            peer = ude.PeerAllReduce(solver)
+        except Exception as e:   # noqa: BLE001
+            print(f"[bench] rank {rank}: peer-memory all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            if peer is not None:
+                solver.peer_detach()
+            peer = None
 
     def step(ev=None, collective=True):
         solver.set_params(th_d)
@@ -173,11 +188,16 @@ def main():
         solver.forward(u0_d, out=out_d)
         if ev:
             ev[1].record()
-        solver.adjoint_l2(y_d, want_grad_u0=False, grad_theta=buf[:P], loss=buf[P:])
-        if ev:
-            ev[2].record()
-        if collective:
-            ude.allreduce_loss_grad(buf)
+        if peer is not None and collective:
+            solver.adjoint_l2_allreduce(y_d, want_grad_u0=False, grad_theta=buf[:P], loss=buf[P:])
+            if ev:
+                ev[2].record()
+        else:
+            solver.adjoint_l2(y_d, want_grad_u0=False, grad_theta=buf[:P], loss=buf[P:])
+            if ev:
+                ev[2].record()
+            if collective:
+                ude.allreduce_loss_grad(buf)
         if ev:
             ev[3].record()
 
@@ -301,10 +321,14 @@ def main():
         "config": {"workload": "LV UDE ensemble, 2->32->32->2 tanh, Tsit5 dt=0.1 x30 saveat 0.1, fwd + InterpolatingAdjoint + L2 loss",
                    "trajectories_per_gpu": n, "global_trajectories": world * n, "parallelism": f"ensemble-sharded x{world}",
                    "l2": "flushed between timed iterations (256 MiB memset, untimed)",
-                   "timing": "CUDA events per step on the launch stream, summed over steps, max over ranks"},
+                   "timing": "CUDA events per step on the launch stream, summed over steps, max over ranks",
+                   "allreduce": ("none (1 GPU)" if world == 1 else
+                                 "fused into the final reduction kernel over NVLink peer memory (CUDA IPC, b200ude_adjoint_l2_allreduce)" if peer is not None
+                                 else "NCCL all-reduce of [grad_theta; loss] (4.9 KB)")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "b200ude_loss_gradient_host: pinned host theta/u0/data -> H2D -> kernels -> D2H grad+loss, wall clock"},
-        "gpu_launches": 3 * a.steps, "kernels_per_step": ["lv32::tc::forward_kernel", "lv32::tc::adjoint_kernel", "ude_reduce_kernel"],
+        "gpu_launches": 3 * a.steps,
+        "kernels_per_step": ["lv32::tc::forward_kernel", "lv32::tc::adjoint_kernel", "ude_reduce_exchange_kernel" if peer is not None else "ude_reduce_kernel"],
         "clocks": clocks, "roofline": roofline, "roofline_fp32": roofline_fp32, "roofline_xu": roofline_xu, "cpu_baseline": cpu,
         "kernel_ms": {"forward": fwd_ms, "adjoint_plus_reduce": adj_ms, "step": float(np.mean(t_step))},
     }

@@ -201,6 +201,20 @@ int32_t b200ude_adam_step(b200ude_handle *h, const b200ude_adam *opt, const void
 int32_t b200ude_train_adam(b200ude_handle *h, const b200ude_adam *opt, const void *u0, const void *data, size_t N,
                            int32_t iters, void *loss_history, void *stream);
 
+/* MULTI-GPU (one process per GPU; the ensemble shards, theta is replicated -- SURVEY.md section 8e).  The only exchange of
+ * the path, the sum over ranks of [grad_theta (P); loss], can run inside the final reduction kernel over NVLink peer memory:
+ * every rank exports an exchange buffer (CUDA IPC), the host program gathers the `world` handles in rank order by whatever
+ * means it has (MPI, torch.distributed, a file), attaches, and synchronises all ranks once (a host barrier) before the first
+ * call.  b200ude_adjoint_l2_allreduce is then b200ude_adjoint_l2 whose loss and grad_theta are the sums over ALL ranks
+ * (bitwise identical on every rank); it is a collective: every rank must call it the same number of times.  grad_u0 stays
+ * local.  Fixed-step handles only.  A peer that never arrives turns the results into NaN after ~2 s instead of hanging. */
+#define B200UDE_PEER_HANDLE_BYTES 64
+int32_t b200ude_peer_export(b200ude_handle *h, void *handle_out /* B200UDE_PEER_HANDLE_BYTES */);
+int32_t b200ude_peer_attach(b200ude_handle *h, int32_t rank, int32_t world, const void *handles /* world x 64 bytes, rank order */);
+int32_t b200ude_peer_detach(b200ude_handle *h);
+int32_t b200ude_adjoint_l2_allreduce(b200ude_handle *h, const void *data, void *loss, void *grad_theta, void *grad_u0,
+                                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -583,3 +583,26 @@ def test_on_device_adam_matches_host_driven_loop(monkeypatch):
     assert r.iterations == iters and np.array_equal(np.array(rec, np.float32), hist["1"][0])
     assert np.array_equal(r.final.cpu().numpy(), hist["1"][1])
     solver.close()
+
+
+def test_peer_allreduce_single_rank_equals_plain_reduce():
+    """The fused reduce + all-reduce kernel (NVLink peer-memory path, b200ude_adjoint_l2_allreduce) with world = 1 is the
+    plain fixed-order reduce bit for bit, over repeated calls (epoch parity, monotonic flags).  The multi-rank exchange
+    itself is exercised by tools/peer_allreduce_check.py under torchrun (needs >= 2 GPUs)."""
+    ude = _ude()
+    N = 3000
+    theta = glorot_theta((2, 32, 32, 2), seed=1)
+    u0, y = synthetic_ensemble(N)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    solver.set_params(torch.from_numpy(theta).cuda())
+    u0d, yd = torch.from_numpy(u0).cuda(), torch.from_numpy(y).cuda()
+    solver.forward(u0d)
+    L0, g0, _ = solver.adjoint_l2(yd)
+    L0, g0 = L0.clone(), g0.clone()
+    pa = ude.PeerAllReduce(solver)
+    for _ in range(5):
+        L1, g1, gu = solver.adjoint_l2_allreduce(yd, want_grad_u0=True)
+        torch.cuda.synchronize()
+        assert torch.equal(L0, L1) and torch.equal(g0, g1)
+    pa.close()
+    solver.close()

@@ -11,4 +11,4 @@ from .sciml import (  # noqa: F401
     InterpolatingAdjoint, LotkaVolterraUDE, NeuralODE, ODEProblem, SEIRExposureUDE, ReverseDiffVJP, Tsit5, UDESolver, Vern7,
     concrete_solve, identity, initial_params, rbf, remake, sciml_train, sciml_train_l2, solve, tanh,
 )
-from .dist import shard_range, allreduce_loss_grad  # noqa: F401
+from .dist import PeerAllReduce, shard_range, allreduce_loss_grad  # noqa: F401

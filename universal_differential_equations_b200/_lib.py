@@ -29,7 +29,9 @@ EXPORTS = [
     "b200ude_num_params", "b200ude_num_save", "b200ude_device_bytes", "b200ude_set_params",
     "b200ude_forward", "b200ude_adjoint", "b200ude_adjoint_l2", "b200ude_solve_host",
     "b200ude_loss_gradient_host", "b200ude_get_params", "b200ude_adam_reset", "b200ude_adam_step", "b200ude_train_adam",
+    "b200ude_peer_export", "b200ude_peer_attach", "b200ude_peer_detach", "b200ude_adjoint_l2_allreduce",
 ]
+PEER_HANDLE_BYTES = 64
 
 
 class Desc(C.Structure):
@@ -115,6 +117,14 @@ def lib():
     L.b200ude_adam_step.argtypes = [vp, C.POINTER(Adam), vp, vp]
     L.b200ude_train_adam.restype = i32
     L.b200ude_train_adam.argtypes = [vp, C.POINTER(Adam), vp, vp, sz, i32, vp, vp]
+    L.b200ude_peer_export.restype = i32
+    L.b200ude_peer_export.argtypes = [vp, vp]
+    L.b200ude_peer_attach.restype = i32
+    L.b200ude_peer_attach.argtypes = [vp, i32, i32, vp]
+    L.b200ude_peer_detach.restype = i32
+    L.b200ude_peer_detach.argtypes = [vp]
+    L.b200ude_adjoint_l2_allreduce.restype = i32
+    L.b200ude_adjoint_l2_allreduce.argtypes = [vp, vp, vp, vp, vp, vp]
     if L.b200ude_version() != ABI_VERSION:
         raise RuntimeError("libb200ude.so ABI version mismatch")
     _lib = L

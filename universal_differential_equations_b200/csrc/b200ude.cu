@@ -81,6 +81,11 @@ struct b200ude_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-buffer path: the data upload overlaps the forward kernel
     cudaEvent_t data_ready = nullptr;
+    // fused reduce + all-reduce over NVLink peer memory (b200ude_peer_*)
+    void *d_peer_buf = nullptr;     // this rank's exchange buffer (cudaMalloc, exported with CUDA IPC)
+    PeerLinks peer;                 // every rank's buffer as mapped here
+    bool peer_attached = false;
+    unsigned peer_epoch = 0;
     // on-device optimiser (b200ude_adam_*, b200ude_train_adam)
     float *d_u0_keep = nullptr, *d_aux_out = nullptr;   // Vern7: u0 of the last forward, saved states of the Tsit5 re-solve
     bool vern7_pending = false;
@@ -223,8 +228,10 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
 }
 
 int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, float *grad_theta,
-                   float *grad_u0, cudaStream_t st)
+                   float *grad_u0, cudaStream_t st, bool peer = false)
 {
+    if (peer && !h->peer_attached) return fail(h, B200UDE_ESTATE, "adjoint_l2_allreduce: b200ude_peer_attach has not been called");
+    if (peer && h->adaptive) return fail(h, B200UDE_EUNSUPPORTED, "adjoint_l2_allreduce: not available with adaptive stepping (all-reduce the result of b200ude_adjoint_l2 instead)");
     if (h->desc.solver == B200UDE_VERN7 && h->vern7_pending) {
         if (!h->d_aux_out && dalloc(h, &h->d_aux_out, (size_t)h->n_save * (size_t)h->D * h->cap) != cudaSuccess)
             return fail(h, B200UDE_ENOMEM, "adjoint: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -265,7 +272,12 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     default: return fail(h, B200UDE_EUNSUPPORTED, "adjoint: no kernel");
     }
     CUDA_TRY(h, e);
-    CUDA_TRY(h, launch_reduce(h->d_partial, grid, h->P + 1, grad_theta, loss, st));
+    if (peer) {
+        h->peer_epoch += 1;
+        CUDA_TRY(h, launch_reduce_exchange(h->d_partial, grid, h->P + 1, h->peer, h->peer_epoch, grad_theta, loss, st));
+    } else {
+        CUDA_TRY(h, launch_reduce(h->d_partial, grid, h->P + 1, grad_theta, loss, st));
+    }
     return B200UDE_OK;
 }
 
@@ -479,6 +491,8 @@ void b200ude_destroy(b200ude_handle *h)
     cudaFree(h->d_theta); cudaFree(h->d_ustep); cudaFree(h->d_dense); cudaFree(h->d_partial);
     cudaFree(h->d_u0); cudaFree(h->d_out); cudaFree(h->d_data); cudaFree(h->d_gu0); cudaFree(h->d_grad);
     cudaFree(h->d_loss); cudaFree(h->d_status);
+    b200ude_peer_detach(h);
+    cudaFree(h->d_peer_buf);
     cudaFree(h->d_u0_keep); cudaFree(h->d_aux_out);
     cudaFree(h->d_adam_m); cudaFree(h->d_adam_v); cudaFree(h->d_adam_t); cudaFree(h->d_train_out);
     cudaFree(h->d_tgrid); cudaFree(h->d_nacc); cudaFree(h->d_cot); cudaFree(h->d_block_loss);
@@ -668,6 +682,69 @@ int32_t b200ude_train_adam(b200ude_handle *h, const b200ude_adam *opt, const voi
     h->adam_t = t_base + iters;
     if (!stream) CUDA_TRY(h, cudaStreamSynchronize(st));
     return B200UDE_OK;
+}
+
+// ---- multi-GPU: fused final reduction + all-reduce over NVLink peer memory ------------------------------------
+static size_t peer_buf_bytes(const b200ude_handle *h)
+{
+    const size_t P1pad = (size_t)((h->P + 1 + 31) / 32) * 32;
+    return (size_t)PEER_HEADER_BYTES + sizeof(float) * 2 * 16 * P1pad;
+}
+
+int32_t b200ude_peer_export(b200ude_handle *h, void *handle_out)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (!handle_out) return fail(h, B200UDE_EINVAL, "peer_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200UDE_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+    if (!h->d_peer_buf) {
+        CUDA_TRY(h, cudaMalloc(&h->d_peer_buf, peer_buf_bytes(h)));
+        h->dev_bytes += peer_buf_bytes(h);
+        CUDA_TRY(h, cudaMemset(h->d_peer_buf, 0, peer_buf_bytes(h)));
+        CUDA_TRY(h, cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t ipc;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&ipc, h->d_peer_buf));
+    memcpy(handle_out, &ipc, sizeof(ipc));
+    return B200UDE_OK;
+}
+
+int32_t b200ude_peer_attach(b200ude_handle *h, int32_t rank, int32_t world, const void *handles)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (!handles || world < 1 || world > 16 || rank < 0 || rank >= world) return fail(h, B200UDE_EINVAL, "peer_attach: need 1 <= world <= 16, 0 <= rank < world");
+    if (!h->d_peer_buf) return fail(h, B200UDE_ESTATE, "peer_attach: call b200ude_peer_export first");
+    if (h->peer_attached) return fail(h, B200UDE_ESTATE, "peer_attach: already attached");
+    for (int r = 0; r < 16; ++r) h->peer.base[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->peer.base[r] = h->d_peer_buf; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char *)handles + (size_t)r * sizeof(ipc), sizeof(ipc));
+        cudaError_t e = cudaIpcOpenMemHandle(&h->peer.base[r], ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q) if (q != rank && h->peer.base[q]) cudaIpcCloseMemHandle(h->peer.base[q]);
+            return fail(h, (int32_t)e, "peer_attach: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+    }
+    h->peer.rank = rank; h->peer.world = world; h->peer.P1pad = ((h->P + 1 + 31) / 32) * 32;
+    h->peer_attached = true;
+    h->peer_epoch = 0;
+    return B200UDE_OK;
+}
+
+int32_t b200ude_peer_detach(b200ude_handle *h)
+{
+    if (!h) return B200UDE_EINVAL;
+    if (h->peer_attached)
+        for (int r = 0; r < h->peer.world; ++r)
+            if (r != h->peer.rank && h->peer.base[r]) cudaIpcCloseMemHandle(h->peer.base[r]);
+    h->peer_attached = false;
+    return B200UDE_OK;
+}
+
+int32_t b200ude_adjoint_l2_allreduce(b200ude_handle *h, const void *data, void *loss, void *grad_theta, void *grad_u0, void *stream)
+{
+    if (!h) return B200UDE_EINVAL;
+    return do_adjoint(h, true, (const float *)data, (float *)loss, (float *)grad_theta, (float *)grad_u0, (cudaStream_t)stream, true);
 }
 
 }  // extern "C"

@@ -63,4 +63,18 @@ cudaError_t launch_reduce(const float *partial, int nblocks, int P1, float *grad
     return cudaGetLastError();
 }
 
+cudaError_t launch_reduce_exchange(const float *partial, int nblocks, int P1, const PeerLinks &pl, unsigned epoch, float *grad, float *loss,
+                                   cudaStream_t st)
+{
+    PeerCtx c;
+    for (int r = 0; r < 16; ++r) {
+        c.flags[r] = r < pl.world ? reinterpret_cast<unsigned *>(pl.base[r]) : nullptr;
+        c.slots[r] = r < pl.world ? reinterpret_cast<float *>(reinterpret_cast<char *>(pl.base[r]) + PEER_HEADER_BYTES) : nullptr;
+    }
+    c.ticket = reinterpret_cast<unsigned *>(pl.base[pl.rank]) + 16;
+    c.rank = pl.rank; c.world = pl.world; c.P1pad = pl.P1pad;
+    ude_reduce_exchange_kernel<<<(P1 + 7) / 8, 256, 0, st>>>(partial, nblocks, P1, c, epoch, grad, loss);
+    return cudaGetLastError();
+}
+
 }  // namespace b200ude

@@ -94,6 +94,13 @@ int adj_rows_seir(int N);
 cudaError_t launch_fwd_fkpp16(const Variant &, const ConstTables &, const FwdParams &, int Nx, cudaStream_t);
 cudaError_t launch_adj_fkpp16(const Variant &, const ConstTables &, const AdjParams &, int Nx, cudaStream_t, int *rows_out);
 int adj_rows_fkpp16(int N, int Nx);
+// exchange buffers of the fused reduce + all-reduce (ude_adjoint.cuh): every rank's buffer as mapped in this process
+constexpr int PEER_HEADER_BYTES = 256;   // flags[16], ticket, padding
+struct PeerLinks {
+    void *base[16];
+    int rank = 0, world = 0, P1pad = 0;
+};
+cudaError_t launch_reduce_exchange(const float *partial, int nblocks, int P1, const PeerLinks &, unsigned epoch, float *grad, float *loss, cudaStream_t);
 cudaError_t launch_reduce(const float *partial, int nblocks, int P1, float *grad, float *loss, cudaStream_t);
 
 }  // namespace b200ude

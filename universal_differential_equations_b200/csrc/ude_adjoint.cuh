@@ -269,4 +269,77 @@ static __global__ void ude_reduce_kernel(const float *__restrict__ partial, int 
     }
 }
 
+// ---- the same reduction fused with the cross-GPU sum over NVLink peer memory (one launch, no NCCL) ----------------------
+// Every rank owns an exchange buffer (cudaMalloc'ed, mapped into every peer process with CUDA IPC):
+//   uint32 flags[16]   flags[src] = number of CTAs of rank `src` whose pushes have landed here (monotonic)
+//   uint32 ticket      local CTA counter (monotonic)
+//   float  slots[2][16][P1pad]   [epoch parity][source rank][entry]
+// Phase 1 (all CTAs, one warp per entry): local fixed-order sum over the partial rows, PUSHED with plain stores into
+// slots[parity][rank][q] of every rank (remote stores over NVLink are fire-and-forget), system-scope fence, then one
+// release increment of flags[rank] on every rank per CTA.  Phase 2 (the last CTA of this rank to finish phase 1): acquire-
+// spin until every source's flag reached epoch * gridDim.x, then sum the `world` slots of every entry in rank order ->
+// all ranks obtain bitwise identical sums.  Parity double-buffering makes the next call's pushes safe: a rank can push for
+// epoch e+2 only after it finished epoch e+1, which needed every peer's e+1 push, which a peer issues only after it finished
+// reading epoch e.  A bounded spin (about 2 s) turns a lost peer into NaN results instead of a hang.
+struct PeerCtx {
+    float *slots[16];        // every rank's slot array (this process's mappings), [2][16][P1pad]
+    unsigned *flags[16];     // every rank's flags
+    unsigned *ticket;        // this rank's CTA counter
+    int rank, world, P1pad;
+};
+
+static __global__ void ude_reduce_exchange_kernel(const float *__restrict__ partial, int nblocks, int P1, PeerCtx ctx, unsigned epoch,
+                                                  float *__restrict__ grad, float *__restrict__ loss)
+{
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int par = (int)(epoch & 1u);
+    if (q < P1) {
+        float acc = 0.f;
+        for (int b = lane; b < nblocks; b += 32) acc += partial[(size_t)b * P1 + q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane < ctx.world) {
+            float *dst = ctx.slots[lane] + ((size_t)par * 16 + ctx.rank) * ctx.P1pad + q;
+            *reinterpret_cast<volatile float *>(dst) = acc;
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int r = 0; r < ctx.world; ++r) atomicAdd_system(ctx.flags[r] + ctx.rank, 1u);
+        const unsigned t = atomicAdd(ctx.ticket, 1u);
+        s_last = ((t + 1u) % gridDim.x) == 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (threadIdx.x < ctx.world) {
+        const unsigned target = epoch * gridDim.x;
+        volatile unsigned *f = ctx.flags[ctx.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int)(*f - target) < 0) {
+            if (clock64() - t0 > 4000000000ll) { s_ok = 0; break; }   // ~2 s at 1.9 GHz
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const float *mine = ctx.slots[ctx.rank] + (size_t)par * 16 * ctx.P1pad;
+    for (int e = threadIdx.x; e < P1; e += blockDim.x) {
+        float tot = 0.f;
+        for (int r = 0; r < ctx.world; ++r) tot += __ldcg(mine + (size_t)r * ctx.P1pad + e);
+        if (!s_ok) tot = __int_as_float(0x7fc00000);
+        if (e == P1 - 1) {
+            if (loss) *loss = tot;
+        } else {
+            grad[e] = tot;
+        }
+    }
+}
+
 }  // namespace b200ude

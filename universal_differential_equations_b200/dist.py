@@ -21,3 +21,32 @@ def allreduce_loss_grad(buf: torch.Tensor):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     return buf
+
+
+class PeerAllReduce:
+    """Sets up the fused reduce + all-reduce over NVLink peer memory for one UDESolver per rank
+    (b200ude_peer_export / b200ude_peer_attach): CUDA IPC handles of the per-rank exchange buffers are gathered with
+    torch.distributed, attached, and all ranks are synchronised once.  Afterwards `solver.adjoint_l2_allreduce(data)` returns
+    the loss and grad_theta summed over all ranks with no NCCL call on the path.  world = 1 (no process group) works too."""
+
+    def __init__(self, solver, group=None):
+        self.solver = solver
+        have_pg = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if have_pg else 0
+        self.world = dist.get_world_size(group) if have_pg else 1
+        mine = solver.peer_export()
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, mine, group=group)
+        else:
+            gathered = [mine]
+        solver.peer_attach(self.rank, self.world, b"".join(gathered))
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=group)   # every rank's buffer is zeroed and mapped before anyone pushes
+
+    def close(self):
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+        self.solver.peer_detach()

@@ -370,6 +370,32 @@ class UDESolver:
         return loss.value, grad_theta, grad_u0
 
 
+    # -- multi-GPU: fused reduce + all-reduce over NVLink peer memory (dist.PeerAllReduce drives these) ----
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        _lib.check(self._h, self._L.b200ude_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == world * _lib.PEER_HANDLE_BYTES
+        _lib.check(self._h, self._L.b200ude_peer_attach(self._h, rank, world, handles))
+
+    def peer_detach(self):
+        _lib.check(self._h, self._L.b200ude_peer_detach(self._h))
+
+    def adjoint_l2_allreduce(self, data: torch.Tensor, want_grad_u0=False, grad_theta=None, loss=None):
+        """adjoint_l2 whose loss and grad_theta are summed over all attached ranks inside the reduction kernel."""
+        data = data.contiguous()
+        N = data.shape[2]
+        if grad_theta is None:
+            grad_theta = torch.empty(self.P, device=data.device, dtype=torch.float32)
+        if loss is None:
+            loss = torch.empty(1, device=data.device, dtype=torch.float32)
+        gu0 = torch.empty((self.d, N), device=data.device, dtype=torch.float32) if want_grad_u0 else None
+        _lib.check(self._h, self._L.b200ude_adjoint_l2_allreduce(self._h, data.data_ptr(), loss.data_ptr(), grad_theta.data_ptr(),
+                                                               gu0.data_ptr() if gu0 is not None else None, _stream_ptr(self.device)))
+        return loss, grad_theta, gu0
+
     # -- on-device optimiser ----------------------------------------------------------------
     @staticmethod
     def _adam_struct(opt, loss_scale=1.0, l2_reg=0.0):
