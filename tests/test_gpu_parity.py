@@ -442,6 +442,42 @@ def test_adaptive_tsit5_forward_and_adjoint_vs_oracle(golden, O):
         sv.close()
 
 
+@pytest.mark.parametrize("N,tol", [(300, 1e-5), (129, 1e-6)])
+def test_adaptive_tensor_core_lv32_vs_oracle_and_runtime_shape(O, N, tol, monkeypatch):
+    """Adaptive Tsit5 (abstol = reltol) on the tensor-core kernels of the headline chain: CTA-uniform attempt loops around
+    the collective 32x32 sweeps, replay adjoint with the mma.sync gradient GEMM.  Against the fp64 oracle (values, not step
+    sequences: fp32 round-off can flip accept/reject decisions) and against the runtime-shape adaptive kernels."""
+    ude = _ude()
+    rng = np.random.default_rng(N)
+    theta = glorot_theta((2, 32, 32, 2), seed=1)
+    u0, _ = synthetic_ensemble(N)
+    y = rng.normal(size=(31, 2, N)).astype(np.float32)
+    ts = np.linspace(0.0, 3.0, 31)
+    res = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("B200UDE_ADAPTIVE_TC", tc)
+        solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N, adaptive=True, abstol=tol, reltol=tol, max_steps=256)
+        res[tc] = _run(solver, theta, u0, y)
+        assert (res[tc][4] == 0).all()
+        solver.close()
+    out, loss, gth, gu, _ = res["1"]
+    m = O.lv_model()
+    l_ref, g_ref, gu_ref = 0.0, np.zeros(1218), np.zeros((2, N))
+    for k in range(N):
+        o64, rec = O.solve_adaptive_dense(m, theta.astype(np.float64), u0[:, k].astype(np.float64), ts, tol, tol)
+        assert np.abs(out[:, :, k] - o64).max() <= 50 * tol * (1 + np.abs(o64).max()) + 3e-5
+        l_ref += ((o64 - y[:, :, k]) ** 2).sum()
+        gk, guk = O.adjoint_replay(m, theta.astype(np.float64), ts, rec, 2 * (o64 - y[:, :, k]))
+        g_ref += gk
+        gu_ref[:, k] = guk
+    assert abs(loss - l_ref) <= 1e-3 * abs(l_ref)
+    assert np.linalg.norm(gth - g_ref) <= 5e-3 * np.linalg.norm(g_ref)
+    assert np.abs(gu - gu_ref).max() <= 5e-3 * np.abs(gu_ref).max()
+    o2, l2, g2, gu2, _ = res["0"]
+    assert np.abs(out - o2).max() <= 50 * tol * (1 + np.abs(o2).max()) + 3e-5
+    assert np.linalg.norm(gth - g2) <= 5e-3 * np.linalg.norm(g2)
+
+
 def test_vern7_fixed_step_forward_vs_oracle(golden, O):
     """solve(prob, Vern7(); saveat, adaptive=false): 9-stage 7th-order steps on the generic kernels vs the oracle's
     Vern7 (tableau = OrdinaryDiffEq's serialized constants, KAT-7).  The interpolating adjoint of a Vern7 handle runs

@@ -41,8 +41,35 @@ static cudaError_t launch_tc(const AdjParams &p, int *rows_out, cudaStream_t st)
     }
     const int grid = (p.N + 127) / 128;
     *rows_out = grid * 4;
-    kern<<<grid, 128, smem, st>>>(p);
+    kern<<<grid, 128, smem, st>>>(p, AdaptiveGrid{});
     return cudaGetLastError();
+}
+
+// adaptive (abstol / reltol) replay adjoint on the tensor-core kernels
+template <int TM>
+static cudaError_t launch_tc_adaptive(const AdjParams &p, const AdaptiveGrid &ag, int *rows_out, cudaStream_t st)
+{
+    auto kern = lv32::tc::adjoint_kernel<TM, 128, 4, 1, true>;
+    constexpr size_t smem = sizeof(lv32::tc::WarpStageT) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int grid = (p.N + 127) / 128;
+    *rows_out = grid * 4;
+    kern<<<grid, 128, smem, st>>>(p, ag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adj_lv32_adaptive(const Variant &v, const ConstTables &t, const AdjParams &p, const AdaptiveGrid &ag, cudaStream_t st, int *rows_out)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    return v.approx_tanh ? launch_tc_adaptive<1>(p, ag, rows_out, st) : launch_tc_adaptive<0>(p, ag, rows_out, st);
 }
 
 cudaError_t launch_adj_lv32(const Variant &v, const ConstTables &t, const AdjParams &p, cudaStream_t st, int *grid_out)

@@ -34,4 +34,14 @@ cudaError_t launch_fwd_lv32(const Variant &v, const ConstTables &t, const FwdPar
     return launch_one<0, WConst>(p, st);
 }
 
+cudaError_t launch_fwd_lv32_adaptive(const Variant &v, const ConstTables &t, const FwdParams &p, const AdaptiveGrid &ag, cudaStream_t st)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    const int grid = (p.N + 127) / 128;
+    if (v.approx_tanh) lv32::tc::adaptive_forward_kernel<1, 128, 4><<<grid, 128, 0, st>>>(p, ag);
+    else lv32::tc::adaptive_forward_kernel<0, 128, 4><<<grid, 128, 0, st>>>(p, ag);
+    return cudaGetLastError();
+}
+
 }  // namespace b200ude

@@ -75,6 +75,8 @@ cudaError_t launch_adj_lv32(const Variant &, const ConstTables &, const AdjParam
 cudaError_t launch_fwd_lv5(int n_prefix, const Variant &, const ConstTables &, const FwdParams &, cudaStream_t);
 cudaError_t launch_adj_lv5(int n_prefix, const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *grid_out);
 int adj_grid_lv32(int N);
+cudaError_t launch_fwd_lv32_adaptive(const Variant &, const ConstTables &, const FwdParams &, const AdaptiveGrid &, cudaStream_t);
+cudaError_t launch_adj_lv32_adaptive(const Variant &, const ConstTables &, const AdjParams &, const AdaptiveGrid &, cudaStream_t, int *rows_out);
 int adj_grid_lv5(int N);
 cudaError_t launch_fwd_generic(const GenericShape &, const ConstTables &, const FwdParams &, cudaStream_t);
 cudaError_t launch_adj_generic(const GenericShape &, const ConstTables &, const AdjParams &, cudaStream_t, int *rows_out);
