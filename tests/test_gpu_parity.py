@@ -478,6 +478,49 @@ def test_adaptive_tensor_core_lv32_vs_oracle_and_runtime_shape(O, N, tol, monkey
     assert np.linalg.norm(gth - g2) <= 5e-3 * np.linalg.norm(g2)
 
 
+def test_adaptive_tensor_core_seir_vs_oracle_and_runtime_shape(O, monkeypatch):
+    """Adaptive Tsit5 on the SEIR exposure tensor-core kernels (seir_exposure.jl:137-141 style call: saveat daily over
+    (0, 21), abstol = reltol): against the fp64 oracle (adaptive solve + replay adjoint) and the runtime-shape kernels.
+    fp32 state with S, N ~ 1.4e7: per-component scales, tol = 1e-4."""
+    ude = _ude()
+    rng = np.random.default_rng(17)
+    N, tol = 150, 1e-4
+    chain = ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1))
+    f = ude.SEIRExposureUDE(chain)
+    theta = glorot_theta((3, 64, 64, 1), seed=2)
+    S0 = 14e6
+    u0 = np.zeros((7, N), np.float32)
+    u0[0] = 0.9 * S0 * rng.uniform(0.9, 1.0, N)
+    u0[1:4] = rng.uniform(0, 50, (3, N)); u0[4] = S0; u0[5] = rng.uniform(0, 10, N); u0[6] = rng.uniform(0, 100, N)
+    ts = np.linspace(0.0, 21.0, 22)
+    m = O.seir_model()
+    w = np.array([0, 1, 1, 1, 0, 0, 0], np.float64)
+    ref = [O.solve_adaptive_dense(m, theta.astype(np.float64), u0[:, k].astype(np.float64), ts, tol, tol) for k in range(N)]
+    y = (np.stack([r[0] for r in ref], axis=2) * (1 + 0.05 * rng.standard_normal((22, 7, N)))).astype(np.float32)
+    res = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("B200UDE_ADAPTIVE_TC", tc)
+        solver = ude.UDESolver(f, 0.0, 1.0, 21, 1, max_trajectories=N, adaptive=True, abstol=tol, reltol=tol, max_steps=256, loss_weights=w)
+        res[tc] = _run(solver, theta, u0, y)
+        assert (res[tc][4] == 0).all()
+        solver.close()
+    out, loss, gth, gu, _ = res["1"]
+    scale = np.abs(np.stack([r[0] for r in ref], axis=2)).max(axis=(0, 2), keepdims=True)
+    l_ref, g_ref = 0.0, np.zeros(4481)
+    for k in range(N):
+        o64, rec = ref[k]
+        assert np.all(np.abs(out[:, :, k] - o64) <= 50 * tol * scale[:, :, 0] + 1e-2)
+        r = (o64 - y[:, :, k]) * w[None, :]
+        l_ref += (w[None, :] * (o64 - y[:, :, k]) ** 2).sum()
+        gk, _ = O.adjoint_replay(m, theta.astype(np.float64), ts, rec, 2 * r)
+        g_ref += gk
+    assert abs(loss - l_ref) <= 2e-2 * abs(l_ref)
+    assert np.linalg.norm(gth - g_ref) <= 3e-2 * np.linalg.norm(g_ref)
+    o2, l2, g2, gu2, _ = res["0"]
+    assert np.all(np.abs(out - o2) <= 50 * tol * scale + 1e-2)
+    assert np.linalg.norm(gth - g2) <= 3e-2 * np.linalg.norm(g2)
+
+
 def test_vern7_fixed_step_forward_vs_oracle(golden, O):
     """solve(prob, Vern7(); saveat, adaptive=false): 9-stage 7th-order steps on the generic kernels vs the oracle's
     Vern7 (tableau = OrdinaryDiffEq's serialized constants, KAT-7).  The interpolating adjoint of a Vern7 handle runs

@@ -100,3 +100,14 @@ s = ude.UDESolver(ude.LotkaVolterraUDE(chain), 0.0, 0.1, 30, 1, max_trajectories
 tf, ta = gpu_time(s, theta, u0, y)
 s.close()
 report("LV 2-32-32-2 ADAPTIVE Tsit5 abstol=reltol=1e-6, N=65536", N, tf, ta, 0.0, None, {"kernels": "lv32::tc::adaptive_forward_kernel / lv32::tc::adjoint_kernel<ADAPT> (B200UDE_ADAPTIVE_TC=0: generic::adaptive_*)"})
+
+# ---- SEIR exposure UDE, adaptive Tsit5 abstol = reltol = 1e-4 (fp32 states of magnitude 1e7), saved daily
+N = 65536
+chain = ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1))
+theta = glorot_theta((3, 64, 64, 1), seed=2)
+u0 = np.zeros((7, N), np.float32); u0[0] = 0.9 * S0 * rng.uniform(0.9, 1.0, N); u0[1:4] = rng.uniform(0, 50, (3, N)); u0[4] = S0
+y = rng.uniform(0, 100, (22, 7, N)).astype(np.float32)
+s = ude.UDESolver(ude.SEIRExposureUDE(chain), 0.0, 1.0, 21, 1, max_trajectories=N, loss_weights=[0, 1, 1, 1, 0, 0, 0], adaptive=True, abstol=1e-4, reltol=1e-4, max_steps=128)
+tf, ta = gpu_time(s, theta, u0, y)
+s.close()
+report("SEIR exposure UDE 3-64-64-1 ADAPTIVE Tsit5 abstol=reltol=1e-4, saveat daily over (0, 21), N=65536", N, tf, ta, 0.0, None, {"kernels": "seir::adaptive_forward_kernel / seir::adjoint_kernel<ADAPT>"})

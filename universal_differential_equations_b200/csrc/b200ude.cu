@@ -178,7 +178,8 @@ int32_t tsit5_forward(b200ude_handle *h, const float *u0, size_t N, float *out, 
     p.N = (int)N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P; p.dt = (float)h->desc.dt;
     cudaError_t e = cudaSuccess;
     if (h->adaptive) {
-        e = h->kid == K_LV32 ? launch_fwd_lv32_adaptive(h->var, h->tab, p, h->ag, st) : launch_fwd_adaptive(h->gen, h->tab, p, h->ag, st);
+        e = h->kid == K_LV32 ? launch_fwd_lv32_adaptive(h->var, h->tab, p, h->ag, st)
+            : h->kid == K_SEIR64 ? launch_fwd_seir_adaptive(h->var, h->tab, p, h->ag, st) : launch_fwd_adaptive(h->gen, h->tab, p, h->ag, st);
         CUDA_TRY(h, e);
         h->last_out = out;
         return B200UDE_OK;
@@ -256,6 +257,7 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
             p.fused_l2 = 0;
         }
         if (h->kid == K_LV32) CUDA_TRY(h, launch_adj_lv32_adaptive(h->var, h->tab, p, h->ag, st, &grid));
+        else if (h->kid == K_SEIR64) CUDA_TRY(h, launch_adj_seir_adaptive(h->var, h->tab, p, h->ag, st, &grid));
         else CUDA_TRY(h, launch_adj_adaptive(h->gen, h->tab, p, h->ag, st, &grid));
         CUDA_TRY(h, launch_reduce(h->d_partial, grid, h->P + 1, grad_theta, loss, st));
         if (l2 && loss) CUDA_TRY(h, launch_l2_finish(h->d_block_loss, loss, st));
@@ -396,7 +398,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         if (!generic_ok(*d) || d->model == B200UDE_MODEL_FKPP)
             return fail(nullptr, B200UDE_EUNSUPPORTED, "create: adaptive stepping is implemented for the LV / SEIR / NODE forms (chain widths <= 64)");
         // adaptive solves run on the runtime-shape kernels, except the headline chain (tensor-core kernels with CTA-uniform attempt loops)
-        if (!(kid == K_LV32 && d->solver == B200UDE_TSIT5 && env_int("B200UDE_ADAPTIVE_TC", 1))) kid = K_GENERIC;
+        if (!((kid == K_LV32 || kid == K_SEIR64) && d->solver == B200UDE_TSIT5 && env_int("B200UDE_ADAPTIVE_TC", 1))) kid = K_GENERIC;
     }
     if (kid == K_NONE)
         return fail(nullptr, B200UDE_EUNSUPPORTED,

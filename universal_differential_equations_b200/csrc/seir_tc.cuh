@@ -281,6 +281,188 @@ __global__ void __launch_bounds__(BLOCK, 1) forward_kernel(FwdParams p)
     cta_teardown(tmem_base);
 }
 
+// ---- adaptive forward kernel (abstol / reltol): Tsit5 + OrdinaryDiffEq's PI controller per trajectory, saveat by the free
+// interpolant, step record for the replay adjoint; CTA-uniform attempt loop (see lv32::tc::adaptive_forward_kernel) ----------
+template <int TM>
+__global__ void __launch_bounds__(BLOCK, 1) adaptive_forward_kernel(FwdParams p, AdaptiveGrid ag)
+{
+    extern __shared__ __align__(1024) float s_dyn[];
+    float *sWf_hi = s_dyn, *sWf_lo = s_dyn + HS * HS;
+    __shared__ __align__(8) uint64_t mbars[GROUPS];
+    __shared__ uint32_t tmem_slot;
+    GrpCtx c = cta_setup(mbars, &tmem_slot);
+    const uint32_t tmem_base = tmem_slot;
+    stage_weights64<false>(p.theta, sWf_hi, sWf_lo, threadIdx.x, BLOCK);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const bool issuer = (threadIdx.x % GROUP) == 0;
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = gid < p.N;
+    const size_t n = live ? (size_t)gid : (size_t)(p.N - 1);
+    const float t0 = ag.t0, t1 = ag.t0 + ag.save_dt * (float)(ag.n_save - 1);
+    const float abstol = ag.abstol, reltol = ag.reltol;
+    const float gamma = 0.9f, qmin = 0.2f, qmax = 10.0f, beta1 = 7.0f / 50.0f, beta2 = 2.0f / 25.0f;
+    State7 u;
+#pragma unroll
+    for (int cc = 0; cc < D; ++cc) u.v[cc] = __ldg(p.u0 + (size_t)cc * N + n);
+    auto store = [&](float *base, int row, const State7 &v) {
+        if (live) {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) base[((size_t)row * D + cc) * N + n] = v.v[cc];
+        }
+    };
+    store(p.out, 0, u);
+    store(p.ustep, 0, u);
+    if (live) ag.tgrid[n] = t0;
+    State7 k[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) k[j].v[cc] = 0.0f;
+    k[0] = rhs_seir<TM>(&c, sWf_hi, sWf_lo, u, 0, issuer);
+    store(p.dense, 0, k[0]);
+    float dt;
+    {   // initial step: Hairer-Norsett-Wanner as in OrdinaryDiffEq
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) {
+            const float sk = abstol + reltol * fabsf(u.v[cc]);
+            d0 += (u.v[cc] / sk) * (u.v[cc] / sk);
+            d1 += (k[0].v[cc] / sk) * (k[0].v[cc] / sk);
+        }
+        d0 = sqrtf(d0 / D); d1 = sqrtf(d1 / D);
+        float dt0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+        dt0 = fminf(dt0, t1 - t0);
+        State7 g;
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) g.v[cc] = fmaf(dt0, k[0].v[cc], u.v[cc]);
+        const State7 f1 = rhs_seir<TM>(&c, sWf_hi, sWf_lo, g, 1, issuer);
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) {
+            const float sk = abstol + reltol * fabsf(u.v[cc]);
+            const float e = (f1.v[cc] - k[0].v[cc]) / sk;
+            d2 += e * e;
+        }
+        d2 = sqrtf(d2 / D) / dt0;
+        const float dm = fmaxf(d1, d2);
+        const float dt1 = dm <= 1e-15f ? fmaxf(1e-6f, dt0 * 1e-3f) : exp10f(-(2.0f + log10f(dm)) / 5.0f);
+        dt = fminf(fminf(100.0f * dt0, dt1), t1 - t0);
+    }
+    float t = t0, qold = 1e-4f;
+    int nacc = 0, isave = 1, bad = 0;
+#pragma unroll 1
+    while (true) {
+        const bool active = (isave < ag.n_save) && !bad;
+        if (!__syncthreads_or(active ? 1 : 0)) break;
+        float h = dt;
+        bool clipped = false;
+        if (t + h >= t1 - 1e-6f * fabsf(t1)) { h = t1 - t; clipped = true; }
+        if (!active) h = 0.0f;
+        State7 un = u;
+#pragma unroll 1
+        for (int i = 1; i < 7; ++i) {
+            State7 g;
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) g.v[cc] = 0.0f;
+#define B200UDE_SEIR_COMB(I)                                                              \
+    case I: {                                                                             \
+        _Pragma("unroll") for (int j = 0; j < I; ++j) if (Tsit5::a(I, j) != 0.0) {        \
+            _Pragma("unroll") for (int cc = 0; cc < D; ++cc)                              \
+                g.v[cc] = fmaf((float)Tsit5::a(I, j), k[j].v[cc], g.v[cc]);               \
+        }                                                                                 \
+    } break;
+            switch (i) {
+                B200UDE_SEIR_COMB(1)
+                B200UDE_SEIR_COMB(2)
+                B200UDE_SEIR_COMB(3)
+                B200UDE_SEIR_COMB(4)
+                B200UDE_SEIR_COMB(5)
+            default:
+                B200UDE_SEIR_COMB(6)
+            }
+#undef B200UDE_SEIR_COMB
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) g.v[cc] = fmaf(h, g.v[cc], u.v[cc]);
+            if (i == 6) un = g;
+            const State7 kk = rhs_seir<TM>(&c, sWf_hi, sWf_lo, g, i, issuer);
+            switch (i) {
+            case 1: k[1] = kk; break;
+            case 2: k[2] = kk; break;
+            case 3: k[3] = kk; break;
+            case 4: k[4] = kk; break;
+            case 5: k[5] = kk; break;
+            default: k[6] = kk; break;
+            }
+        }
+        if (active) {
+            float ee = 0.0f;
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) {
+                float e = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) e = fmaf(lv32::tc::tsit5_btilde_rt(j), k[j].v[cc], e);
+                e *= h;
+                const float sc = abstol + reltol * fmaxf(fabsf(u.v[cc]), fabsf(un.v[cc]));
+                ee += (e / sc) * (e / sc);
+            }
+            const float EEst = sqrtf(ee / D);
+            if (!(EEst <= 3.0e38f)) {
+                bad = 1;
+            } else {
+                const float q11 = powf(EEst, beta1);
+                float q = fminf(fmaxf(q11 / powf(qold, beta2) / gamma, 1.0f / qmax), 1.0f / qmin);
+                if (EEst <= 1.0f) {
+                    if (nacc >= ag.max_steps) {
+                        bad = 2;
+                    } else {
+                        const float tn = clipped ? t1 : t + h;
+#pragma unroll
+                        for (int i = 1; i < 7; ++i) store(p.dense, nacc * 6 + i, k[i]);
+                        while (isave < ag.n_save) {
+                            const float ts = t0 + ag.save_dt * (float)isave;
+                            if (ts > tn + 1e-6f * fabsf(tn)) break;
+                            float bw[7];
+                            lv32::tc::tsit5_weights_fwd(fminf((ts - t) / h, 1.0f), bw);
+                            State7 o;
+#pragma unroll
+                            for (int cc = 0; cc < D; ++cc) {
+                                float acc = 0.0f;
+#pragma unroll
+                                for (int j = 0; j < 7; ++j) acc = fmaf(bw[j], k[j].v[cc], acc);
+                                o.v[cc] = fmaf(h, acc, u.v[cc]);
+                            }
+                            store(p.out, isave, o);
+                            ++isave;
+                        }
+                        qold = fmaxf(EEst, 1e-4f);
+                        if (q >= 1.0f && q <= 1.2f) q = 1.0f;
+                        if (!clipped || h >= dt) dt = h / q;
+                        else dt = fmaxf(dt, h / q);
+                        t = tn;
+                        ++nacc;
+                        if (live) ag.tgrid[(size_t)nacc * N + n] = t;
+                        u = un;
+                        k[0] = k[6];
+                        store(p.ustep, nacc, u);
+                    }
+                } else {
+                    dt = h / fminf(1.0f / qmin, q11 / gamma);
+                }
+            }
+        }
+    }
+    if (live) ag.nacc[n] = nacc;
+    if (p.status && live) {
+        bool ok = true;
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) ok = ok && (fabsf(u.v[cc]) <= 3.0e38f);
+        p.status[n] = bad == 2 ? 2 : ((bad || !ok) ? 1 : 0);
+    }
+    cta_teardown(tmem_base);
+}
+
 // ---- adjoint kernel --------------------------------------------------------------------------------------
 constexpr int SLD64 = 68;   // staged row stride (floats): 64 + 4
 struct __align__(16) GroupStage {
@@ -294,8 +476,8 @@ struct __align__(16) GroupStage {
 // GEMM = 1: the group's gradient GEMM dW2 += q2 (x) h1 (64 x 64 outputs, K = 128 trajectories) as 3xTF32 warp-level
 // mma.sync.m16n8k8 -- warp w of the group owns the 16 rows j = 16 w .. 16 w + 15 and all 8 column tiles; fragments are read
 // from the staged rows with the bank-conflict-free k permutation of lv32_tc.cuh.  GEMM = 0: FFMA2 8 x 4 register tiles.
-template <int TM, int GEMM>
-__global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
+template <int TM, int GEMM, bool ADAPT = false>
+__global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p, AdaptiveGrid ag)
 {
     extern __shared__ __align__(1024) float s_dyn[];
     float *sWf_hi = s_dyn, *sWf_lo = s_dyn + HS * HS, *sWb_hi = s_dyn + 2 * HS * HS, *sWb_lo = s_dyn + 3 * HS * HS;
@@ -339,8 +521,169 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
     for (int cc = 0; cc < D; ++cc) lam[cc] = 0.0f;
     float loss = 0.0f;
     const int n_save = p.n_steps / p.save_every + 1;
-    loss_jump<D>(p, n_save - 1, n, N, lam, loss);
+    bool first_flush = true;
 
+    // One evaluation of (df/du)^T g (-> kn) and of the theta-gradient quadrature term at state u, stage argument g:
+    // sc = quadrature weight (h b_i), isc = 1 / sc (0 for a masked thread), lvm = 0/1 mask.
+    auto eval_core = [&](int stage, const float (&u)[D], const float (&g)[D], float sc, float isc, float lvm, float (&kn)[D]) {
+        const int zb = lv32::c_zero[stage] << 2;
+        float x[3];
+        seir_inputs(u, x);
+        const float sg = lvm * sc * (g[1] - g[0]);   // z enters dS with -, dE with +
+        group_sync(c.bar_id);                       // the previous stage's column passes are done with SG / U / B1
+        st->SG[tg] = sg;
+        *reinterpret_cast<float4 *>(&st->U[tg * 4]) = make_float4(x[0], x[1], x[2], 0.0f);
+
+        // ---- chain forward ----
+        float v[HS];
+#pragma unroll
+        for (int j4 = 0; j4 < HS; j4 += 4) {
+            const float4 wb = ldw4(zb + OFF_B1 + j4), w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
+            const float b_[4] = {wb.x, wb.y, wb.z, wb.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[j4 + k] = tanh_dev<TM>(fmaf(w2_[k], x[2], fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k]))));
+            *reinterpret_cast<float4 *>(rowB2 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // h1 row
+        }
+        tc_issue64(c, v, sWf_hi, sWf_lo, issuer);
+        tc_collect64(c, v);   // v = W2 h1
+        // h2 = tanh(. + b2) -> B1 row;  q2 = W3 * sg * (1 - h2^2) stays in v
+#pragma unroll
+        for (int j4 = 0; j4 < HS; j4 += 4) {
+            const float4 b2 = ldw4(zb + OFF_B2 + j4), w3 = ldw4(zb + OFF_W3 + j4);
+            const float b_[4] = {b2.x, b2.y, b2.z, b2.w}, w3_[4] = {w3.x, w3.y, w3.z, w3.w};
+            float h2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                h2[k] = tanh_dev<TM>(v[j4 + k] + b_[k]);
+                v[j4 + k] = w3_[k] * sg * fmaf(-h2[k], h2[k], 1.0f);
+            }
+            *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        }
+        group_sync(c.bar_id);
+        // column pass A: dW3[j] += sum_t SG[t] h2[t][j];  db3 += sum_t SG[t]
+#pragma unroll 8
+        for (int t = tlo; t < tlo + 64; ++t) {
+            const float sgt = st->SG[t];
+            a_w3 = fmaf(sgt, st->B1[t * SLD64 + jc], a_w3);
+            a_b3 += sgt;
+        }
+        group_sync(c.bar_id);
+#pragma unroll
+        for (int j4 = 0; j4 < HS; j4 += 4) *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // q2 row
+        // ---- W2^T q2 on the tensor core; gradient GEMM of the group while the MMAs are in flight ----
+        tc_issue64(c, v, sWb_hi, sWb_lo, issuer);
+        if constexpr (GEMM == 1) {
+#pragma unroll 1
+            for (int ks = 0; ks < GROUP / 8; ++ks) {
+                const float *q0 = st->B1 + (8 * ks + 2 * tig) * SLD64 + 16 * wg + fg, *q1 = q0 + SLD64;
+                const float *h0 = st->B2 + (8 * ks + 2 * tig) * SLD64 + fg, *h1r = h0 + SLD64;
+                uint32_t ah[4], al[4];
+                lv32::tc::split_tf32(q0[0], ah[0], al[0]);
+                lv32::tc::split_tf32(q0[8], ah[1], al[1]);
+                lv32::tc::split_tf32(q1[0], ah[2], al[2]);
+                lv32::tc::split_tf32(q1[8], ah[3], al[3]);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        lv32::tc::split_tf32(h0[8 * (4 * half + k)], bh[k][0], bl[k][0]);
+                        lv32::tc::split_tf32(h1r[8 * (4 * half + k)], bh[k][1], bl[k][1]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float (&cf)[4] = *reinterpret_cast<float (*)[4]>(&macc[4 * (4 * half + k)]);
+                        lv32::tc::mma_m16n8k8(cf, al, bh[k]);
+                        lv32::tc::mma_m16n8k8(cf, ah, bl[k]);
+                        lv32::tc::mma_m16n8k8(cf, ah, bh[k]);
+                    }
+                }
+            }
+            lv32::tc::tmem_flush32(sum_taddr, macc, first_flush); first_flush = false;   // per evaluation: 48-MMA chains
+#pragma unroll 8
+            for (int t = tlo; t < tlo + 64; ++t) a_b2 += st->B1[t * SLD64 + jc];   // db2[j] += sum_t q2[t][j]
+        } else {
+            float4 G0[2], G1[2], Hh[2];
+            auto load_row = [&](int t, int b) {
+                const float *r1 = st->B1 + t * SLD64, *r2 = st->B2 + t * SLD64;
+                G0[b] = *reinterpret_cast<const float4 *>(r1 + jt * 8);
+                G1[b] = *reinterpret_cast<const float4 *>(r1 + jt * 8 + 4);
+                Hh[b] = *reinterpret_cast<const float4 *>(r2 + it * 4);
+            };
+            auto use_row = [&](int b) {
+                const float gj[8] = {G0[b].x, G0[b].y, G0[b].z, G0[b].w, G1[b].x, G1[b].y, G1[b].z, G1[b].w};
+                const float2 h01 = make_float2(Hh[b].x, Hh[b].y), h23 = make_float2(Hh[b].z, Hh[b].w);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    acc[2 * jj] = fma2(bc(gj[jj]), h01, acc[2 * jj]);
+                    acc[2 * jj + 1] = fma2(bc(gj[jj]), h23, acc[2 * jj + 1]);
+                }
+            };
+            load_row(0, 0);
+#pragma unroll 1
+            for (int t = 0; t < GROUP; t += 2) {
+                load_row(t + 1, 1);
+                use_row(0);
+                if (t + 2 < GROUP) load_row(t + 2, 0);
+                use_row(1);
+            }
+#pragma unroll 8
+            for (int t = tlo; t < tlo + 64; ++t) a_b2 += st->B1[t * SLD64 + jc];   // db2[j] += sum_t q2[t][j]
+        }
+        tc_collect64(c, v);   // v = W2^T q2
+        group_sync(c.bar_id);  // everyone is done reading q2 / h1 rows
+        float dx0 = 0.0f, dx1 = 0.0f, dx2 = 0.0f;
+#pragma unroll
+        for (int j4 = 0; j4 < HS; j4 += 4) {
+            const float4 hh = *reinterpret_cast<const float4 *>(rowB2 + j4);
+            const float4 w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
+            const float h_[4] = {hh.x, hh.y, hh.z, hh.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[j4 + k] *= fmaf(-h_[k], h_[k], 1.0f);   // q1
+                dx0 = fmaf(w0_[k], v[j4 + k], dx0);
+                dx1 = fmaf(w1_[k], v[j4 + k], dx1);
+                dx2 = fmaf(w2_[k], v[j4 + k], dx2);
+            }
+            *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // q1 row
+        }
+        dx0 *= isc; dx1 *= isc; dx2 *= isc;   // cotangent of the chain input, quadrature weight removed
+        // (df/du)^T g: physics Jacobian of seir_exposure.jl:117-130 plus the chain-input map [S/N, I, D/N]
+        {
+            const float S = u[0], Nn = u[4], Dd = u[5];
+            const float cS = b0 * F / Nn, cN = -b0 * S * F / (Nn * Nn), invN = 1.0f / Nn;
+                        kn[0] = g[0] * (-cS - mu) + g[1] * cS + dx0 * invN;
+            kn[1] = g[1] * (-(sgm + mu)) + g[2] * sgm + g[6] * sgm;
+            kn[2] = g[2] * (-(gm + mu)) + g[3] * gm + g[5] * dd * gm + dx1;
+            kn[3] = g[3] * (-mu);
+            kn[4] = g[0] * (-cN) + g[1] * cN + g[4] * (-mu) - dx0 * S * invN * invN - dx2 * Dd * invN * invN;
+            kn[5] = g[5] * (-lm) + dx2 * invN;
+            kn[6] = 0.0f;
+        }
+        group_sync(c.bar_id);
+        // column pass B: dW1[j][m] += sum_t q1[t][j] x[t][m];  db1[j] += sum_t q1[t][j]
+#pragma unroll 8
+        for (int t = tlo; t < tlo + 64; ++t) {
+            const float qq = st->B1[t * SLD64 + jc];
+            const float4 u4 = *reinterpret_cast<const float4 *>(&st->U[t * 4]);
+            a_w10 = fmaf(qq, u4.x, a_w10);
+            a_w11 = fmaf(qq, u4.y, a_w11);
+            a_w12 = fmaf(qq, u4.z, a_w12);
+            a_b1 += qq;
+        }
+    };
+#define B200UDE_SEIR_SETKL_ALL()                                                                      \
+    switch (stage) {                                                                                  \
+    case 0: _Pragma("unroll") for (int cc = 0; cc < D; ++cc) kl[0][cc] = kn[cc]; break;               \
+    case 1: _Pragma("unroll") for (int cc = 0; cc < D; ++cc) kl[1][cc] = kn[cc]; break;               \
+    case 2: _Pragma("unroll") for (int cc = 0; cc < D; ++cc) kl[2][cc] = kn[cc]; break;               \
+    case 3: _Pragma("unroll") for (int cc = 0; cc < D; ++cc) kl[3][cc] = kn[cc]; break;               \
+    case 4: _Pragma("unroll") for (int cc = 0; cc < D; ++cc) kl[4][cc] = kn[cc]; break;               \
+    default: _Pragma("unroll") for (int cc = 0; cc < D; ++cc) kl[5][cc] = kn[cc]; break;              \
+    }
+
+    if constexpr (!ADAPT) {
+    loss_jump<D>(p, n_save - 1, n, N, lam, loss);
 #pragma unroll 1
     for (int s = p.n_steps - 1; s >= 0; --s) {
         float kl[6][D];
@@ -368,164 +711,9 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
                 B200UDE_SEIR_PRE(5)
             }
 #undef B200UDE_SEIR_PRE
-            const int zb = lv32::c_zero[stage] << 2;
-            float x[3];
-            seir_inputs(u, x);
-            const float sg = lv * sc * (g[1] - g[0]);   // z enters dS with -, dE with +
-            group_sync(c.bar_id);                       // the previous stage's column passes are done with SG / U / B1
-            st->SG[tg] = sg;
-            *reinterpret_cast<float4 *>(&st->U[tg * 4]) = make_float4(x[0], x[1], x[2], 0.0f);
-
-            // ---- chain forward ----
-            float v[HS];
-#pragma unroll
-            for (int j4 = 0; j4 < HS; j4 += 4) {
-                const float4 wb = ldw4(zb + OFF_B1 + j4), w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
-                const float b_[4] = {wb.x, wb.y, wb.z, wb.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[j4 + k] = tanh_dev<TM>(fmaf(w2_[k], x[2], fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k]))));
-                *reinterpret_cast<float4 *>(rowB2 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // h1 row
-            }
-            tc_issue64(c, v, sWf_hi, sWf_lo, issuer);
-            tc_collect64(c, v);   // v = W2 h1
-            // h2 = tanh(. + b2) -> B1 row;  q2 = W3 * sg * (1 - h2^2) stays in v
-#pragma unroll
-            for (int j4 = 0; j4 < HS; j4 += 4) {
-                const float4 b2 = ldw4(zb + OFF_B2 + j4), w3 = ldw4(zb + OFF_W3 + j4);
-                const float b_[4] = {b2.x, b2.y, b2.z, b2.w}, w3_[4] = {w3.x, w3.y, w3.z, w3.w};
-                float h2[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    h2[k] = tanh_dev<TM>(v[j4 + k] + b_[k]);
-                    v[j4 + k] = w3_[k] * sg * fmaf(-h2[k], h2[k], 1.0f);
-                }
-                *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(h2[0], h2[1], h2[2], h2[3]);
-            }
-            group_sync(c.bar_id);
-            // column pass A: dW3[j] += sum_t SG[t] h2[t][j];  db3 += sum_t SG[t]
-#pragma unroll 8
-            for (int t = tlo; t < tlo + 64; ++t) {
-                const float sgt = st->SG[t];
-                a_w3 = fmaf(sgt, st->B1[t * SLD64 + jc], a_w3);
-                a_b3 += sgt;
-            }
-            group_sync(c.bar_id);
-#pragma unroll
-            for (int j4 = 0; j4 < HS; j4 += 4) *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // q2 row
-            // ---- W2^T q2 on the tensor core; gradient GEMM of the group while the MMAs are in flight ----
-            tc_issue64(c, v, sWb_hi, sWb_lo, issuer);
-            if constexpr (GEMM == 1) {
-#pragma unroll 1
-                for (int ks = 0; ks < GROUP / 8; ++ks) {
-                    const float *q0 = st->B1 + (8 * ks + 2 * tig) * SLD64 + 16 * wg + fg, *q1 = q0 + SLD64;
-                    const float *h0 = st->B2 + (8 * ks + 2 * tig) * SLD64 + fg, *h1r = h0 + SLD64;
-                    uint32_t ah[4], al[4];
-                    lv32::tc::split_tf32(q0[0], ah[0], al[0]);
-                    lv32::tc::split_tf32(q0[8], ah[1], al[1]);
-                    lv32::tc::split_tf32(q1[0], ah[2], al[2]);
-                    lv32::tc::split_tf32(q1[8], ah[3], al[3]);
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            lv32::tc::split_tf32(h0[8 * (4 * half + k)], bh[k][0], bl[k][0]);
-                            lv32::tc::split_tf32(h1r[8 * (4 * half + k)], bh[k][1], bl[k][1]);
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            float (&cf)[4] = *reinterpret_cast<float (*)[4]>(&macc[4 * (4 * half + k)]);
-                            lv32::tc::mma_m16n8k8(cf, al, bh[k]);
-                            lv32::tc::mma_m16n8k8(cf, ah, bl[k]);
-                            lv32::tc::mma_m16n8k8(cf, ah, bh[k]);
-                        }
-                    }
-                }
-                lv32::tc::tmem_flush32(sum_taddr, macc, (s == p.n_steps - 1) && (stage == 0));   // per evaluation: 48-MMA chains
-#pragma unroll 8
-                for (int t = tlo; t < tlo + 64; ++t) a_b2 += st->B1[t * SLD64 + jc];   // db2[j] += sum_t q2[t][j]
-            } else {
-                float4 G0[2], G1[2], Hh[2];
-                auto load_row = [&](int t, int b) {
-                    const float *r1 = st->B1 + t * SLD64, *r2 = st->B2 + t * SLD64;
-                    G0[b] = *reinterpret_cast<const float4 *>(r1 + jt * 8);
-                    G1[b] = *reinterpret_cast<const float4 *>(r1 + jt * 8 + 4);
-                    Hh[b] = *reinterpret_cast<const float4 *>(r2 + it * 4);
-                };
-                auto use_row = [&](int b) {
-                    const float gj[8] = {G0[b].x, G0[b].y, G0[b].z, G0[b].w, G1[b].x, G1[b].y, G1[b].z, G1[b].w};
-                    const float2 h01 = make_float2(Hh[b].x, Hh[b].y), h23 = make_float2(Hh[b].z, Hh[b].w);
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        acc[2 * jj] = fma2(bc(gj[jj]), h01, acc[2 * jj]);
-                        acc[2 * jj + 1] = fma2(bc(gj[jj]), h23, acc[2 * jj + 1]);
-                    }
-                };
-                load_row(0, 0);
-#pragma unroll 1
-                for (int t = 0; t < GROUP; t += 2) {
-                    load_row(t + 1, 1);
-                    use_row(0);
-                    if (t + 2 < GROUP) load_row(t + 2, 0);
-                    use_row(1);
-                }
-#pragma unroll 8
-                for (int t = tlo; t < tlo + 64; ++t) a_b2 += st->B1[t * SLD64 + jc];   // db2[j] += sum_t q2[t][j]
-            }
-            tc_collect64(c, v);   // v = W2^T q2
-            group_sync(c.bar_id);  // everyone is done reading q2 / h1 rows
-            float dx0 = 0.0f, dx1 = 0.0f, dx2 = 0.0f;
-#pragma unroll
-            for (int j4 = 0; j4 < HS; j4 += 4) {
-                const float4 hh = *reinterpret_cast<const float4 *>(rowB2 + j4);
-                const float4 w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
-                const float h_[4] = {hh.x, hh.y, hh.z, hh.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    v[j4 + k] *= fmaf(-h_[k], h_[k], 1.0f);   // q1
-                    dx0 = fmaf(w0_[k], v[j4 + k], dx0);
-                    dx1 = fmaf(w1_[k], v[j4 + k], dx1);
-                    dx2 = fmaf(w2_[k], v[j4 + k], dx2);
-                }
-                *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // q1 row
-            }
-            dx0 *= isc; dx1 *= isc; dx2 *= isc;   // cotangent of the chain input, quadrature weight removed
-            // (df/du)^T g: physics Jacobian of seir_exposure.jl:117-130 plus the chain-input map [S/N, I, D/N]
-            {
-                const float S = u[0], Nn = u[4], Dd = u[5];
-                const float cS = b0 * F / Nn, cN = -b0 * S * F / (Nn * Nn), invN = 1.0f / Nn;
-                float kn[D];
-                kn[0] = g[0] * (-cS - mu) + g[1] * cS + dx0 * invN;
-                kn[1] = g[1] * (-(sgm + mu)) + g[2] * sgm + g[6] * sgm;
-                kn[2] = g[2] * (-(gm + mu)) + g[3] * gm + g[5] * dd * gm + dx1;
-                kn[3] = g[3] * (-mu);
-                kn[4] = g[0] * (-cN) + g[1] * cN + g[4] * (-mu) - dx0 * S * invN * invN - dx2 * Dd * invN * invN;
-                kn[5] = g[5] * (-lm) + dx2 * invN;
-                kn[6] = 0.0f;
-                switch (stage) {
-#define B200UDE_SEIR_SETKL(I) case I: _Pragma("unroll") for (int cc = 0; cc < D; ++cc) kl[I][cc] = kn[cc]; break;
-                    B200UDE_SEIR_SETKL(0)
-                    B200UDE_SEIR_SETKL(1)
-                    B200UDE_SEIR_SETKL(2)
-                    B200UDE_SEIR_SETKL(3)
-                    B200UDE_SEIR_SETKL(4)
-                default:
-#pragma unroll
-                    for (int cc = 0; cc < D; ++cc) kl[5][cc] = kn[cc];
-#undef B200UDE_SEIR_SETKL
-                }
-            }
-            group_sync(c.bar_id);
-            // column pass B: dW1[j][m] += sum_t q1[t][j] x[t][m];  db1[j] += sum_t q1[t][j]
-#pragma unroll 8
-            for (int t = tlo; t < tlo + 64; ++t) {
-                const float qq = st->B1[t * SLD64 + jc];
-                const float4 u4 = *reinterpret_cast<const float4 *>(&st->U[t * 4]);
-                a_w10 = fmaf(qq, u4.x, a_w10);
-                a_w11 = fmaf(qq, u4.y, a_w11);
-                a_w12 = fmaf(qq, u4.z, a_w12);
-                a_b1 += qq;
-            }
+            float kn[D];
+            eval_core(stage, u, g, sc, isc, lv, kn);
+            B200UDE_SEIR_SETKL_ALL()
         }
 #pragma unroll
         for (int cc = 0; cc < D; ++cc) {
@@ -536,6 +724,97 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p)
         }
         if (s % p.save_every == 0) loss_jump<D>(p, s / p.save_every, n, N, lam, loss);
     }
+    } else {
+    // ---- adaptive: replay the accepted forward steps backwards, split at the save times (see lv32_tc.cuh); CTA-uniform loops ----
+    __shared__ int s_nmax;
+    if (threadIdx.x == 0) s_nmax = 0;
+    __syncthreads();
+    const int nacc = ag.nacc[n];
+    atomicMax(&s_nmax, live ? nacc : 0);
+    __syncthreads();
+    const int nmax = s_nmax;
+    int isave = ag.n_save - 1;
+    auto jump = [&](int is) {
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) lam[cc] += __ldg(p.cot + ((size_t)is * D + cc) * N + n);
+    };
+    if (live) jump(isave);
+    --isave;
+#pragma unroll 1
+    for (int s = nmax - 1; s >= 0; --s) {
+        const bool act_s = live && s < nacc;
+        const int sc_ = act_s ? s : 0;
+        const float tn = ag.tgrid[(size_t)sc_ * N + n], tn1 = ag.tgrid[(size_t)(sc_ + 1) * N + n], hn = tn1 - tn;
+        const float eps = 1e-5f * hn, inv_hn = 1.0f / hn;
+        float cur = tn1;
+#pragma unroll 1
+        while (true) {
+            const bool has = act_s && cur > tn + eps;
+            if (!__syncthreads_or(has ? 1 : 0)) break;
+            float ta = tn;
+            const float ts = ag.t0 + ag.save_dt * (float)isave;
+            if (has && isave >= 0 && ts > tn + eps) ta = ts;
+            const float h = has ? cur - ta : 0.0f;
+            const float lvm = has ? 1.0f : 0.0f, inv_h = has ? 1.0f / h : 0.0f;
+            float kl[6][D];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+#pragma unroll
+                for (int cc = 0; cc < D; ++cc) kl[j][cc] = 0.0f;
+#pragma unroll 1
+            for (int stage = 0; stage < 6; ++stage) {
+                float u[D], g[D], sc, isc, ci;
+#define B200UDE_SEIR_PRE(I)                                        \
+    case I: {                                                      \
+        stage_arg<D, I>(lam, kl, h, g);                            \
+        sc = h * (float)Tsit5::b(I);                               \
+        isc = inv_h * (float)(1.0 / Tsit5::b(I));                  \
+        ci = (float)Tsit5::c(I);                                   \
+    } break;
+                switch (stage) {
+                    B200UDE_SEIR_PRE(0)
+                    B200UDE_SEIR_PRE(1)
+                    B200UDE_SEIR_PRE(2)
+                    B200UDE_SEIR_PRE(3)
+                    B200UDE_SEIR_PRE(4)
+                default:
+                    B200UDE_SEIR_PRE(5)
+                }
+#undef B200UDE_SEIR_PRE
+                {
+                    const float Th = fminf(fmaxf((cur - ci * h - tn) * inv_hn, 0.0f), 1.0f);
+                    float bw[7];
+                    lv32::tc::tsit5_weights(Th, bw);
+#pragma unroll
+                    for (int cc = 0; cc < D; ++cc) {
+                        float acc2 = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) acc2 = fmaf(bw[j], __ldg(p.dense + ((size_t)(sc_ * 6 + j) * D + cc) * N + n), acc2);
+                        u[cc] = fmaf(hn, acc2, __ldg(p.ustep + ((size_t)sc_ * D + cc) * N + n));
+                    }
+                }
+                float kn[D];
+                eval_core(stage, u, g, sc, isc, lvm, kn);
+                B200UDE_SEIR_SETKL_ALL()
+            }
+            if (has) {
+#pragma unroll
+                for (int cc = 0; cc < D; ++cc) {
+                    float a = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) a = fmaf((float)Tsit5::b(j), kl[j][cc], a);
+                    lam[cc] = fmaf(h, a, lam[cc]);
+                }
+                cur = ta;
+                if (isave >= 0 && fabsf(ts - ta) <= eps) { jump(isave); --isave; }
+            }
+        }
+    }
+    if constexpr (GEMM == 1) {
+        if (first_flush) lv32::tc::tmem_flush32(sum_taddr, macc, true);   // no accepted step at all: the sums are zero
+    }
+    }
+#undef B200UDE_SEIR_SETKL_ALL
     if (p.grad_u0 && live) {
 #pragma unroll
         for (int cc = 0; cc < D; ++cc) p.grad_u0[(size_t)cc * N + n] = lam[cc];
