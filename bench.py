@@ -244,13 +244,13 @@ def main():
     u0_h = torch.from_numpy(u0).pin_memory()
     y_h = torch.from_numpy(y).pin_memory()
     g_h = torch.empty(P).pin_memory()
-    for _ in range(2):
+    for _ in range(4):
         solver.loss_gradient_host(th_h, u0_h, y_h, grad_theta=g_h)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    e2e_steps = max(3, a.steps // 2)
+    e2e_steps = max(5, a.steps)
     for _ in range(e2e_steps):
         l_h, _, _ = solver.loss_gradient_host(th_h, u0_h, y_h, grad_theta=g_h)
         if world > 1:

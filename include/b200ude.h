@@ -71,7 +71,10 @@ extern "C" {
 #define B200UDE_VERN7 1
 
 /* sensealg */
-#define B200UDE_INTERPOLATING_ADJOINT 0
+#define B200UDE_INTERPOLATING_ADJOINT 0 /* InterpolatingAdjoint(autojacvec = ReverseDiffVJP())  seir_exposure.jl:71,140 */
+#define B200UDE_DISCRETE_ADJOINT 1      /* exact gradient of the discrete fixed-step scheme by reverse accumulation through the
+                                           stages: the quantity ForwardDiffSensitivity() computes in forward mode
+                                           (scenario_1.jl:86, scenario_2.jl:108, hudson_bay.jl:102); LV chains, Tsit5 fixed step */
 
 /* memory space of a pointer argument */
 #define B200UDE_HOST 0
@@ -111,7 +114,7 @@ typedef struct b200ude_desc {
     int32_t n_consts;
     double consts[16];    /* fixed physics constants */
     int32_t solver;       /* B200UDE_TSIT5 | B200UDE_VERN7 */
-    int32_t sensealg;     /* B200UDE_INTERPOLATING_ADJOINT */
+    int32_t sensealg;     /* B200UDE_INTERPOLATING_ADJOINT | B200UDE_DISCRETE_ADJOINT */
     double t0;            /* tspan[1] */
     double dt;            /* fixed step (adaptive = false); saveat = t0 + i*save_every*dt */
     int32_t n_steps;      /* number of steps; tspan[2] = t0 + n_steps*dt */

@@ -167,6 +167,33 @@ def adjoint_fixed(m, theta, out, dense, dt, n_steps, dLdout, save_every=1):
     return g, gu
 
 
+def adjoint_discrete(m, theta, out, dense, dt, n_steps, dLdout, save_every=1):
+    """Exact gradient of the discrete fixed-step Tsit5 scheme (ForwardDiffSensitivity's result): grad_theta[P], grad_u0[d]."""
+    suf, ct = _dt(theta.dtype)
+    g = np.zeros(num_params(m), dtype=theta.dtype)
+    gu = np.empty(m.d, dtype=theta.dtype)
+    getattr(lib(), "ude_adjoint_discrete_fixed" + suf)(C.byref(m), _p(np.ascontiguousarray(theta)), _p(np.ascontiguousarray(out)),
+                                                       _p(np.ascontiguousarray(dense)), ct(dt), n_steps, save_every,
+                                                       _p(np.ascontiguousarray(dLdout, dtype=theta.dtype)), _p(g), _p(gu))
+    return g, gu
+
+
+def ensemble_loss_grad_discrete(m, theta, u0, y, wmask, dt, n_steps, save_every=1):
+    """Like ensemble_loss_grad with the discrete adjoint (python loop over trajectories; small N only)."""
+    N = u0.shape[1]
+    g = np.zeros(num_params(m), dtype=theta.dtype)
+    gu = np.zeros((m.d, N), dtype=theta.dtype)
+    loss = 0.0
+    for k in range(N):
+        out, dense = solve_fixed(m, theta, u0[:, k].astype(theta.dtype), dt, n_steps, save_every=save_every, want_dense=True)
+        r = (out - y[:, :, k]) * np.asarray(wmask)[None, :]
+        loss += float((np.asarray(wmask)[None, :] * (out - y[:, :, k]) ** 2).sum())
+        gk, guk = adjoint_discrete(m, theta, out, dense, dt, n_steps, 2 * r, save_every=save_every)
+        g += gk
+        gu[:, k] = guk
+    return loss, g, gu
+
+
 def ensemble_loss_grad(m, theta, u0, y, wmask, dt, n_steps, save_every=1, n_threads=None, want_out=False, want_gu0=True):
     """u0[d, N], y[n_save, d, N] -> loss, grad_theta[P], grad_u0[d, N] (, out[n_save, d, N])."""
     suf, ct = _dt(theta.dtype)

@@ -97,6 +97,11 @@ int ude_solve_adaptive_f64(const ude_model *m, const double *theta, const double
 void ude_adjoint_fixed_f64(const ude_model *m, const double *theta, const double *out,
                            const double *dense, double dt, int n_steps, int save_every,
                            const double *dLdout, double *grad_theta, double *grad_u0);
+/* exact gradient of the discrete fixed-step Tsit5 scheme by reverse accumulation through the stages (what
+ * ForwardDiffSensitivity, scenario_1.jl:86, computes in forward mode); same arguments as ude_adjoint_fixed */
+void ude_adjoint_discrete_fixed_f64(const ude_model *m, const double *theta, const double *out,
+                                    const double *dense, double dt, int n_steps, int save_every,
+                                    const double *dLdout, double *grad_theta, double *grad_u0);
 /* ensemble loss + gradient, trajectory-fastest layouts: u0[d][N], y[n_save][d][N], wmask[d]
  * L = sum_n sum_i sum_k wmask[k] (u_k(t_i) - y)^2.  out (optional) [n_save][d][N].
  * grad_theta[P] (set), grad_u0 (optional) [d][N].  OpenMP over trajectories. */
@@ -118,6 +123,9 @@ int ude_solve_adaptive_f32(const ude_model *m, const float *theta, const float *
 void ude_adjoint_fixed_f32(const ude_model *m, const float *theta, const float *out,
                            const float *dense, float dt, int n_steps, int save_every,
                            const float *dLdout, float *grad_theta, float *grad_u0);
+void ude_adjoint_discrete_fixed_f32(const ude_model *m, const float *theta, const float *out,
+                                    const float *dense, float dt, int n_steps, int save_every,
+                                    const float *dLdout, float *grad_theta, float *grad_u0);
 double ude_ensemble_loss_grad_f32(const ude_model *m, const float *theta, const float *u0,
                                   const float *y, const float *wmask, size_t N, float dt,
                                   int n_steps, int save_every, float *out, float *grad_theta,

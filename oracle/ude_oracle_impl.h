@@ -431,6 +431,63 @@ int FN(ude_solve_adaptive)(const ude_model *m, const REAL *th, const REAL *u0, c
     return isave == n_save ? nacc : -1;
 }
 
+/* ------------------------------------------------ discrete adjoint ---------- */
+/* Exact gradient of the DISCRETE fixed-step Tsit5 scheme (what ForwardDiffSensitivity, scenario_1.jl:86 /
+ * scenario_2.jl:108 / hudson_bay.jl:102, computes in forward mode -- here by reverse accumulation through the
+ * stages): with g_i = u_n + dt sum_{j<i} a_ij k_j, k_i = f(g_i), u_{n+1} = u_n + dt sum_{i<=6} b_i k_i,
+ *   kbar_i = dt (b_i ubar_{n+1} + sum_{j>i} a_ji gbar_j),  gbar_i = J_u(g_i)^T kbar_i,
+ *   ubar_n = ubar_{n+1} + sum_i gbar_i,  grad_theta += J_theta(g_i)^T kbar_i.
+ * k_7 (FSAL) has weight 0 in the update and is the next step's k_1 = f(u_{n+1}), which that step accounts for. */
+void FN(ude_adjoint_discrete_fixed)(const ude_model *m, const REAL *th, const REAL *out, const REAL *dense,
+                                    REAL dt, int n_steps, int save_every, const REAL *dLdout,
+                                    REAL *grad_theta, REAL *grad_u0)
+{
+    const ude_tableau *tb = ude_get_tableau(UDE_TSIT5);
+    const int d = m->d, s = 7;
+    REAL lam[UDE_MAX_STATE], kb[UDE_MAX_STATE], x[UDE_MAX_STATE];
+    REAL gb[6 * UDE_MAX_STATE];
+    const int n_save = n_steps / save_every + 1;
+    for (int k = 0; k < d; ++k) lam[k] = dLdout[(size_t)(n_save - 1) * d + k];
+    REAL *ustart = (REAL *)malloc(sizeof(REAL) * (size_t)(n_steps + 1) * d);
+    for (int k = 0; k < d; ++k) ustart[k] = out[k];
+    for (int n = 0; n < n_steps; ++n) {
+        const REAL *ks = dense + (size_t)n * s * d;
+        if ((n + 1) % save_every == 0) {
+            for (int k = 0; k < d; ++k) ustart[(size_t)(n + 1) * d + k] = out[(size_t)((n + 1) / save_every) * d + k];
+        } else {
+            for (int k = 0; k < d; ++k) {
+                REAL acc = 0;
+                for (int j = 0; j < 6; ++j) acc += (REAL)tb->A[6][j] * ks[(size_t)j * d + k];
+                ustart[(size_t)(n + 1) * d + k] = ustart[(size_t)n * d + k] + dt * acc;
+            }
+        }
+    }
+    for (int n = n_steps - 1; n >= 0; --n) {
+        const REAL *ks = dense + (size_t)n * s * d;
+        const REAL *u_n = ustart + (size_t)n * d;
+        for (int i = 5; i >= 0; --i) {
+            for (int k = 0; k < d; ++k) {
+                REAL acc = 0;
+                for (int j = 0; j < i; ++j) acc += (REAL)tb->A[i][j] * ks[(size_t)j * d + k];
+                x[k] = u_n[k] + dt * acc;
+                REAL c = (REAL)tb->A[6][i] * lam[k];
+                for (int j = i + 1; j < 6; ++j) c += (REAL)tb->A[j][i] * gb[(size_t)j * d + k];
+                kb[k] = dt * c;
+            }
+            FN(ude_rhs_vjp)(m, th, x, kb, gb + (size_t)i * d, grad_theta, (REAL)1);
+        }
+        for (int k = 0; k < d; ++k) {
+            REAL acc = lam[k];
+            for (int i = 0; i < 6; ++i) acc += gb[(size_t)i * d + k];
+            lam[k] = acc;
+        }
+        if (n % save_every == 0)
+            for (int k = 0; k < d; ++k) lam[k] += dLdout[(size_t)(n / save_every) * d + k];
+    }
+    for (int k = 0; k < d; ++k) grad_u0[k] = lam[k];
+    free(ustart);
+}
+
 /* ------------------------------------------------ interpolating adjoint ---- */
 /* InterpolatingAdjoint (seir_exposure.jl:71,140; Fisher-KPP-CNN.jl:136): the
  * augmented state [lambda; mu] is integrated from T back to t0 with the same

@@ -685,3 +685,51 @@ def test_peer_allreduce_single_rank_equals_plain_reduce():
         assert torch.equal(L0, L1) and torch.equal(g0, g1)
     pa.close()
     solver.close()
+
+
+@pytest.mark.parametrize("shape", ["lv32", "lv5", "lv5p2"])
+def test_discrete_adjoint_forwarddiff_sensitivity_vs_oracle(O, shape):
+    """sensealg = ForwardDiffSensitivity() (scenario_1.jl:86, hudson_bay.jl:102): the exact gradient of the discrete
+    fixed-step Tsit5 scheme, computed by reverse accumulation through the stages (B200UDE_DISCRETE_ADJOINT), against the
+    oracle's discrete adjoint (= torch autograd through the scheme to 1e-11, tests/test_oracle_golden.py) and, as a
+    kernel-only check, against central finite differences of the GPU loss along a random direction."""
+    ude = _ude()
+    rng = np.random.default_rng(11)
+    N = 200
+    u0, y = synthetic_ensemble(N)
+    if shape == "lv32":
+        f, widths, acts, pre = _lv32(ude), (2, 32, 32, 2), ("tanh", "tanh", "identity"), 0
+        theta = glorot_theta(widths, seed=1)
+    else:
+        rates = 2 if shape == "lv5p2" else 0
+        f, widths, acts, pre = _lv5(ude, ("rbf", "rbf", "tanh"), rates), (2, 5, 5, 5, 2), ("rbf", "rbf", "tanh", "identity"), rates
+        theta = np.concatenate([[1.3, 1.8][:rates], glorot_theta(widths, seed=2)]).astype(np.float32)
+    m = O.lv_model(widths, acts, n_prefix=pre) if shape != "lv32" else O.lv_model()
+    solver = ude.UDESolver(f, 0.0, 0.1, 30, 1, max_trajectories=N, sensealg=ude.ForwardDiffSensitivity())
+    out, loss, g, gu, status = _run(solver, theta, u0, y)
+    l64, g64, gu64 = O.ensemble_loss_grad_discrete(m, theta.astype(np.float64), u0.astype(np.float64), y.astype(np.float64), np.ones(2), 0.1, 30)
+    assert (status == 0).all()
+    assert abs(loss - l64) <= 1e-4 * abs(l64)
+    assert np.linalg.norm(g - g64) <= 2e-4 * np.linalg.norm(g64)
+    assert np.abs(gu - gu64).max() <= 2e-4 * np.abs(gu64).max()
+    # the interpolating (continuous) adjoint differs from it by the truncation error only
+    s2 = ude.UDESolver(f, 0.0, 0.1, 30, 1, max_trajectories=N)
+    _, _, gc, _, _ = _run(s2, theta, u0, y)
+    assert 0 < np.linalg.norm(gc - g) <= 1e-3 * np.linalg.norm(g)
+    # directional finite difference of the GPU loss itself (fp32: large step, loose tolerance)
+    v = rng.standard_normal(theta.size).astype(np.float32)
+    v /= np.linalg.norm(v)
+    eps = 2e-2
+    lp = _run(solver, theta + eps * v, u0, y)[1]
+    lm = _run(solver, theta - eps * v, u0, y)[1]
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - float(g @ v)) <= 2e-2 * abs(fd) + 1e-3 * np.linalg.norm(g)
+    solver.close(); s2.close()
+
+
+def test_discrete_adjoint_unsupported_configurations_fail_loudly():
+    ude = _ude()
+    from universal_differential_equations_b200._lib import B200UDEError, EUNSUPPORTED
+    with pytest.raises(B200UDEError) as e:
+        ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=4, sensealg=ude.ForwardDiffSensitivity(), adaptive=True, abstol=1e-6, reltol=1e-6)
+    assert e.value.code == EUNSUPPORTED

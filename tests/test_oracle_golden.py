@@ -197,6 +197,12 @@ def test_interpolating_adjoint_vs_autograd_through_the_scheme(O):
     assert abs(float(loss) - l) < 1e-10 * l
     assert np.linalg.norm(th.grad.numpy() - g) < 1e-6 * np.linalg.norm(g)
     assert np.abs(U0.grad.numpy() - gu).max() < 1e-6 * np.abs(gu).max()
+    # the oracle's DISCRETE adjoint (reverse accumulation through the stages = ForwardDiffSensitivity's result,
+    # scenario_1.jl:86) is the same quantity as autograd through the scheme: equal to round-off
+    ld, gd, gud = O.ensemble_loss_grad_discrete(m, theta, u0.astype(np.float64), y.astype(np.float64), np.ones(2), 0.1, 30)
+    assert abs(ld - float(loss)) < 1e-12 * ld
+    assert np.linalg.norm(th.grad.numpy() - gd) < 1e-11 * np.linalg.norm(gd)
+    assert np.abs(U0.grad.numpy() - gud).max() < 1e-11 * np.abs(gud).max()
 
 
 def test_fp32_oracle_close_to_fp64(O):

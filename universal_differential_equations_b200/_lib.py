@@ -18,7 +18,7 @@ F32, F64 = 0, 1
 MODEL_LV, MODEL_SEIR, MODEL_FKPP, MODEL_NODE = 0, 1, 2, 3
 ACT_IDENTITY, ACT_TANH, ACT_RBF = 0, 1, 2
 TSIT5, VERN7 = 0, 1
-INTERPOLATING_ADJOINT = 0
+INTERPOLATING_ADJOINT, DISCRETE_ADJOINT = 0, 1
 HOST, DEVICE = 0, 1
 FLAG_APPROX_TANH = 1
 OK, EINVAL, EUNSUPPORTED, ESTATE, ENOMEM, ENODEVICE = 0, -1, -2, -3, -4, -5

@@ -381,7 +381,8 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     if (d->dtype != B200UDE_F32) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only B200UDE_F32 kernels exist in this build");
     if (d->n_layers < 1 || d->n_layers > B200UDE_MAX_LAYERS) return fail(nullptr, B200UDE_EINVAL, "create: n_layers=%d out of range", d->n_layers);
     if (d->solver != B200UDE_TSIT5 && d->solver != B200UDE_VERN7) return fail(nullptr, B200UDE_EINVAL, "create: unknown solver %d", d->solver);
-    if (d->sensealg != B200UDE_INTERPOLATING_ADJOINT) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: unknown sensealg %d", d->sensealg);
+    if (d->sensealg != B200UDE_INTERPOLATING_ADJOINT && d->sensealg != B200UDE_DISCRETE_ADJOINT)
+        return fail(nullptr, B200UDE_EUNSUPPORTED, "create: unknown sensealg %d", d->sensealg);
     if (!(d->dt > 0) || d->n_steps < 1 || d->save_every < 1 || d->n_steps % d->save_every != 0)
         return fail(nullptr, B200UDE_EINVAL, "create: need dt>0, n_steps>=1, save_every>=1 dividing n_steps");
     if (d->max_trajectories == 0 || d->max_trajectories > (1ull << 26)) return fail(nullptr, B200UDE_EINVAL, "create: max_trajectories out of range");
@@ -400,6 +401,10 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         // adaptive solves run on the runtime-shape kernels, except the headline chain (tensor-core kernels with CTA-uniform attempt loops)
         if (!((kid == K_LV32 || kid == K_SEIR64) && d->solver == B200UDE_TSIT5 && env_int("B200UDE_ADAPTIVE_TC", 1))) kid = K_GENERIC;
     }
+    if (d->sensealg == B200UDE_DISCRETE_ADJOINT &&
+        (d->adaptive || d->solver != B200UDE_TSIT5 || !(kid == K_LV32 || kid == K_LV5P0 || kid == K_LV5P1 || kid == K_LV5P2)))
+        return fail(nullptr, B200UDE_EUNSUPPORTED,
+                    "create: the discrete adjoint has kernels for fixed-step Tsit5 on the LV chains 2-32-32-2 and 2-5-5-5-2 (the scripts that use ForwardDiffSensitivity)");
     if (kid == K_NONE)
         return fail(nullptr, B200UDE_EUNSUPPORTED,
                     "create: no sm_100a kernel for this model/chain (built: LV 2-32-32-2 tanh; LV 2-5-5-5-2; generic LV/SEIR/NODE chains with widths <= 64, <= 5 layers)");
@@ -436,6 +441,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         if (P > 8192) { delete h; return fail(nullptr, B200UDE_EUNSUPPORTED, "create: %d parameters exceed the constant-bank budget", P); }
     }
     h->var.approx_tanh = (d->flags & B200UDE_FLAG_APPROX_TANH) ? 1 : 0;
+    h->var.discrete = d->sensealg == B200UDE_DISCRETE_ADJOINT ? 1 : 0;
     // tuning knobs for experiments (defaults are the measured-best variant)
     h->var.fwd_smem = env_int("B200UDE_FWD_SMEM", 0);
     h->var.fwd_T = env_int("B200UDE_FWD_T", 1) == 2 ? 2 : 1;

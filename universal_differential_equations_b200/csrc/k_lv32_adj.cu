@@ -26,10 +26,10 @@ static cudaError_t launch_one(const AdjParams &p, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int TM, int GEMM>
+template <int TM, int GEMM, bool DISC = false>
 static cudaError_t launch_tc(const AdjParams &p, int *rows_out, cudaStream_t st)
 {
-    auto kern = lv32::tc::adjoint_kernel<TM, 128, 4, GEMM>;
+    auto kern = lv32::tc::adjoint_kernel<TM, 128, 4, GEMM, false, DISC>;
     constexpr size_t smem = sizeof(lv32::tc::WarpStageT) * 4;
     static bool attr_set = false;
     if (!attr_set) {
@@ -76,6 +76,7 @@ cudaError_t launch_adj_lv32(const Variant &v, const ConstTables &t, const AdjPar
 {
     cudaError_t e = upload_tables(t, st);
     if (e != cudaSuccess) return e;
+    if (v.discrete) return v.approx_tanh ? launch_tc<1, 1, true>(p, grid_out, st) : launch_tc<0, 1, true>(p, grid_out, st);
     if (v.adj_tc == 2) return v.approx_tanh ? launch_tc<1, 1>(p, grid_out, st) : launch_tc<0, 1>(p, grid_out, st);
     if (v.adj_tc) return v.approx_tanh ? launch_tc<1, 0>(p, grid_out, st) : launch_tc<0, 0>(p, grid_out, st);
     const int grid = ((p.N + 1) / 2 + ADJ_BLOCK_GEMM - 1) / ADJ_BLOCK_GEMM;

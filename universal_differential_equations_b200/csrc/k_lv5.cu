@@ -23,25 +23,32 @@ cudaError_t launch_fwd_lv5(int n_prefix, const Variant &, const ConstTables &t, 
     }
 }
 
-template <int NP>
+template <int NP, bool DISC>
 static cudaError_t launch_one(const AdjParams &p, int grid, cudaStream_t st)
 {
-    auto kern = ude_adjoint_lane_kernel<CfgLV5<NP>, 0, WConst, ADJ_BLOCK_LANE, 1>;
+    auto kern = ude_adjoint_lane_kernel<CfgLV5<NP>, 0, WConst, ADJ_BLOCK_LANE, 1, DISC>;
     const size_t smem = sizeof(float) * (CfgLV5<NP>::P + 1);
     kern<<<grid, ADJ_BLOCK_LANE, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_adj_lv5(int n_prefix, const Variant &, const ConstTables &t, const AdjParams &p, cudaStream_t st, int *grid_out)
+cudaError_t launch_adj_lv5(int n_prefix, const Variant &v, const ConstTables &t, const AdjParams &p, cudaStream_t st, int *grid_out)
 {
     cudaError_t e = upload_tables(t, st);
     if (e != cudaSuccess) return e;
     const int grid = adj_grid_lv5(p.N);
     *grid_out = grid;
+    if (v.discrete) {   // exact gradient of the discrete scheme (ForwardDiffSensitivity's result)
+        switch (n_prefix) {
+        case 0: return launch_one<0, true>(p, grid, st);
+        case 1: return launch_one<1, true>(p, grid, st);
+        default: return launch_one<2, true>(p, grid, st);
+        }
+    }
     switch (n_prefix) {
-    case 0: return launch_one<0>(p, grid, st);
-    case 1: return launch_one<1>(p, grid, st);
-    default: return launch_one<2>(p, grid, st);
+    case 0: return launch_one<0, false>(p, grid, st);
+    case 1: return launch_one<1, false>(p, grid, st);
+    default: return launch_one<2, false>(p, grid, st);
     }
 }
 

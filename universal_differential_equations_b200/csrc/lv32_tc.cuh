@@ -535,7 +535,8 @@ __device__ __forceinline__ void tmem_flush32(uint32_t taddr, float (&m)[32], boo
 // GEMM = 1: the same product as 3xTF32 warp-level mma.sync.m16n8k8 (M = j, N = i, K = the warp's 32 trajectories):
 //           fragments are read straight from the staged rows; the contraction index inside a k-step is permuted
 //           (k = tig -> t = 2 tig, k = tig + 4 -> t = 2 tig + 1) so that every fragment load is bank-conflict free.
-template <int TM, int BLOCK, int MINB, int GEMM, bool ADAPT = false>
+// DISC: discrete adjoint (exact gradient of the fixed-step scheme, ude_adjoint.cuh) instead of the interpolating adjoint.
+template <int TM, int BLOCK, int MINB, int GEMM, bool ADAPT = false, bool DISC = false>
 __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p, AdaptiveGrid ag)
 {
     static_assert(BLOCK == 128, "one TMEM lane per thread: 128 trajectories per CTA");
@@ -726,14 +727,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p, Adapt
 #pragma unroll
         for (int j = 0; j < 6; ++j) { kl[j][0] = 0.f; kl[j][1] = 0.f; }
 #pragma unroll 1
-        for (int stage = 0; stage < 6; ++stage) {
+        for (int it6 = 0; it6 < 6; ++it6) {
+            const int stage = DISC ? 5 - it6 : it6;   // the discrete adjoint walks the forward stages backwards
             float x[2], g[2], sc, isc;
 #define B200UDE_TC_STAGE_PRE(I)                                    \
     case I: {                                                      \
-        interp_state<2, I>(p, s, n, N, dt, x);                     \
-        stage_arg<2, I>(lam, kl, dt, g);                           \
-        sc = dt * (float)Tsit5::b(I);                              \
-        isc = inv_dt * (float)(1.0 / Tsit5::b(I));                 \
+        if constexpr (DISC) {                                      \
+            fwd_stage_state<2, I>(p, s, n, N, dt, x);              \
+            disc_stage_cot<2, I>(lam, kl, dt, g);                  \
+            sc = 1.0f;                                             \
+            isc = 1.0f;                                            \
+        } else {                                                   \
+            interp_state<2, I>(p, s, n, N, dt, x);                 \
+            stage_arg<2, I>(lam, kl, dt, g);                       \
+            sc = dt * (float)Tsit5::b(I);                          \
+            isc = inv_dt * (float)(1.0 / Tsit5::b(I));             \
+        }                                                          \
     } break;
             switch (stage) {
                 B200UDE_TC_STAGE_PRE(0)
@@ -758,10 +767,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p, Adapt
         }
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-            float a = 0.0f;
+            if constexpr (DISC) {
+                float a = lam[cc];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) a = fmaf((float)Tsit5::b(j), kl[j][cc], a);
-            lam[cc] = fmaf(dt, a, lam[cc]);
+                for (int j = 0; j < 6; ++j) a += kl[j][cc];
+                lam[cc] = a;
+            } else {
+                float a = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) a = fmaf((float)Tsit5::b(j), kl[j][cc], a);
+                lam[cc] = fmaf(dt, a, lam[cc]);
+            }
         }
         if (s % p.save_every == 0) loss_jump<2>(p, s / p.save_every, n, N, lam, loss);
         if constexpr (GEMM == 1) { tmem_flush32(c.tmem + 96 + c.lane_base, macc, first_flush); first_flush = false; }   // per step: 72-MMA chains

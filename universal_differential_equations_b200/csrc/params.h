@@ -44,7 +44,8 @@ struct Variant {
     int adj_smem = 0;
     int approx_tanh = 0;
     int fwd_tc = 0;      // 1: tcgen05 (3xTF32) forward kernel
-    int adj_tc = 0;      // 1: tcgen05 (3xTF32) adjoint kernel
+    int adj_tc = 0;      // 1: tcgen05 (3xTF32) adjoint kernel, FFMA2 gradient GEMM; 2: mma.sync gradient GEMM
+    int discrete = 0;    // 1: discrete adjoint (exact gradient of the fixed-step scheme) instead of the interpolating adjoint
 };
 
 constexpr int FWD_BLOCK = 128;      // small-chain forward kernels

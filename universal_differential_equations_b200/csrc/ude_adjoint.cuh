@@ -48,6 +48,35 @@ __device__ __forceinline__ void stage_arg(const float (&lam)[D], const float (&k
     }
 }
 
+// ---- discrete adjoint (exact gradient of the fixed-step Tsit5 scheme; what ForwardDiffSensitivity computes,
+// scenario_1.jl:86): stage argument g_i = u_n + dt sum_{j<i} a_ij k_j from the stored step start and stage derivatives ...
+template <int D, int I>
+__device__ __forceinline__ void fwd_stage_state(const AdjParams &p, int s, size_t n, size_t N, float dt, float (&x)[D])
+{
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < I; ++j)
+            if (Tsit5::a(I, j) != 0.0)
+                acc = fmaf((float)Tsit5::a(I, j), __ldg(p.dense + ((size_t)(s * 6 + j) * D + c) * N + n), acc);
+        x[c] = fmaf(dt, acc, __ldg(p.ustep + ((size_t)s * D + c) * N + n));
+    }
+}
+// ... and the cotangent of k_i: kbar_i = dt (b_i ubar_{n+1} + sum_{j>i} a_ji gbar_j), gbar_j = J_u(g_j)^T kbar_j of the later stages
+template <int D, int I>
+__device__ __forceinline__ void disc_stage_cot(const float (&lam)[D], const float (&gb)[6][D], float dt, float (&kb)[D])
+{
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        float acc = (float)Tsit5::b(I) * lam[c];
+#pragma unroll
+        for (int j = I + 1; j < 6; ++j)
+            if (Tsit5::a(j, I) != 0.0) acc = fmaf((float)Tsit5::a(j, I), gb[j][c], acc);
+        kb[c] = dt * acc;
+    }
+}
+
 // lambda += dL/du(t_isave); with fused_l2 also accumulates the loss
 template <int D>
 __device__ __forceinline__ void loss_jump(const AdjParams &p, int isave, size_t n, size_t N, float (&lam)[D], float &loss)
@@ -71,7 +100,7 @@ __device__ __forceinline__ void loss_jump(const AdjParams &p, int isave, size_t 
 // =====================================================================================================
 // small chains: per-lane register accumulators
 // =====================================================================================================
-template <class C, int TM, class W, int BLOCK, int MINB>
+template <class C, int TM, class W, int BLOCK, int MINB, bool DISC = false>
 __global__ void __launch_bounds__(BLOCK, MINB) ude_adjoint_lane_kernel(AdjParams p)
 {
     static_assert(C::MODEL == MODEL_LV, "only the LV family has a kernel in this build");
@@ -197,6 +226,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) ude_adjoint_lane_kernel(AdjParams
         stage_arg<D, I>(lam, kl, dt, g);                        \
         stage_eval(dt * (float)Tsit5::b(I), x, g, kl[I]);       \
     }
+#define B200UDE_LANE_DSTAGE(I)                                  \
+    {                                                           \
+        float x[DIN], kb[D];                                    \
+        fwd_stage_state<D, I>(p, s, n, N, dt, x);               \
+        disc_stage_cot<D, I>(lam, kl, dt, kb);                  \
+        stage_eval(1.0f, x, kb, kl[I]);                         \
+    }
+        if constexpr (DISC) {
+            // reverse accumulation through the forward stages 6..1 of step s; kl[i] holds gbar_i = J_u(g_i)^T kbar_i
+            B200UDE_LANE_DSTAGE(5)
+            B200UDE_LANE_DSTAGE(4)
+            B200UDE_LANE_DSTAGE(3)
+            B200UDE_LANE_DSTAGE(2)
+            B200UDE_LANE_DSTAGE(1)
+            B200UDE_LANE_DSTAGE(0)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                float acc = lam[c];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc += kl[j][c];
+                lam[c] = acc;
+            }
+        } else {
         // k_7 of the backward step only feeds FSAL / error estimation: not needed
         B200UDE_LANE_STAGE(0)
         B200UDE_LANE_STAGE(1)
@@ -204,7 +256,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) ude_adjoint_lane_kernel(AdjParams
         B200UDE_LANE_STAGE(3)
         B200UDE_LANE_STAGE(4)
         B200UDE_LANE_STAGE(5)
-#undef B200UDE_LANE_STAGE
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             float acc = 0.0f;
@@ -212,6 +263,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) ude_adjoint_lane_kernel(AdjParams
             for (int j = 0; j < 6; ++j) acc = fmaf((float)Tsit5::b(j), kl[j][c], acc);
             lam[c] = fmaf(dt, acc, lam[c]);
         }
+        }
+#undef B200UDE_LANE_STAGE
+#undef B200UDE_LANE_DSTAGE
         if (s % p.save_every == 0) loss_jump<D>(p, s / p.save_every, n, N, lam, loss);
     }
     if (p.grad_u0 && live) {

@@ -223,7 +223,11 @@ class InterpolatingAdjoint:
 
 
 class ForwardDiffSensitivity:
-    """Named by the LV scripts (scenario_1.jl:86); not provided by this path."""
+    """ForwardDiffSensitivity() of the LV scripts (scenario_1.jl:86, scenario_2.jl:108, hudson_bay.jl:102): the exact
+    derivative of the discrete solver scheme.  The reference pushes dual numbers through the solver (cost O(P) forward
+    solves); here the same quantity comes from reverse accumulation through the Tsit5 stages (one backward sweep,
+    B200UDE_DISCRETE_ADJOINT).  Fixed-step Tsit5 on the LV chains."""
+    code = _lib.DISCRETE_ADJOINT
 
 
 # --------------------------------------------------------------------------- engine
@@ -239,9 +243,7 @@ class UDESolver:
                  max_steps=512):
         alg = alg or Tsit5()
         sensealg = sensealg or InterpolatingAdjoint()
-        if isinstance(sensealg, ForwardDiffSensitivity):
-            raise NotImplementedError("ForwardDiffSensitivity is not part of the B200 path; use InterpolatingAdjoint()")
-        if not isinstance(sensealg, InterpolatingAdjoint):
+        if not isinstance(sensealg, (InterpolatingAdjoint, ForwardDiffSensitivity)):
             raise TypeError(f"unsupported sensealg {sensealg!r}")
         if not torch.cuda.is_available():
             raise RuntimeError("b200ude needs a CUDA device (sm_100a); there is no CPU fallback")
