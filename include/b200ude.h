@@ -60,6 +60,8 @@ extern "C" {
 #define B200UDE_MODEL_FKPP 2 /* pointwise reaction net + D0 * 3-tap periodic stencil, n_suffix = 5
                                 Fisher-KPP-CNN.jl:111-126, scenario_3.jl:103-114 */
 #define B200UDE_MODEL_NODE 3 /* du = NN(u) */
+#define B200UDE_MODEL_SEIR_NODE 4 /* the SEIR script's black-box baseline dudt_node: dS,dE,dI,dR,dD = first five outputs of
+                                     NN([S/N,E,I,R,N,D/N,C]), dN = -mu N, dC = sigma E   seir_exposure.jl:52-64; consts as MODEL_SEIR */
 
 /* activations of the dense chain */
 #define B200UDE_ACT_IDENTITY 0

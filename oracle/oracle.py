@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libude_oracle.so")
 
-MODEL_LV, MODEL_SEIR, MODEL_FKPP, MODEL_NODE = 0, 1, 2, 3
+MODEL_LV, MODEL_SEIR, MODEL_FKPP, MODEL_NODE, MODEL_SEIR_NODE = 0, 1, 2, 3, 4
 ACT_IDENTITY, ACT_TANH, ACT_RBF = 0, 1, 2
 TSIT5, VERN7 = 0, 1
 _ACT = {"identity": 0, "tanh": 1, "rbf": 2}
@@ -78,6 +78,11 @@ SEIR_CONSTS = (10.0, 0.5944, 0.4239, 1117.3, 0.02, 1 / 3, 1 / 5, 0.2, 1 / 11.2) 
 
 def seir_model(widths=(3, 64, 64, 1), acts=("tanh", "tanh", "identity")):
     return make_model(MODEL_SEIR, 7, widths, acts, consts=SEIR_CONSTS)
+
+
+def seir_node_model(widths=(7, 64, 64, 64, 7), acts=("tanh", "tanh", "tanh", "identity")):
+    """The script's black-box baseline dudt_node (seir_exposure.jl:52-64)."""
+    return make_model(MODEL_SEIR_NODE, 7, widths, acts, consts=SEIR_CONSTS)
 
 
 def fkpp_model(nx, widths, acts):

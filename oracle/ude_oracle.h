@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-enum { UDE_MODEL_LV = 0, UDE_MODEL_SEIR = 1, UDE_MODEL_FKPP = 2, UDE_MODEL_NODE = 3 };
+enum { UDE_MODEL_LV = 0, UDE_MODEL_SEIR = 1, UDE_MODEL_FKPP = 2, UDE_MODEL_NODE = 3, UDE_MODEL_SEIR_NODE = 4 };
 enum { UDE_ACT_IDENTITY = 0, UDE_ACT_TANH = 1, UDE_ACT_RBF = 2 };
 enum { UDE_TSIT5 = 0, UDE_VERN7 = 1 };
 

@@ -146,6 +146,18 @@ void FN(ude_rhs)(const ude_model *m, const REAL *th, const REAL *u, REAL *du)
         }
         break;
     }
+    case UDE_MODEL_SEIR_NODE: {
+        /* seir_exposure.jl:55-64: dS,dE,dI,dR,dD = first five outputs of ann_node([S/N,E,I,R,N,D/N,C]); dN = -mu N; dC = sigma E */
+        const REAL mu = (REAL)m->consts[4], sg = (REAL)m->consts[5];
+        const REAL N = u[4];
+        REAL x[7] = { u[0] / N, u[1], u[2], u[3], N, u[5] / N, u[6] };
+        FN(chain_forward_store)(m, thc, x, hs, pre);
+        du[0] = hs[L][0]; du[1] = hs[L][1]; du[2] = hs[L][2]; du[3] = hs[L][3];
+        du[4] = -mu * N;
+        du[5] = hs[L][4];
+        du[6] = sg * u[1];
+        break;
+    }
     default: /* UDE_MODEL_NODE: du = NN(u) */
         FN(chain_forward_store)(m, thc, u, hs, pre);
         for (int k = 0; k < m->d; ++k) du[k] = hs[L][k];
@@ -218,6 +230,22 @@ void FN(ude_rhs_vjp)(const ude_model *m, const REAL *th, const REAL *u, const RE
                 gsx[4] += w * (w1 * u[im] + w2 * u[i] + w3 * u[ip]) * lam[i];
             }
         }
+        break;
+    }
+    case UDE_MODEL_SEIR_NODE: {
+        const REAL mu = (REAL)m->consts[4], sg = (REAL)m->consts[5];
+        const REAL S = u[0], N = u[4], D = u[5];
+        REAL x[7] = { S / N, u[1], u[2], u[3], N, D / N, u[6] };
+        REAL dy[7] = { lam[0], lam[1], lam[2], lam[3], lam[5], 0, 0 };
+        FN(chain_forward_store)(m, thc, x, hs, pre);
+        FN(chain_vjp)(m, thc, hs, pre, dy, dx, gthc, w);
+        dlam[0] = dx[0] / N;
+        dlam[1] = dx[1] + sg * lam[6];
+        dlam[2] = dx[2];
+        dlam[3] = dx[3];
+        dlam[4] = dx[4] - mu * lam[4] - dx[0] * S / (N * N) - dx[5] * D / (N * N);
+        dlam[5] = dx[5] / N;
+        dlam[6] = dx[6];
         break;
     }
     default:

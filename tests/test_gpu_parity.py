@@ -733,3 +733,35 @@ def test_discrete_adjoint_unsupported_configurations_fail_loudly():
     with pytest.raises(B200UDEError) as e:
         ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=4, sensealg=ude.ForwardDiffSensitivity(), adaptive=True, abstol=1e-6, reltol=1e-6)
     assert e.value.code == EUNSUPPORTED
+
+
+def test_seir_neural_ode_baseline_vs_oracle(O):
+    """dudt_node of the SEIR script (seir_exposure.jl:52-64; the black-box baseline trained before the UDE): chain
+    7-64-64-64-7 tanh (P = 9287, the largest parameter vector of the path) on [S/N, E, I, R, N, D/N, C], five outputs used,
+    dN and dC physical.  Runtime-shape kernels vs the oracle: forward, loss on E, I, R, gradient."""
+    ude = _ude()
+    rng = np.random.default_rng(23)
+    N = 40
+    widths = (7, 64, 64, 64, 7)
+    chain = ude.FastChain(ude.FastDense(7, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 7))
+    f = ude.SEIRNeuralODE(chain)
+    assert f.num_params() == 9287
+    theta = (0.3 * glorot_theta(widths, seed=6)).astype(np.float32)
+    S0 = 14e6
+    u0 = np.zeros((7, N), np.float32)
+    u0[0] = 0.9 * S0 * rng.uniform(0.9, 1.0, N)
+    u0[1:4] = rng.uniform(0, 50, (3, N)); u0[4] = S0; u0[5] = rng.uniform(0, 10, N); u0[6] = rng.uniform(0, 100, N)
+    n_steps, dt, every = 40, 0.25, 4
+    m = O.seir_node_model()
+    assert O.num_params(m) == 9287
+    w = np.array([0, 1, 1, 1, 0, 0, 0], np.float64)
+    y = np.stack([O.solve_fixed(m, theta.astype(np.float64) * 1.05, u0[:, k].astype(np.float64), dt, n_steps, save_every=every) for k in range(N)], axis=2).astype(np.float32)
+    solver = ude.UDESolver(f, 0.0, dt, n_steps, every, max_trajectories=N, loss_weights=w)
+    out, loss, gth, gu, status = _run(solver, theta, u0, y)
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, w, dt, n_steps, save_every=every, want_out=True)
+    assert (status == 0).all()
+    scale = np.abs(out64).max(axis=(0, 2), keepdims=True)
+    assert np.all(np.abs(out - out64) <= 2e-5 * scale + 1e-3)
+    assert abs(loss - l64) <= 5e-3 * abs(l64) + 1e-6
+    assert np.linalg.norm(gth - g64) <= 1e-2 * np.linalg.norm(g64)
+    solver.close()

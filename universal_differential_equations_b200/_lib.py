@@ -15,7 +15,7 @@ SO_PATH = os.path.join(CSRC, "libb200ude.so")
 # ---- constants mirrored from include/b200ude.h -------------------------------
 ABI_VERSION = 1
 F32, F64 = 0, 1
-MODEL_LV, MODEL_SEIR, MODEL_FKPP, MODEL_NODE = 0, 1, 2, 3
+MODEL_LV, MODEL_SEIR, MODEL_FKPP, MODEL_NODE, MODEL_SEIR_NODE = 0, 1, 2, 3, 4
 ACT_IDENTITY, ACT_TANH, ACT_RBF = 0, 1, 2
 TSIT5, VERN7 = 0, 1
 INTERPOLATING_ADJOINT, DISCRETE_ADJOINT = 0, 1

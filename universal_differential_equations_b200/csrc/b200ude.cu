@@ -143,6 +143,7 @@ bool generic_ok(const b200ude_desc &d)
     if (d.model == B200UDE_MODEL_LV) return d.state_dim == 2 && din == 2 && dout == 2 && d.n_prefix >= 0 && d.n_prefix <= 2 && d.n_consts >= 2;
     if (d.model == B200UDE_MODEL_SEIR) return d.state_dim == 7 && din == 3 && dout == 1 && d.n_prefix == 0 && d.n_consts >= 9;
     if (d.model == B200UDE_MODEL_FKPP) return d.state_dim >= 3 && d.state_dim <= 256 && din == 1 && dout == 1 && d.n_prefix == 0 && d.n_suffix == 5 && d.n_loss_weights == 0;
+    if (d.model == B200UDE_MODEL_SEIR_NODE) return d.state_dim == 7 && din == 7 && dout == 7 && d.n_prefix == 0 && d.n_consts >= 9;
     if (d.model == B200UDE_MODEL_NODE) return d.state_dim >= 1 && d.state_dim <= 8 && din == d.state_dim && dout == d.state_dim && d.n_prefix == 0;
     return false;
 }
@@ -438,7 +439,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         h->gen.model = d->model; h->gen.D = d->state_dim; h->gen.din = d->widths[0]; h->gen.dout = d->widths[d->n_layers];
         h->gen.n_layers = d->n_layers; h->gen.n_prefix = d->n_prefix; h->gen.P = P;
         for (int l = 0; l < 8; ++l) { h->gen.widths[l] = l <= d->n_layers ? d->widths[l] : 0; h->gen.acts[l] = l < d->n_layers ? d->acts[l] : 0; }
-        if (P > 8192) { delete h; return fail(nullptr, B200UDE_EUNSUPPORTED, "create: %d parameters exceed the constant-bank budget", P); }
+        if (P > 12288) { delete h; return fail(nullptr, B200UDE_EUNSUPPORTED, "create: %d parameters exceed the constant-bank budget", P); }
     }
     h->var.approx_tanh = (d->flags & B200UDE_FLAG_APPROX_TANH) ? 1 : 0;
     h->var.discrete = d->sensealg == B200UDE_DISCRETE_ADJOINT ? 1 : 0;

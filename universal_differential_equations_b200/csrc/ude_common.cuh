@@ -29,12 +29,12 @@
 
 namespace b200ude {
 
-constexpr int MODEL_LV = 0, MODEL_SEIR = 1, MODEL_FKPP = 2, MODEL_NODE = 3;
+constexpr int MODEL_LV = 0, MODEL_SEIR = 1, MODEL_FKPP = 2, MODEL_NODE = 3, MODEL_SEIR_NODE = 4;
 constexpr int ACT_IDENTITY = 0, ACT_TANH = 1, ACT_RBF = 2, ACT_RUNTIME = -1;
 constexpr int GRAD_LANE = 0;   // every lane keeps all P partial sums in registers (small chains)
 constexpr int GRAD_WARPGEMM = 1;  // H x H layer via per-warp smem-staged outer-product GEMM
 
-constexpr int MAX_THETA = 8192;  // floats; 32 KB of the 64 KB constant bank
+constexpr int MAX_THETA = 12288;  // floats; 48 KB of the 64 KB constant bank (the script's 7-64-64-64-7 neural ODE has 9287)
 static __constant__ __align__(16) float c_theta[MAX_THETA];
 static __constant__ float c_consts[16];
 static __constant__ float c_lossw[16];

@@ -65,6 +65,9 @@ __device__ __forceinline__ void model_inputs(const float *u, float *x)
     if (c_gen.model == MODEL_SEIR) {
         const float invN = 1.0f / u[4];
         x[0] = u[0] * invN; x[1] = u[2]; x[2] = u[5] * invN;
+    } else if (c_gen.model == MODEL_SEIR_NODE) {   // [S/N, E, I, R, N, D/N, C]  seir_exposure.jl:58
+        const float invN = 1.0f / u[4];
+        x[0] = u[0] * invN; x[1] = u[1]; x[2] = u[2]; x[3] = u[3]; x[4] = u[4]; x[5] = u[5] * invN; x[6] = u[6];
     } else {
         for (int i = 0; i < c_gen.din; ++i) x[i] = u[i];
     }
@@ -93,6 +96,11 @@ __device__ __forceinline__ void model_rhs(const float *u, float *du)
         du[4] = -mu * N;
         du[5] = dd * gm * I - lm * Dd;
         du[6] = sg * E;
+    } else if (c_gen.model == MODEL_SEIR_NODE) {   // dS,dE,dI,dR,dD = first five chain outputs; dN = -mu N; dC = sigma E  (seir_exposure.jl:55-64)
+        du[0] = y[0]; du[1] = y[1]; du[2] = y[2]; du[3] = y[3];
+        du[4] = -c_consts[4] * u[4];
+        du[5] = y[4];
+        du[6] = c_consts[5] * u[1];
     } else {
         for (int k = 0; k < c_gen.D; ++k) du[k] = y[k];
     }
@@ -237,6 +245,7 @@ __device__ __forceinline__ void model_vjp(const float *u, const float *g, float 
     model_inputs(u, x);
     const float w = sc * lv;   // quadrature weight, zero for padding lanes
     if (c_gen.model == MODEL_SEIR) dy[0] = g[1] - g[0];   // z enters dS with -, dE with +
+    else if (c_gen.model == MODEL_SEIR_NODE) { dy[0] = g[0]; dy[1] = g[1]; dy[2] = g[2]; dy[3] = g[3]; dy[4] = g[5]; dy[5] = 0.0f; dy[6] = 0.0f; }
     else for (int m = 0; m < c_gen.dout; ++m) dy[m] = g[m];
     chain_vjp(x, dy, w, dx, gw, lane);
     if (c_gen.model == MODEL_LV) {
@@ -261,6 +270,15 @@ __device__ __forceinline__ void model_vjp(const float *u, const float *g, float 
         kl[4] = g[0] * (-cN) + g[1] * cN + g[4] * (-mu) - dx[0] * S / (N * N) - dx[2] * Dd / (N * N);
         kl[5] = g[5] * (-lm) + dx[2] / N;
         kl[6] = 0.0f;
+    } else if (c_gen.model == MODEL_SEIR_NODE) {
+        const float S = u[0], N = u[4], Dd = u[5], mu = c_consts[4], sg = c_consts[5];
+        kl[0] = dx[0] / N;
+        kl[1] = dx[1] + sg * g[6];
+        kl[2] = dx[2];
+        kl[3] = dx[3];
+        kl[4] = dx[4] - mu * g[4] - dx[0] * S / (N * N) - dx[5] * Dd / (N * N);
+        kl[5] = dx[5] / N;
+        kl[6] = dx[6];
     } else {
         for (int k = 0; k < c_gen.D; ++k) kl[k] = dx[k];
     }

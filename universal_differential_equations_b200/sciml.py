@@ -179,6 +179,23 @@ class NeuralODE:
         return self.chain.num_params()
 
 
+@dataclass
+class SEIRNeuralODE:
+    """dudt_node of the SEIR script (seir_exposure.jl:52-64): dS,dE,dI,dR,dD = first five outputs of
+    ann_node([S/N,E,I,R,N,D/N,C]), dN = -mu N, dC = sigma E; chain 7 -> ... -> 7 (the script: 7-64-64-64-7 tanh)."""
+    chain: FastChain
+    p_: Sequence[float] = SEIR_P   # seir_exposure.jl:33
+
+    model = _lib.MODEL_SEIR_NODE
+    state_dim = 7
+
+    def consts(self):
+        return tuple(float(x) for x in self.p_)
+
+    def num_params(self):
+        return self.chain.num_params()
+
+
 # --------------------------------------------------------------------------- problem / algorithm types
 @dataclass
 class ODEProblem:
