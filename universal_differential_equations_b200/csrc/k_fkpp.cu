@@ -4,11 +4,20 @@
 
 namespace b200ude {
 
+#include <cstdlib>
+// packed kernels (two adjacent grid points per thread, FFMA2) for even grids; B200UDE_FKPP_PACKED=0 selects the scalar ones
+static bool use_packed(int Nx)
+{
+    const char *e = getenv("B200UDE_FKPP_PACKED");
+    return (Nx % 2 == 0) && !(e && *e == '0');
+}
+
 static void geom16(int Nx, fkpp::Geom *g, int *threads)
 {
+    const int per_traj = use_packed(Nx) ? Nx / 2 : Nx;   // threads per trajectory
     g->Nx = Nx;
-    g->tpc = Nx >= 128 ? 1 : 128 / Nx;
-    *threads = ((g->tpc * Nx + 31) / 32) * 32;
+    g->tpc = per_traj >= 128 ? 1 : 128 / per_traj;
+    *threads = ((g->tpc * per_traj + 31) / 32) * 32;
 }
 
 int adj_rows_fkpp16(int N, int Nx)
@@ -24,7 +33,8 @@ static cudaError_t fwd(const FwdParams &p, int Nx, cudaStream_t st)
     fkpp::Geom g; int th;
     geom16(Nx, &g, &th);
     const int grid = (p.N + g.tpc - 1) / g.tpc;
-    fkpp::forward_kernel<16, TM><<<grid, th, sizeof(float) * 2 * g.tpc * g.Nx, st>>>(p, g);
+    if (use_packed(Nx)) fkpp::forward_kernel2<16, TM><<<grid, th, sizeof(float) * 2 * g.tpc * g.Nx, st>>>(p, g);   // [2][tpc * Nx/2] float2
+    else fkpp::forward_kernel<16, TM><<<grid, th, sizeof(float) * 2 * g.tpc * g.Nx, st>>>(p, g);
     return cudaGetLastError();
 }
 
@@ -33,11 +43,26 @@ static cudaError_t adj(const AdjParams &p, int Nx, cudaStream_t st, int *rows_ou
 {
     fkpp::Geom g; int th;
     geom16(Nx, &g, &th);
-    const int grid = (p.N + g.tpc - 1) / g.tpc, slots = g.tpc * g.Nx, nwarp = th / 32;
-    size_t smem = sizeof(float) * 4 * (size_t)(((slots + 1) / 2) * 2) + (size_t)nwarp * sizeof(fkpp::WarpRows<16>);
+    const int grid = (p.N + g.tpc - 1) / g.tpc, nwarp = th / 32;
     const size_t red = sizeof(float) * (size_t)nwarp * (fkpp::Off<16>::P + 1);
-    if (red > smem) smem = red;
     *rows_out = grid;
+    if (use_packed(Nx)) {
+        const int slots = g.tpc * (g.Nx / 2);
+        size_t smem = sizeof(float) * 8 * (size_t)slots + (size_t)nwarp * sizeof(fkpp::WarpRows2<16>);
+        if (red > smem) smem = red;
+        auto kern = fkpp::adjoint_kernel2<16, TM>;
+        static bool done = false;
+        if (!done) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            done = true;
+        }
+        kern<<<grid, th, smem, st>>>(p, g);
+        return cudaGetLastError();
+    }
+    const int slots = g.tpc * g.Nx;
+    size_t smem = sizeof(float) * 4 * (size_t)(((slots + 1) / 2) * 2) + (size_t)nwarp * sizeof(fkpp::WarpRows<16>);
+    if (red > smem) smem = red;
     fkpp::adjoint_kernel<16, TM><<<grid, th, smem, st>>>(p, g);
     return cudaGetLastError();
 }
