@@ -202,7 +202,9 @@ int32_t b200ude_adam_step(b200ude_handle *h, const b200ude_adam *opt, const void
 /* `iters` full iterations without a host round trip: forward, fused-L2 adjoint, fixed-order reduce, ADAM update -- the first
  * launched directly, the rest as replays of one captured CUDA graph.  u0 [d][N], data [n_save][d][N]: DEVICE pointers.
  * loss_history: DEVICE float[iters] or NULL; slot i = loss at the pre-update theta of iteration i (what the reference's
- * callback records).  stream NULL = the handle's own stream, synchronised before returning. */
+ * callback records).  stream NULL = the handle's own stream, synchronised before returning.  With peers attached
+ * (b200ude_peer_attach, below) every iteration uses the loss and gradient summed over ALL ranks: the call is then a collective,
+ * every rank runs the same iterations in lock step and applies the identical update to its replica of theta. */
 int32_t b200ude_train_adam(b200ude_handle *h, const b200ude_adam *opt, const void *u0, const void *data, size_t N,
                            int32_t iters, void *loss_history, void *stream);
 

@@ -476,6 +476,17 @@ def test_adaptive_tensor_core_lv32_vs_oracle_and_runtime_shape(O, N, tol, monkey
     o2, l2, g2, gu2, _ = res["0"]
     assert np.abs(out - o2).max() <= 50 * tol * (1 + np.abs(o2).max()) + 3e-5
     assert np.linalg.norm(gth - g2) <= 5e-3 * np.linalg.norm(g2)
+    if N == 300:
+        # step budget exhausted -> status 2 (no hang, no crash), and the adjoint of the truncated record still runs
+        s3 = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N, adaptive=True, abstol=1e-7, reltol=1e-7, max_steps=3)
+        _, _, g3, _, st3 = _run(s3, theta, u0, y)
+        assert (st3 == 2).all() and np.isfinite(g3).all()
+        # a diverging start -> status 1 for that trajectory only
+        ub = u0.copy(); ub[:, 5] = 3e38
+        s4 = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N, adaptive=True, abstol=tol, reltol=tol, max_steps=256)
+        st4 = _run(s4, theta, ub, y)[4]
+        assert st4[5] == 1 and (np.delete(st4, 5) == 0).all()
+        s3.close(); s4.close()
 
 
 def test_adaptive_tensor_core_seir_vs_oracle_and_runtime_shape(O, monkeypatch):

@@ -85,7 +85,6 @@ struct b200ude_handle {
     void *d_peer_buf = nullptr;     // this rank's exchange buffer (cudaMalloc, exported with CUDA IPC)
     PeerLinks peer;                 // every rank's buffer as mapped here
     bool peer_attached = false;
-    unsigned peer_epoch = 0;
     // on-device optimiser (b200ude_adam_*, b200ude_train_adam)
     float *d_u0_keep = nullptr, *d_aux_out = nullptr;   // Vern7: u0 of the last forward, saved states of the Tsit5 re-solve
     bool vern7_pending = false;
@@ -277,8 +276,7 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     }
     CUDA_TRY(h, e);
     if (peer) {
-        h->peer_epoch += 1;
-        CUDA_TRY(h, launch_reduce_exchange(h->d_partial, grid, h->P + 1, h->peer, h->peer_epoch, grad_theta, loss, st));
+        CUDA_TRY(h, launch_reduce_exchange(h->d_partial, grid, h->P + 1, h->peer, grad_theta, loss, st));
     } else {
         CUDA_TRY(h, launch_reduce(h->d_partial, grid, h->P + 1, grad_theta, loss, st));
     }
@@ -664,7 +662,9 @@ int32_t b200ude_train_adam(b200ude_handle *h, const b200ude_adam *opt, const voi
     auto one_iteration = [&]() -> int32_t {
         int32_t r = do_forward(h, (const float *)u0, N, h->d_train_out, nullptr, st);
         if (r) return r;
-        r = do_adjoint(h, true, (const float *)data, h->d_loss, h->d_grad, nullptr, st);
+        // with peers attached (b200ude_peer_attach) the gradient and the loss are the sums over all ranks: every rank runs the
+        // same iterations in lock step and applies the identical update to its replica of theta
+        r = do_adjoint(h, true, (const float *)data, h->d_loss, h->d_grad, nullptr, st, h->peer_attached);
         if (r) return r;
         CUDA_TRY(h, launch_adam(h, opt, h->d_grad, h->d_loss, (float *)loss_history, t_base, st));
         return B200UDE_OK;
@@ -738,7 +738,6 @@ int32_t b200ude_peer_attach(b200ude_handle *h, int32_t rank, int32_t world, cons
     }
     h->peer.rank = rank; h->peer.world = world; h->peer.P1pad = ((h->P + 1 + 31) / 32) * 32;
     h->peer_attached = true;
-    h->peer_epoch = 0;
     return B200UDE_OK;
 }
 

@@ -91,8 +91,7 @@ cudaError_t launch_reduce(const float *partial, int nblocks, int P1, float *grad
     return cudaGetLastError();
 }
 
-cudaError_t launch_reduce_exchange(const float *partial, int nblocks, int P1, const PeerLinks &pl, unsigned epoch, float *grad, float *loss,
-                                   cudaStream_t st)
+cudaError_t launch_reduce_exchange(const float *partial, int nblocks, int P1, const PeerLinks &pl, float *grad, float *loss, cudaStream_t st)
 {
     PeerCtx c;
     for (int r = 0; r < 16; ++r) {
@@ -101,7 +100,7 @@ cudaError_t launch_reduce_exchange(const float *partial, int nblocks, int P1, co
     }
     c.ticket = reinterpret_cast<unsigned *>(pl.base[pl.rank]) + 16;
     c.rank = pl.rank; c.world = pl.world; c.P1pad = pl.P1pad;
-    ude_reduce_exchange_kernel<<<(P1 + 7) / 8, 256, 0, st>>>(partial, nblocks, P1, c, epoch, grad, loss);
+    ude_reduce_exchange_kernel<<<(P1 + 7) / 8, 256, 0, st>>>(partial, nblocks, P1, c, grad, loss);
     return cudaGetLastError();
 }
 

@@ -105,7 +105,7 @@ struct PeerLinks {
     void *base[16];
     int rank = 0, world = 0, P1pad = 0;
 };
-cudaError_t launch_reduce_exchange(const float *partial, int nblocks, int P1, const PeerLinks &, unsigned epoch, float *grad, float *loss, cudaStream_t);
+cudaError_t launch_reduce_exchange(const float *partial, int nblocks, int P1, const PeerLinks &, float *grad, float *loss, cudaStream_t);
 cudaError_t launch_reduce(const float *partial, int nblocks, int P1, float *grad, float *loss, cudaStream_t);
 
 }  // namespace b200ude

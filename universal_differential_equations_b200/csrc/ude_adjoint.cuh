@@ -327,6 +327,8 @@ static __global__ void ude_reduce_kernel(const float *__restrict__ partial, int 
 // Every rank owns an exchange buffer (cudaMalloc'ed, mapped into every peer process with CUDA IPC):
 //   uint32 flags[16]   flags[src] = number of CTAs of rank `src` whose pushes have landed here (monotonic)
 //   uint32 ticket      local CTA counter (monotonic)
+//   uint32 epoch       number of completed calls (device-resident so that launch arguments never change: the call can sit
+//                      in a replayed CUDA graph, b200ude_train_adam); read by every CTA at its start, bumped by the last CTA
 //   float  slots[2][16][P1pad]   [epoch parity][source rank][entry]
 // Phase 1 (all CTAs, one warp per entry): local fixed-order sum over the partial rows, PUSHED with plain stores into
 // slots[parity][rank][q] of every rank (remote stores over NVLink are fire-and-forget), system-scope fence, then one
@@ -342,10 +344,12 @@ struct PeerCtx {
     int rank, world, P1pad;
 };
 
-static __global__ void ude_reduce_exchange_kernel(const float *__restrict__ partial, int nblocks, int P1, PeerCtx ctx, unsigned epoch,
+static __global__ void ude_reduce_exchange_kernel(const float *__restrict__ partial, int nblocks, int P1, PeerCtx ctx,
                                                   float *__restrict__ grad, float *__restrict__ loss)
 {
     __shared__ int s_last;
+    // no CTA of this launch can have bumped it yet: the bump happens after ALL CTAs took their ticket, which follows this read
+    const unsigned epoch = *reinterpret_cast<volatile unsigned *>(ctx.ticket + 1) + 1u;
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int par = (int)(epoch & 1u);
@@ -394,6 +398,8 @@ static __global__ void ude_reduce_exchange_kernel(const float *__restrict__ part
             grad[e] = tot;
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(ctx.ticket + 1) = epoch;
 }
 
 }  // namespace b200ude
