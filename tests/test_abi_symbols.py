@@ -83,3 +83,22 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "ude_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_ctypes_mirrors_have_the_sizes_the_c_compiler_gives_the_header(tmp_path):
+    """sizeof / offsetof of b200ude_desc and b200ude_adam as gcc lays them out == the ctypes mirrors in _lib.py
+    (a drifted mirror would otherwise only show up as EINVAL from create() on a GPU box)."""
+    import subprocess
+    from universal_differential_equations_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "b200ude.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200ude_desc), offsetof(b200ude_desc, consts), '
+        'offsetof(b200ude_desc, loss_weights), offsetof(b200ude_desc, max_trajectories), offsetof(b200ude_desc, max_steps), '
+        'sizeof(b200ude_adam), offsetof(b200ude_adam, l2_reg)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    D, A = _lib.Desc, _lib.Adam
+    want = [C.sizeof(D), D.consts.offset, D.loss_weights.offset, D.max_trajectories.offset, D.max_steps.offset, C.sizeof(A), A.l2_reg.offset]
+    assert got == want, (got, want)
