@@ -19,8 +19,11 @@ N = 300
 u0, y = synthetic_ensemble(N)
 lv32 = ude.LotkaVolterraUDE(ude.FastChain(ude.FastDense(2, 32, ude.tanh), ude.FastDense(32, 32, ude.tanh), ude.FastDense(32, 2)))
 run("lv32", lv32, glorot_theta((2, 32, 32, 2), seed=1), u0, y, 0.1, 30, 1)
+run("lv32-adaptive-tc", lv32, glorot_theta((2, 32, 32, 2), seed=1), u0, y, 0.1, 30, 1, adaptive=True, abstol=1e-5, reltol=1e-5, max_steps=200)
+run("lv32-discrete", lv32, glorot_theta((2, 32, 32, 2), seed=1), u0, y, 0.1, 30, 1, sensealg=ude.ForwardDiffSensitivity())
 lv5 = ude.LotkaVolterraUDE(ude.FastChain(ude.FastDense(2, 5, ude.rbf), ude.FastDense(5, 5, ude.rbf), ude.FastDense(5, 5, ude.tanh), ude.FastDense(5, 2)), trainable_rates=2)
 run("lv5p2", lv5, np.concatenate([[1.3, 1.8], glorot_theta((2, 5, 5, 5, 2), seed=2)]), u0, y, 0.1, 30, 1)
+run("lv5p2-discrete", lv5, np.concatenate([[1.3, 1.8], glorot_theta((2, 5, 5, 5, 2), seed=2)]), u0, y, 0.1, 30, 1, sensealg=ude.ForwardDiffSensitivity())
 gen = ude.LotkaVolterraUDE(ude.FastChain(ude.FastDense(2, 7, ude.tanh), ude.FastDense(7, 2)))
 run("generic", gen, glorot_theta((2, 7, 2), seed=3), u0, y, 0.1, 30, 1)
 run("adaptive", gen, glorot_theta((2, 7, 2), seed=3), u0, y, 0.1, 30, 1, adaptive=True, abstol=1e-5, reltol=1e-5, max_steps=200)
@@ -32,7 +35,10 @@ us = np.zeros((7, Ns), np.float32); us[0] = 0.9 * S0; us[1:4] = rng.uniform(0, 5
 ys = rng.uniform(0, 100, (8, 7, Ns)).astype(np.float32)
 seir = ude.SEIRExposureUDE(ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1)))
 run("seir64", seir, glorot_theta((3, 64, 64, 1), seed=2), us, ys, 0.25, 28, 4, loss_weights=[0, 1, 1, 1, 0, 0, 0])
-for nx, n in ((26, 7), (256, 3)):
+run("seir64-adaptive-tc", seir, glorot_theta((3, 64, 64, 1), seed=2), us, ys, 1.0, 7, 1, loss_weights=[0, 1, 1, 1, 0, 0, 0], adaptive=True, abstol=1e-4, reltol=1e-4, max_steps=128)
+node = ude.SEIRNeuralODE(ude.FastChain(ude.FastDense(7, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 7)))
+run("seir-node", node, 0.3 * glorot_theta((7, 64, 64, 64, 7), seed=6), us[:, :40].copy(), ys[:, :, :40].copy(), 0.25, 28, 4, loss_weights=[0, 1, 1, 1, 0, 0, 0])
+for nx, n in ((26, 7), (27, 5), (256, 3)):
     fk = ude.FisherKPPUDE(ude.FastChain(ude.FastDense(1, 16, ude.tanh), ude.FastDense(16, 16, ude.tanh), ude.FastDense(16, 1)), nx)
     th = np.concatenate([glorot_theta((1, 16, 16, 1), seed=4), [1.1, -2.3, 0.9, 0.0, 0.01 * (nx - 1) ** 2]])
     x = np.linspace(0, 1, nx)
