@@ -313,6 +313,8 @@ def test_seir_tensor_core_vs_runtime_shape_kernels(N, monkeypatch):
         torch.cuda.synchronize()
         res.append((out, loss, g, gu, g2.cpu().numpy(), gu2.cpu().numpy()))
         assert (status == 0).all()
+        rep = _run(solver, theta, u0, y)   # bitwise reproducible run to run
+        assert np.array_equal(rep[0], out) and rep[1] == loss and np.array_equal(rep[2], g) and np.array_equal(rep[3], gu)
         solver.close()
     a, b = res
     scale = np.abs(b[0]).max(axis=(0, 2), keepdims=True)
@@ -377,6 +379,8 @@ def test_fisher_kpp_tuned_vs_runtime_shape_kernels(nx, N, monkeypatch):
         torch.cuda.synchronize()
         assert (status == 0).all()
         res.append((out, loss, g, gu, g2.cpu().numpy(), gu2.cpu().numpy()))
+        rep = _run(solver, theta, u0, y)   # fixed-order reductions: bitwise reproducible run to run
+        assert np.array_equal(rep[0], out) and rep[1] == loss and np.array_equal(rep[2], g) and np.array_equal(rep[3], gu)
         solver.close()
     a, b = res
     assert np.abs(a[0] - b[0]).max() <= 2e-6 * (1 + np.abs(b[0]).max())
