@@ -503,11 +503,19 @@ __device__ __forceinline__ void mma_m16n8k8(float (&d)[4], const uint32_t (&a)[4
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+// 3xTF32 operand split for mma.sync: the tensor core reads only the upper 19 bits of a .tf32 operand register (the low 13
+// mantissa bits are ignored), so the fp32 value itself serves as the "hi" operand (= its truncation) and only the residual
+// lo = x - trunc(x) has to be formed: one LOP + one FADD per element.  (B200UDE_TF32_RNA_SPLIT: explicit round-to-nearest hi.)
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
 {
+#ifdef B200UDE_TF32_RNA_SPLIT
     const float h = tf32_rna(x);
     hi = __float_as_uint(h);
     lo = __float_as_uint(x - h);
+#else
+    hi = __float_as_uint(x);
+    lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
+#endif
 }
 
 // Running sums kept in spare tensor-memory columns (one 32-column row per thread): sum += m with ordinary round-to-nearest
