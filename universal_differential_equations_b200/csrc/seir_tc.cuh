@@ -67,9 +67,9 @@ __device__ __forceinline__ void tc_issue64(GrpCtx &c, const float (&a)[HS], cons
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float h = tf32_rna(a[8 * q + k]);
-            hi[k] = __float_as_uint(h);
-            lo[k] = __float_as_uint(a[8 * q + k] - h);
+            // the tensor core reads the upper 19 bits of a tf32 operand: the value itself is the hi operand (see split_tf32)
+            hi[k] = __float_as_uint(a[8 * q + k]);
+            lo[k] = __float_as_uint(a[8 * q + k] - __uint_as_float(hi[k] & 0xFFFFE000u));
         }
         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(c.tmem + HS + 8 * q + c.lane_base),
                      "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
