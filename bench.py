@@ -285,8 +285,8 @@ def main():
         "bound": "hbm", "achieved": n * BYTES_ADJ / (adj_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": n * BYTES_ADJ / (adj_ms * 1e-3) / 1e9 / hbm_peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
-        "traffic": 131.5e6 * (n / 65536.0),
-        "traffic_source": "ncu --set full capture of this kernel at N=65536: dram read 127.5 MB + write 4.0 MB (profiles/r01_ncu_kernel_summaries.txt); algorithmic bytes %.1f MB" % (65536 * BYTES_ADJ / 1e6),
+        "traffic": 132.5e6 * (n / 65536.0),
+        "traffic_source": "ncu --set full capture of this kernel at N=65536: dram read 127.5 MB + write 5.0 MB (profiles/r01b_ncu_kernel_summaries.txt); algorithmic bytes %.1f MB" % (65536 * BYTES_ADJ / 1e6),
         "note": "the path is compute-bound by construction (SURVEY.md 8d, ~430 FLOP/B): roofline_fp32 (CUDA-core FP32 peak, which the tensor-core kernels bypass for the 32x32 layers) and roofline_xu (MUFU, the nearest bound of the tensor-core forward kernel) are the informative ones",
     }
     roofline_fp32 = {
