@@ -201,6 +201,7 @@ int32_t tsit5_forward(b200ude_handle *h, const float *u0, size_t N, float *out, 
 
 int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int32_t *status, cudaStream_t st)
 {
+    CUDA_TRY(h, cudaSetDevice(h->desc.device));   // launches, symbol copies and function attributes go to the handle's device
     if (!h->have_theta) return fail(h, B200UDE_ESTATE, "forward: set_params has not been called");
     if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "forward: N=%zu outside (0, max_trajectories=%zu]", N, h->cap);
     if (!u0 || !out) return fail(h, B200UDE_EINVAL, "forward: null pointer");
@@ -231,6 +232,7 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
 int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, float *grad_theta,
                    float *grad_u0, cudaStream_t st, bool peer = false)
 {
+    CUDA_TRY(h, cudaSetDevice(h->desc.device));
     if (peer && !h->peer_attached) return fail(h, B200UDE_ESTATE, "adjoint_l2_allreduce: b200ude_peer_attach has not been called");
     if (peer && h->adaptive) return fail(h, B200UDE_EUNSUPPORTED, "adjoint_l2_allreduce: not available with adaptive stepping (all-reduce the result of b200ude_adjoint_l2 instead)");
     if (h->desc.solver == B200UDE_VERN7 && h->vern7_pending) {

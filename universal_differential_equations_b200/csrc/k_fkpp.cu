@@ -51,7 +51,8 @@ static cudaError_t adj(const AdjParams &p, int Nx, cudaStream_t st, int *rows_ou
         size_t smem = sizeof(float) * 8 * (size_t)slots + (size_t)nwarp * sizeof(fkpp::WarpRows2<16>);
         if (red > smem) smem = red;
         auto kern = fkpp::adjoint_kernel2<16, TM>;
-        static bool done = false;
+        static PerDeviceOnce once;
+        bool &done = once.flag();
         if (!done) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return e;

@@ -14,7 +14,8 @@ static cudaError_t launch_one(const AdjParams &p, int grid, cudaStream_t st)
 {
     auto kern = lv32::adjoint_kernel<TM, W, ADJ_BLOCK_GEMM, 1>;
     constexpr size_t smem = sizeof(lv32::WarpStage3);
-    static bool attr_set = false;
+    static PerDeviceOnce once;
+    bool &attr_set = once.flag();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -31,7 +32,8 @@ static cudaError_t launch_tc(const AdjParams &p, int *rows_out, cudaStream_t st)
 {
     auto kern = lv32::tc::adjoint_kernel<TM, 128, 4, GEMM, false, DISC>;
     constexpr size_t smem = sizeof(lv32::tc::WarpStageT) * 4;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
+    bool &attr_set = once.flag();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -51,7 +53,8 @@ static cudaError_t launch_tc_adaptive(const AdjParams &p, const AdaptiveGrid &ag
 {
     auto kern = lv32::tc::adjoint_kernel<TM, 128, 4, 1, true>;
     constexpr size_t smem = sizeof(lv32::tc::WarpStageT) * 4;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
+    bool &attr_set = once.flag();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

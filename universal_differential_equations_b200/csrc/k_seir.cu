@@ -25,8 +25,8 @@ static cudaError_t launch_fwd(const FwdParams &p, cudaStream_t st)
 {
     auto kern = seir::forward_kernel<TM>;
     constexpr size_t smem = 2 * seir::HS * seir::HS * sizeof(float);
-    static bool done = false;
-    cudaError_t e = set_smem(kern, smem, &done);
+    static PerDeviceOnce once;
+    cudaError_t e = set_smem(kern, smem, &once.flag());
     if (e != cudaSuccess) return e;
     kern<<<(p.N + seir::BLOCK - 1) / seir::BLOCK, seir::BLOCK, smem, st>>>(p);
     return cudaGetLastError();
@@ -37,8 +37,8 @@ static cudaError_t launch_fwd_adaptive_t(const FwdParams &p, const AdaptiveGrid 
 {
     auto kern = seir::adaptive_forward_kernel<TM>;
     constexpr size_t smem = 2 * seir::HS * seir::HS * sizeof(float);
-    static bool done = false;
-    cudaError_t e = set_smem(kern, smem, &done);
+    static PerDeviceOnce once;
+    cudaError_t e = set_smem(kern, smem, &once.flag());
     if (e != cudaSuccess) return e;
     kern<<<(p.N + seir::BLOCK - 1) / seir::BLOCK, seir::BLOCK, smem, st>>>(p, ag);
     return cudaGetLastError();
@@ -49,8 +49,8 @@ static cudaError_t launch_adj(const AdjParams &p, cudaStream_t st)
 {
     auto kern = seir::adjoint_kernel<TM, GEMM>;
     constexpr size_t smem = 4 * seir::HS * seir::HS * sizeof(float) + seir::GROUPS * sizeof(seir::GroupStage);
-    static bool done = false;
-    cudaError_t e = set_smem(kern, smem, &done);
+    static PerDeviceOnce once;
+    cudaError_t e = set_smem(kern, smem, &once.flag());
     if (e != cudaSuccess) return e;
     kern<<<(p.N + seir::BLOCK - 1) / seir::BLOCK, seir::BLOCK, smem, st>>>(p, AdaptiveGrid{});
     return cudaGetLastError();
@@ -61,8 +61,8 @@ static cudaError_t launch_adj_adaptive_t(const AdjParams &p, const AdaptiveGrid 
 {
     auto kern = seir::adjoint_kernel<TM, 1, true>;
     constexpr size_t smem = 4 * seir::HS * seir::HS * sizeof(float) + seir::GROUPS * sizeof(seir::GroupStage);
-    static bool done = false;
-    cudaError_t e = set_smem(kern, smem, &done);
+    static PerDeviceOnce once;
+    cudaError_t e = set_smem(kern, smem, &once.flag());
     if (e != cudaSuccess) return e;
     kern<<<(p.N + seir::BLOCK - 1) / seir::BLOCK, seir::BLOCK, smem, st>>>(p, ag);
     return cudaGetLastError();

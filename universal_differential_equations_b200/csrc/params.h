@@ -48,6 +48,17 @@ struct Variant {
     int discrete = 0;    // 1: discrete adjoint (exact gradient of the fixed-step scheme) instead of the interpolating adjoint
 };
 
+// function attributes (dynamic shared-memory size) are per device: one-time flags are kept per device ordinal
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool &flag()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return done[dev & 63];
+    }
+};
+
 constexpr int FWD_BLOCK = 128;      // small-chain forward kernels
 constexpr int FWD_BLOCK_LV32 = 32;  // packed LV32 forward: one warp (64 trajectories) per CTA -> even spread over the SMs
 constexpr int ADJ_BLOCK_GEMM = 32;   // H=32 adjoint: one warp (64 trajectories) per CTA
