@@ -780,3 +780,30 @@ def test_seir_neural_ode_baseline_vs_oracle(O):
     assert abs(loss - l64) <= 5e-3 * abs(l64) + 1e-6
     assert np.linalg.norm(gth - g64) <= 1e-2 * np.linalg.norm(g64)
     solver.close()
+
+
+def test_two_devices_in_one_process_interleaved():
+    """One handle per device in ONE process, calls interleaved: constant tables, function attributes and launches follow
+    the handle's device.  (Needs >= 2 GPUs; the benchmark itself runs one process per GPU.)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ude = _ude()
+    N = 700
+    theta = glorot_theta((2, 32, 32, 2), seed=1)
+    u0, y = synthetic_ensemble(N)
+    chain = ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1))
+    res = []
+    solvers = [ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N, device=f"cuda:{d}") for d in (0, 1)]
+    for rep in range(2):
+        for d, sv in enumerate(solvers):
+            with torch.cuda.device(d):
+                dev = torch.device("cuda", d)
+                sv.set_params(torch.from_numpy(theta).to(dev))
+                out = sv.forward(torch.from_numpy(u0).to(dev))
+                L, g, _ = sv.adjoint_l2(torch.from_numpy(y).to(dev))
+                torch.cuda.synchronize(dev)
+                res.append((out.cpu().numpy(), float(L), g.cpu().numpy()))
+    for r in res[1:]:
+        assert np.array_equal(r[0], res[0][0]) and r[1] == res[0][1] and np.array_equal(r[2], res[0][2])
+    for sv in solvers:
+        sv.close()
