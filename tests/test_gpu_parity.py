@@ -603,7 +603,8 @@ def test_vern7_adaptive_forward_vs_oracle_and_reference(golden, O):
     solver.close()
 
 
-def test_on_device_adam_reproduces_reference_loss_history(golden):
+@pytest.mark.parametrize("sens", ["interpolating", "forwarddiff"])
+def test_on_device_adam_reproduces_reference_loss_history(golden, sens):
     """KAT-4 on the GPU: b200ude_train_adam (forward + adjoint + ADAM(0.1) without a host round trip, CUDA-graph
     replayed) from the reference's initial parameters reproduces the reference's stored loss history
     (scenario_1.jl:111-114; losses recorded at the pre-update theta).  fp32 state/gradient vs the reference's
@@ -613,7 +614,9 @@ def test_on_device_adam_reproduces_reference_loss_history(golden):
     theta0 = theta_scenario1_init(g).astype(np.float32)
     X = g["X"].astype(np.float32)                       # [2, 31]
     sub = 8
-    solver = ude.UDESolver(_lv5(ude), 0.0, 0.1 / sub, 30 * sub, sub, max_trajectories=1)
+    # "forwarddiff": the sensealg the script itself uses (scenario_1.jl:86) = exact gradient of the discrete scheme
+    solver = ude.UDESolver(_lv5(ude), 0.0, 0.1 / sub, 30 * sub, sub, max_trajectories=1,
+                           sensealg=ude.ForwardDiffSensitivity() if sens == "forwarddiff" else ude.InterpolatingAdjoint())
     u0 = torch.from_numpy(np.ascontiguousarray(X[:, :1])).cuda()
     data = torch.from_numpy(np.ascontiguousarray(X.T[:, :, None])).cuda()   # [31, 2, 1]
     solver.set_params(torch.from_numpy(theta0).cuda())

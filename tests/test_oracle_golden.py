@@ -128,7 +128,7 @@ def test_kat8_hudson_bay_fastchain_layout(O, golden):
     assert np.abs(out.T - g["Xhat"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("model", ["lv", "seir", "fkpp"])
+@pytest.mark.parametrize("model", ["lv", "seir", "fkpp", "seir_node"])
 def test_rhs_vjp_matches_finite_differences(O, model):
     rng = np.random.default_rng(3)
     if model == "lv":
@@ -136,6 +136,9 @@ def test_rhs_vjp_matches_finite_differences(O, model):
         u = np.array([0.7, 2.3])
     elif model == "seir":
         m = O.seir_model((3, 16, 16, 1))
+        u = np.array([1.2e7, 80.0, 90.0, 130.0, 1.4e7, 20.0, 250.0])
+    elif model == "seir_node":   # dudt_node (seir_exposure.jl:52-64)
+        m = O.seir_node_model((7, 12, 12, 7), ("tanh", "tanh", "identity"))
         u = np.array([1.2e7, 80.0, 90.0, 130.0, 1.4e7, 20.0, 250.0])
     else:
         m = O.fkpp_model(9, (1, 6, 6, 1), ("tanh", "tanh", "identity"))
