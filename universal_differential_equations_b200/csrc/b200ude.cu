@@ -26,8 +26,8 @@ thread_local std::string g_create_error;
 //   K_LV32   LV 2 -> 32 -> 32 -> 2 tanh                      BASELINE config 2
 //   K_LV5Px  LV 2 -> 5 -> 5 -> 5 -> 2, per-layer activations, x trainable linear rates
 //            scenario_1.jl:62-73 (x=0), scenario_2.jl:79-98 (x=1), hudson_bay.jl:77-91 (x=2)
-//   K_GENERIC  any LV / SEIR / NODE form with chain widths <= 64 and <= 5 layers (k_generic.cu): functional
-//            coverage (seir_exposure.jl:114-130 shapes), not tuned
+//   K_GENERIC  any LV / SEIR / SEIR_NODE / NODE form with chain widths <= 64 and <= 5 layers (k_generic.cu): functional
+//            coverage (seir_exposure.jl:52-64,114-130 shapes), not tuned; also Vern7 and the adaptive path of untuned chains
 //   K_FKPP     Fisher-KPP UPDE: pointwise chain 1 -> ... -> 1 + 3-tap periodic stencil (Fisher-KPP-CNN.jl:111-126)
 //   K_SEIR64   SEIR exposure UDE 3 -> 64 -> 64 -> 1 tanh, tensor-core kernels (k_seir.cu)      BASELINE config 3
 //   K_FKPP16   Fisher-KPP UPDE with the 1 -> 16 -> 16 -> 1 tanh reaction chain (k_fkpp.cu)                BASELINE config 4

@@ -2,14 +2,19 @@
 //
 // The chain's 32 x 32 layer, evaluated for the 128 trajectories of a CTA, is a [128 x 32] x [32 x 32]
 // GEMM: exactly one tcgen05.mma tile (M = 128 = one trajectory per TMEM lane / per thread, N = 32, K = 32).
-// fp32 accuracy is kept with the 3xTF32 split  A_hi B_hi + A_lo B_hi + A_hi B_lo  (hi = round-to-nearest
-// TF32, lo = remainder): 12 UTCHMMA instructions per layer instead of 1024 FFMAs per trajectory,
-// measured max error 3.4e-6 on |D| <= 8 (profiles/r01_tcgen05_unit_test.txt).
+// fp32 accuracy is kept with the 3xTF32 split  A_hi B_hi + A_lo B_hi + A_hi B_lo  (weights: hi = round-to-nearest
+// TF32, lo = remainder, split once per launch; activations: the tensor core reads only the upper 19 bits of a tf32
+// operand, so the value itself is the hi operand and lo = x - trunc(x)): 12 UTCHMMA instructions per layer instead of
+// 1024 FFMAs per trajectory, measured max error 3.4e-6 on |D| <= 8 (profiles/r01_tcgen05_unit_test.txt).
 //   - A (the activations) never touches shared memory: every thread writes its own row straight into
 //     tensor memory (tcgen05.st, 32x32b) and reads its row of the accumulator back with tcgen05.ld;
 //   - B (weights, hi and lo) sits in shared memory in the canonical K-major no-swizzle layout;
 //   - one elected thread issues the MMAs and commits them to an mbarrier the CTA waits on.
-// TMEM per CTA: 128 columns (accumulator 32, A_hi 32, A_lo 32) -> four CTAs share an SM's 512 columns.
+// TMEM per CTA: 128 columns (accumulator 32, A_hi 32, A_lo 32, running dW2 sums of the adjoint 32) -> four CTAs share
+// an SM's 512 columns.
+// Kernels in this file: forward_kernel (fixed step), adaptive_forward_kernel (PI controller, saveat interpolation, step
+// record), adjoint_kernel<GEMM, ADAPT, DISC> (interpolating adjoint on the fixed grid / replay of an adaptive solve /
+// discrete adjoint; gradient GEMM on the FMA pipe or on mma.sync).
 #pragma once
 #include "lv32_packed.cuh"
 #include "ude_adjoint.cuh"

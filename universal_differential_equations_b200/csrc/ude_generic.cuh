@@ -2,7 +2,8 @@
 //
 // Functional coverage for every recognised UDE form whose chain has no specialised kernel: any dense chain
 // with widths <= 64 and <= 5 layers, models LV (0/1/2 trainable rates), SEIR (7 states, chain on
-// [S/N, I, D/N], SEIR_exposure/seir_exposure.jl:117-130) and NODE.  One trajectory per thread, weights read
+// [S/N, I, D/N], SEIR_exposure/seir_exposure.jl:117-130), SEIR_NODE (the script's black-box baseline, :52-64) and NODE;
+// also the adaptive Tsit5 forward / replay-adjoint kernels, the Vern7 forward kernels and the runtime-shape Fisher-KPP kernels.  One trajectory per thread, weights read
 // from the constant bank with runtime indices, activations in per-thread local arrays, Tsit5 forward with
 // dense output and the interpolating adjoint exactly as in the specialised kernels.  The ensemble-summed
 // parameter gradient is reduced deterministically: every contribution is summed over the warp's lanes with a
