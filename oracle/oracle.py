@@ -172,6 +172,41 @@ def adjoint_fixed(m, theta, out, dense, dt, n_steps, dLdout, save_every=1):
     return g, gu
 
 
+def rkc2_coefficients(s):
+    """RKC2 recurrence coefficients for s stages: dict(mt1, mu, nu, mt, ga, c, w, beta) (arrays indexed by stage)."""
+    arr = [np.zeros(s + 1) for _ in range(6)]
+    mt1, beta = C.c_double(0), C.c_double(0)
+    rc = lib().ude_rkc2_coefficients(s, C.byref(mt1), *[_p(a) for a in arr[:4]], _p(arr[4]), _p(arr[5]), C.byref(beta))
+    if rc != 0:
+        raise ValueError("2 <= s <= 64")
+    return dict(mt1=mt1.value, mu=arr[0], nu=arr[1], mt=arr[2], ga=arr[3], c=arr[4], w=arr[5][:s], beta=beta.value)
+
+
+def solve_rkc2(m, theta, u0, dt, n_steps, stages, save_every=1, want_record=False):
+    """Fixed-step RKC2 solve: out[n_save, d] (and the record (ustep, fstep)[n_steps+1, d] the adjoint reads)."""
+    suf, ct = _dt(theta.dtype)
+    u0 = np.ascontiguousarray(u0, dtype=theta.dtype)
+    out = np.empty((n_steps // save_every + 1, m.d), dtype=theta.dtype)
+    us = np.empty((n_steps + 1, m.d), dtype=theta.dtype)
+    fs = np.empty((n_steps + 1, m.d), dtype=theta.dtype)
+    rc = getattr(lib(), "ude_solve_rkc2_fixed" + suf)(C.byref(m), _p(np.ascontiguousarray(theta)), _p(u0), ct(dt), n_steps, stages,
+                                                      save_every, _p(out), _p(us), _p(fs))
+    if rc != 0:
+        raise FloatingPointError("oracle: RKC2 solve failed (%d)" % rc)
+    return (out, us, fs) if want_record else out
+
+
+def adjoint_rkc2(m, theta, ustep, fstep, dt, n_steps, stages, dLdout, save_every=1):
+    """Interpolating adjoint of an RKC2 solve (lambda stepped backwards with RKC2, u(t) by cubic Hermite): grad_theta, grad_u0."""
+    suf, ct = _dt(theta.dtype)
+    g = np.zeros(num_params(m), dtype=theta.dtype)
+    gu = np.empty(m.d, dtype=theta.dtype)
+    getattr(lib(), "ude_adjoint_rkc2_fixed" + suf)(C.byref(m), _p(np.ascontiguousarray(theta)), _p(np.ascontiguousarray(ustep)),
+                                                   _p(np.ascontiguousarray(fstep)), ct(dt), n_steps, stages, save_every,
+                                                   _p(np.ascontiguousarray(dLdout, dtype=theta.dtype)), _p(g), _p(gu))
+    return g, gu
+
+
 def adjoint_discrete(m, theta, out, dense, dt, n_steps, dLdout, save_every=1):
     """Exact gradient of the discrete fixed-step Tsit5 scheme (ForwardDiffSensitivity's result): grad_theta[P], grad_u0[d]."""
     suf, ct = _dt(theta.dtype)

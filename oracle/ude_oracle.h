@@ -110,6 +110,19 @@ double ude_ensemble_loss_grad_f64(const ude_model *m, const double *theta, const
                                   int n_steps, int save_every, double *out, double *grad_theta,
                                   double *grad_u0, int n_threads);
 
+/* RKC2 (second-order Runge-Kutta-Chebyshev, the closed-form ROCK2-class stabilised explicit method): fixed step, `stages`
+ * stages per step; ustep / fstep [n_steps+1][d] (u_n and f(u_n)) feed the cubic-Hermite dense output of the adjoint, which
+ * integrates lambda backwards with RKC2 itself.  grad_theta is ACCUMULATED. */
+int ude_rkc2_coefficients(int s, double *mt1, double *mu, double *nu, double *mt, double *ga, double *c, double *w, double *beta);
+int ude_solve_rkc2_fixed_f64(const ude_model *m, const double *theta, const double *u0, double dt, int n_steps, int stages,
+                             int save_every, double *out, double *ustep, double *fstep);
+void ude_adjoint_rkc2_fixed_f64(const ude_model *m, const double *theta, const double *ustep, const double *fstep, double dt,
+                                int n_steps, int stages, int save_every, const double *dLdout, double *grad_theta, double *grad_u0);
+int ude_solve_rkc2_fixed_f32(const ude_model *m, const float *theta, const float *u0, float dt, int n_steps, int stages,
+                             int save_every, float *out, float *ustep, float *fstep);
+void ude_adjoint_rkc2_fixed_f32(const ude_model *m, const float *theta, const float *ustep, const float *fstep, float dt,
+                                int n_steps, int stages, int save_every, const float *dLdout, float *grad_theta, float *grad_u0);
+
 /* ---- single precision (same semantics; state, parameters and arithmetic in float) ---- */
 void ude_mlp_forward_f32(const ude_model *m, const float *theta_chain, const float *x, float *y);
 void ude_rhs_f32(const ude_model *m, const float *theta, const float *u, float *du);

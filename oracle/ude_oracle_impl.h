@@ -459,6 +459,147 @@ int FN(ude_solve_adaptive)(const ude_model *m, const REAL *th, const REAL *u0, c
     return isave == n_save ? nacc : -1;
 }
 
+/* ------------------------------------------------ RKC2 (stabilised explicit) -- */
+/* Second-order Runge-Kutta-Chebyshev (Sommeijer, Shampine, Verwer 1998): the closed-form member of the family the
+ * north star names as ROCK2 (Climate/NeuralPDE/npde.jl:61,82; ROCK2's own coefficient tables are not in the reference).
+ * Per step with s stages:  Y0 = u, Y1 = Y0 + mt1 h F0,
+ *   Yj = (1 - mu_j - nu_j) Y0 + mu_j Y_{j-1} + nu_j Y_{j-2} + mt_j h F_{j-1} + ga_j h F0,  u_next = Y_s.
+ * Dense output = cubic Hermite on (u_n, f_n, u_{n+1}, f_{n+1}) (OrdinaryDiffEq's default interpolant for such methods).
+ * The interpolating adjoint integrates lambda backwards with the SAME scheme; mu never feeds back, so its update is a fixed
+ * linear combination h sum_k w_k G_k of the stage integrands, with w from running the recurrence on unit vectors. */
+#ifndef UDE_RKC_TABLES_DEFINED
+#define UDE_RKC_TABLES_DEFINED
+#define UDE_RKC_MAX_STAGES 64
+typedef struct {
+    int s;
+    double mt1;
+    double mu[UDE_RKC_MAX_STAGES + 1], nu[UDE_RKC_MAX_STAGES + 1], mt[UDE_RKC_MAX_STAGES + 1], ga[UDE_RKC_MAX_STAGES + 1];
+    double c[UDE_RKC_MAX_STAGES + 1];   /* stage abscissae, c[0] = 0, c[s] = 1 */
+    double w[UDE_RKC_MAX_STAGES + 1];   /* quadrature weights of the stage integrands F_0..F_{s-1} */
+    double beta;                        /* length of the real stability interval */
+} ude_rkc_tables;
+
+static void ude_rkc2_tables(int s, ude_rkc_tables *t)
+{
+    const double eps = 2.0 / 13.0;
+    const double w0 = 1.0 + eps / ((double)s * s);
+    double T[UDE_RKC_MAX_STAGES + 1], dT[UDE_RKC_MAX_STAGES + 1], d2T[UDE_RKC_MAX_STAGES + 1], b[UDE_RKC_MAX_STAGES + 1] = {0};
+    T[0] = 1; T[1] = w0; dT[0] = 0; dT[1] = 1; d2T[0] = 0; d2T[1] = 0;
+    for (int j = 2; j <= s; ++j) {
+        T[j] = 2 * w0 * T[j - 1] - T[j - 2];
+        dT[j] = 2 * T[j - 1] + 2 * w0 * dT[j - 1] - dT[j - 2];
+        d2T[j] = 4 * dT[j - 1] + 2 * w0 * d2T[j - 1] - d2T[j - 2];
+    }
+    const double w1 = dT[s] / d2T[s];
+    for (int j = 2; j <= s; ++j) b[j] = d2T[j] / (dT[j] * dT[j]);
+    b[0] = b[1] = b[2];
+    t->s = s;
+    t->mt1 = b[1] * w1;
+    t->beta = (w0 + 1.0) * d2T[s] / dT[s];
+    for (int j = 2; j <= s; ++j) {
+        t->mu[j] = 2 * b[j] * w0 / b[j - 1];
+        t->nu[j] = -b[j] / b[j - 2];
+        t->mt[j] = 2 * b[j] * w1 / b[j - 1];
+        t->ga[j] = -(1.0 - b[j - 1] * T[j - 1]) * t->mt[j];
+    }
+    /* abscissae and quadrature weights from the recurrence itself (y' = 1, and unit impulses in F_k) */
+    double W[UDE_RKC_MAX_STAGES + 1][UDE_RKC_MAX_STAGES + 1];
+    memset(W, 0, sizeof W);
+    t->c[0] = 0; t->c[1] = t->mt1;
+    W[1][0] = t->mt1;
+    for (int j = 2; j <= s; ++j) {
+        t->c[j] = t->mu[j] * t->c[j - 1] + t->nu[j] * t->c[j - 2] + t->mt[j] + t->ga[j];
+        for (int k = 0; k < j; ++k) W[j][k] = t->mu[j] * W[j - 1][k] + t->nu[j] * W[j - 2][k];
+        W[j][j - 1] += t->mt[j];
+        W[j][0] += t->ga[j];
+    }
+    for (int k = 0; k < s; ++k) t->w[k] = W[s][k];
+}
+
+int ude_rkc2_coefficients(int s, double *mt1, double *mu, double *nu, double *mt, double *ga, double *c, double *w, double *beta)
+{
+    if (s < 2 || s > UDE_RKC_MAX_STAGES) return -1;
+    ude_rkc_tables t;
+    ude_rkc2_tables(s, &t);
+    *mt1 = t.mt1; *beta = t.beta;
+    for (int j = 0; j <= s; ++j) { mu[j] = j >= 2 ? t.mu[j] : 0; nu[j] = j >= 2 ? t.nu[j] : 0; mt[j] = j >= 2 ? t.mt[j] : 0; ga[j] = j >= 2 ? t.ga[j] : 0; c[j] = t.c[j]; w[j] = j < s ? t.w[j] : 0; }
+    return 0;
+}
+#endif
+
+/* forward: out[n_save][d]; ustep[n_steps+1][d] and fstep[n_steps+1][d] (f(u_n)) are the record the adjoint reads */
+int FN(ude_solve_rkc2_fixed)(const ude_model *m, const REAL *th, const REAL *u0, REAL dt, int n_steps, int stages,
+                             int save_every, REAL *out, REAL *ustep, REAL *fstep)
+{
+    if (stages < 2 || stages > UDE_RKC_MAX_STAGES) return -2;
+    ude_rkc_tables t;
+    ude_rkc2_tables(stages, &t);
+    const int d = m->d, s = stages;
+    REAL u[UDE_MAX_STATE], F0[UDE_MAX_STATE], F[UDE_MAX_STATE], Y0[UDE_MAX_STATE], Y1[UDE_MAX_STATE], Y2[UDE_MAX_STATE];
+    for (int k = 0; k < d; ++k) u[k] = u0[k];
+    for (int k = 0; k < d; ++k) out[k] = u[k];
+    int isave = 1;
+    for (int n = 0; n < n_steps; ++n) {
+        FN(ude_rhs)(m, th, u, F0);
+        if (ustep) for (int k = 0; k < d; ++k) { ustep[(size_t)n * d + k] = u[k]; fstep[(size_t)n * d + k] = F0[k]; }
+        for (int k = 0; k < d; ++k) { Y0[k] = u[k]; Y1[k] = u[k] + (REAL)t.mt1 * dt * F0[k]; }
+        for (int j = 2; j <= s; ++j) {
+            FN(ude_rhs)(m, th, Y1, F);
+            const REAL mu = (REAL)t.mu[j], nu = (REAL)t.nu[j], mt = (REAL)t.mt[j], ga = (REAL)t.ga[j];
+            for (int k = 0; k < d; ++k) Y2[k] = ((REAL)1 - mu - nu) * u[k] + mu * Y1[k] + nu * Y0[k] + mt * dt * F[k] + ga * dt * F0[k];
+            for (int k = 0; k < d; ++k) { Y0[k] = Y1[k]; Y1[k] = Y2[k]; }
+        }
+        for (int k = 0; k < d; ++k) u[k] = Y1[k];
+        if ((n + 1) % save_every == 0) {
+            for (int k = 0; k < d; ++k) out[(size_t)isave * d + k] = u[k];
+            ++isave;
+        }
+        if (!FN(all_finite)(u, d)) return -1;
+    }
+    if (ustep) {
+        FN(ude_rhs)(m, th, u, F0);
+        for (int k = 0; k < d; ++k) { ustep[(size_t)n_steps * d + k] = u[k]; fstep[(size_t)n_steps * d + k] = F0[k]; }
+    }
+    return 0;
+}
+
+/* interpolating adjoint of an RKC2 solve: lambda stepped backwards with RKC2 itself, u(t) by cubic Hermite */
+void FN(ude_adjoint_rkc2_fixed)(const ude_model *m, const REAL *th, const REAL *ustep, const REAL *fstep, REAL dt, int n_steps,
+                                int stages, int save_every, const REAL *dLdout, REAL *grad_theta, REAL *grad_u0)
+{
+    ude_rkc_tables t;
+    ude_rkc2_tables(stages, &t);
+    const int d = m->d, s = stages;
+    REAL lam[UDE_MAX_STATE], x[UDE_MAX_STATE], F0[UDE_MAX_STATE], F[UDE_MAX_STATE], Y0[UDE_MAX_STATE], Y1[UDE_MAX_STATE], Y2[UDE_MAX_STATE];
+    const int n_save = n_steps / save_every + 1;
+    for (int k = 0; k < d; ++k) lam[k] = dLdout[(size_t)(n_save - 1) * d + k];
+    for (int n = n_steps - 1; n >= 0; --n) {
+        const REAL *y0 = ustep + (size_t)n * d, *y1 = ustep + (size_t)(n + 1) * d, *f0 = fstep + (size_t)n * d, *f1 = fstep + (size_t)(n + 1) * d;
+        /* stage k of the backward step sits at t_{n+1} - c_k dt, i.e. Theta = 1 - c_k of the forward step */
+        for (int j = 0; j < s; ++j) {
+            const REAL Th = (REAL)1 - (REAL)t.c[j];
+            for (int k = 0; k < d; ++k)
+                x[k] = ((REAL)1 - Th) * y0[k] + Th * y1[k]
+                     + Th * (Th - (REAL)1) * (((REAL)1 - (REAL)2 * Th) * (y1[k] - y0[k]) + (Th - (REAL)1) * dt * f0[k] + Th * dt * f1[k]);
+            const REAL *Yj = j == 0 ? lam : Y1;
+            REAL *Fj = j == 0 ? F0 : F;
+            FN(ude_rhs_vjp)(m, th, x, Yj, Fj, grad_theta, dt * (REAL)t.w[j]);
+            if (j == 0) {
+                for (int k = 0; k < d; ++k) { Y0[k] = lam[k]; Y1[k] = lam[k] + (REAL)t.mt1 * dt * F0[k]; }
+            } else {
+                const int jj = j + 1;   /* F = G(Y_j) feeds Y_{j+1} */
+                const REAL mu = (REAL)t.mu[jj], nu = (REAL)t.nu[jj], mt = (REAL)t.mt[jj], ga = (REAL)t.ga[jj];
+                for (int k = 0; k < d; ++k) Y2[k] = ((REAL)1 - mu - nu) * lam[k] + mu * Y1[k] + nu * Y0[k] + mt * dt * F[k] + ga * dt * F0[k];
+                for (int k = 0; k < d; ++k) { Y0[k] = Y1[k]; Y1[k] = Y2[k]; }
+            }
+        }
+        for (int k = 0; k < d; ++k) lam[k] = Y1[k];
+        if (n % save_every == 0)
+            for (int k = 0; k < d; ++k) lam[k] += dLdout[(size_t)(n / save_every) * d + k];
+    }
+    for (int k = 0; k < d; ++k) grad_u0[k] = lam[k];
+}
+
 /* ------------------------------------------------ discrete adjoint ---------- */
 /* Exact gradient of the DISCRETE fixed-step Tsit5 scheme (what ForwardDiffSensitivity, scenario_1.jl:86 /
  * scenario_2.jl:108 / hudson_bay.jl:102, computes in forward mode -- here by reverse accumulation through the

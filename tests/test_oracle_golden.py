@@ -240,3 +240,44 @@ def test_replay_adjoint_matches_error_controlled_backward_solve(O, golden):
         assert nback > rec[3]                      # the backward solve takes its own (more) steps
         assert n(g_rep - g_ada) < bound * n(g_ada) and n(g_rep - g_true) < bound * n(g_true)
         assert n(gu_rep - gu_ada) < bound * n(gu_ada)
+
+
+def test_rkc2_oracle_coefficients_convergence_and_adjoint(O):
+    """RKC2 (second-order Runge-Kutta-Chebyshev; the closed-form ROCK2-class stabilised explicit method, north star /
+    Climate/NeuralPDE/npde.jl:61): recurrence coefficients are consistent (c_s = 1, sum w = 1, sum w c = 1/2, stability
+    interval ~ 0.65 s^2), the forward solve of the stiff Fisher-KPP grid converges with order 2 towards Tsit5, and the
+    interpolating adjoint (lambda stepped backwards by RKC2, cubic-Hermite dense output) converges with order 2 to the
+    Tsit5 interpolating-adjoint gradient."""
+    from helpers import glorot_theta
+    for s in (2, 5, 16, 64):
+        c = O.rkc2_coefficients(s)
+        assert abs(c["c"][s] - 1) < 1e-12 and abs(c["w"].sum() - 1) < 1e-12 and abs((c["w"] * c["c"][:s]).sum() - 0.5) < 1e-12
+        assert 0.45 * s * s < c["beta"] < 0.67 * s * s + 1   # -> 0.65 s^2 for large s (1.96 at s = 2)
+    Nx = 64
+    widths = (1, 16, 16, 1)
+    m = O.fkpp_model(Nx, widths, ("tanh", "tanh", "identity"))
+    D0 = 0.01 * (Nx - 1) ** 2
+    th = np.concatenate([glorot_theta(widths, seed=3), [1.0, -2.0, 1.0, 0.0, D0]]).astype(np.float64)
+    x = np.linspace(0, 1, Nx)
+    u0 = 0.5 * (np.tanh((x - 0.35) / 0.05) - np.tanh((x - 0.65) / 0.05))
+    y = np.tile(u0[None], (6, 1)) * 0.9
+
+    def tsit(dt):
+        n = int(round(1.0 / dt))
+        out, dense = O.solve_fixed(m, th, u0, dt, n, save_every=n // 5, want_dense=True)
+        g, gu = O.adjoint_fixed(m, th, out, dense, dt, n, 2 * (out - y), save_every=n // 5)
+        return out, g, gu
+    ref, g_ref, gu_ref = tsit(2e-3)
+    errs, gerrs = [], []
+    for dt, s in ((0.05, 6), (0.025, 5), (0.0125, 4)):
+        n = int(round(1.0 / dt))
+        assert O.rkc2_coefficients(s)["beta"] > dt * (4 * D0 + 2)          # inside the stability interval
+        out, us, fs = O.solve_rkc2(m, th, u0, dt, n, s, save_every=n // 5, want_record=True)
+        g, gu = O.adjoint_rkc2(m, th, us, fs, dt, n, s, 2 * (out - y), save_every=n // 5)
+        errs.append(np.abs(out - ref).max())
+        gerrs.append(np.linalg.norm(g - g_ref) / np.linalg.norm(g_ref))
+    assert errs[0] < 1e-4 and errs[1] < errs[0] / 2.5 and errs[2] < errs[1] / 2.5
+    assert gerrs[0] < 1e-3 and gerrs[1] < gerrs[0] / 3 and gerrs[2] < gerrs[1] / 3
+    # Tsit5 itself is unstable at these steps: dt * rho = 8 > 3.3
+    with pytest.raises(FloatingPointError):
+        O.solve_fixed(m, th, u0, 0.05, 20)
