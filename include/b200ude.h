@@ -71,6 +71,10 @@ extern "C" {
 /* solver (OrdinaryDiffEq algorithm the reference passes to solve/concrete_solve) */
 #define B200UDE_TSIT5 0
 #define B200UDE_VERN7 1
+#define B200UDE_RKC2 2 /* second-order Runge-Kutta-Chebyshev with desc.n_stages stages per step: the closed-form stabilised explicit
+                          method of the class of ROCK2 (Climate/NeuralPDE/npde.jl:61,82; ROCK2's own coefficient tables are not in the
+                          reference); real stability interval ~ 0.65 n_stages^2; dense output = cubic Hermite; the interpolating
+                          adjoint steps lambda backwards with RKC2 itself.  Fisher-KPP UPDE (1-16-16-1 chain, even grids), fixed step */
 
 /* sensealg */
 #define B200UDE_INTERPOLATING_ADJOINT 0 /* InterpolatingAdjoint(autojacvec = ReverseDiffVJP())  seir_exposure.jl:71,140 */
@@ -115,7 +119,7 @@ typedef struct b200ude_desc {
     int32_t n_suffix;     /* trainable scalars after the chain in theta */
     int32_t n_consts;
     double consts[16];    /* fixed physics constants */
-    int32_t solver;       /* B200UDE_TSIT5 | B200UDE_VERN7 */
+    int32_t solver;       /* B200UDE_TSIT5 | B200UDE_VERN7 | B200UDE_RKC2 */
     int32_t sensealg;     /* B200UDE_INTERPOLATING_ADJOINT | B200UDE_DISCRETE_ADJOINT */
     double t0;            /* tspan[1] */
     double dt;            /* fixed step (adaptive = false); saveat = t0 + i*save_every*dt */
@@ -129,7 +133,7 @@ typedef struct b200ude_desc {
     int32_t adaptive;   /* 0: fixed step dt (adaptive = false). 1: Tsit5 with OrdinaryDiffEq's PI controller, abstol / reltol;
                            saveat = t0 + i*save_every*dt, i = 0..n_steps/save_every (dt only defines the save grid) */
     int32_t max_steps;  /* adaptive: capacity of ACCEPTED steps per trajectory (status 2 when exceeded) */
-    uint32_t reserved;
+    int32_t n_stages;   /* B200UDE_RKC2: stages per step (2..64); choose dt * spectral_radius <= 0.65 n_stages^2.  0 otherwise */
 } b200ude_desc;
 
 int32_t b200ude_version(void);

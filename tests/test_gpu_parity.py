@@ -810,3 +810,44 @@ def test_two_devices_in_one_process_interleaved():
         assert np.array_equal(r[0], res[0][0]) and r[1] == res[0][1] and np.array_equal(r[2], res[0][2])
     for sv in solvers:
         sv.close()
+
+
+@pytest.mark.parametrize("nx,N,stages,dt,n_steps", [(64, 9, 6, 0.05, 20), (256, 3, 8, 0.0125, 16)])
+def test_rkc2_stabilised_solver_fisher_kpp_vs_oracle(O, nx, N, stages, dt, n_steps):
+    """solver = RKC2 (the closed-form ROCK2-class stabilised explicit method; ROCK2(eigen_est) in the reference's stiff PDE
+    script, Climate/NeuralPDE/npde.jl:61) on the stiff Fisher-KPP grid at steps where Tsit5 is unstable (dt * rho = 8 / 33 vs
+    its limit 3.3): forward solve, fused-L2 loss, interpolating adjoint (lambda stepped backwards by RKC2, cubic-Hermite dense
+    output) against the oracle's RKC2 path, which converges with order 2 to the Tsit5 results (tests/test_oracle_golden.py)."""
+    ude = _ude()
+    rng = np.random.default_rng(nx)
+    widths = (1, 16, 16, 1)
+    layers = [ude.FastDense(1, 16, ude.tanh), ude.FastDense(16, 16, ude.tanh), ude.FastDense(16, 1)]
+    f = ude.FisherKPPUDE(ude.FastChain(*layers), nx)
+    D0 = 0.01 * (nx - 1) ** 2
+    theta = np.concatenate([glorot_theta(widths, seed=3), [1.0, -2.0, 1.0, 0.0, D0]]).astype(np.float32)
+    x = np.linspace(0, 1, nx)
+    u0 = np.stack([0.5 * (np.tanh((x - (0.5 - d / 2)) / 0.05) - np.tanh((x - (0.5 + d / 2)) / 0.05)) for d in rng.uniform(0.15, 0.5, N)], axis=1).astype(np.float32)
+    every = n_steps // 4
+    y = (0.9 * np.repeat(u0[None], 5, axis=0)).astype(np.float32)
+    alg = ude.ROCK2(stages=stages)
+    assert ude.ROCK2(eigen_est=4 * D0 + 2).n_stages(dt) <= stages        # the requested stage count covers dt * rho
+    solver = ude.UDESolver(f, 0.0, dt, n_steps, every, max_trajectories=N, alg=alg)
+    out, loss, g, gu, status = _run(solver, theta, u0, y)
+    assert (status == 0).all()
+    m = O.fkpp_model(nx, widths, ("tanh", "tanh", "identity"))
+    th64 = theta.astype(np.float64)
+    l_ref, g_ref, gu_ref, o_ref = 0.0, np.zeros(theta.size), np.zeros((nx, N)), np.zeros((5, nx, N))
+    for k in range(N):
+        o, us, fs = O.solve_rkc2(m, th64, u0[:, k].astype(np.float64), dt, n_steps, stages, save_every=every, want_record=True)
+        r = o - y[:, :, k]
+        gk, guk = O.adjoint_rkc2(m, th64, us, fs, dt, n_steps, stages, 2 * r, save_every=every)
+        l_ref += (r ** 2).sum(); g_ref += gk; gu_ref[:, k] = guk; o_ref[:, :, k] = o
+    assert np.abs(out - o_ref).max() <= 1e-4 * (1 + np.abs(o_ref).max())
+    assert abs(loss - l_ref) <= 1e-3 * abs(l_ref)
+    assert np.linalg.norm(g - g_ref) <= 5e-3 * np.linalg.norm(g_ref)
+    assert np.abs(gu - gu_ref).max() <= 5e-3 * np.abs(gu_ref).max()
+    # Tsit5 at the same step is far outside its stability region
+    s5 = ude.UDESolver(f, 0.0, dt, n_steps, every, max_trajectories=N)
+    o5, st5 = s5.solve_host(theta, u0)
+    assert (st5 != 0).any() or np.abs(o5).max() > 1e3
+    solver.close(); s5.close()

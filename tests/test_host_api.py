@@ -95,3 +95,17 @@ def test_sciml_train_bfgs_and_callback_halt():
     got = []
     ude.sciml_train(lambda th: (loss(th), "pred"), np.zeros(2, np.float32), ude.ADAM(0.05), cb=lambda th, l, pred: got.append(pred) or True, maxiters=5)
     assert got == ["pred"]
+
+
+def test_rock2_stage_selection_from_eigen_est():
+    """ROCK2(eigen_est = rho) picks the smallest RKC2 stage count whose real stability interval covers 1.05 dt rho."""
+    from universal_differential_equations_b200.sciml import _rkc2_beta
+    assert abs(_rkc2_beta(2) - 1.9629629629629626) < 1e-12 and 0.64 * 64 * 64 < _rkc2_beta(64) < 0.66 * 64 * 64
+    for dt, rho in ((0.0125, 2603.0), (0.05, 160.8), (0.1, 2603.0)):
+        s = ude.ROCK2(eigen_est=rho).n_stages(dt)
+        assert _rkc2_beta(s) >= 1.05 * dt * rho and (s == 2 or _rkc2_beta(s - 1) < 1.05 * dt * rho)
+    assert ude.ROCK2(stages=7).n_stages(0.3) == 7
+    with pytest.raises(ValueError):
+        ude.ROCK2().n_stages(0.1)
+    with pytest.raises(ValueError):
+        ude.ROCK2(eigen_est=1e9).n_stages(1.0)

@@ -17,7 +17,7 @@ ABI_VERSION = 1
 F32, F64 = 0, 1
 MODEL_LV, MODEL_SEIR, MODEL_FKPP, MODEL_NODE, MODEL_SEIR_NODE = 0, 1, 2, 3, 4
 ACT_IDENTITY, ACT_TANH, ACT_RBF = 0, 1, 2
-TSIT5, VERN7 = 0, 1
+TSIT5, VERN7, RKC2 = 0, 1, 2
 INTERPOLATING_ADJOINT, DISCRETE_ADJOINT = 0, 1
 HOST, DEVICE = 0, 1
 FLAG_APPROX_TANH = 1
@@ -47,7 +47,7 @@ class Desc(C.Structure):
         ("abstol", C.c_double), ("reltol", C.c_double),
         ("n_loss_weights", C.c_int32), ("loss_weights", C.c_double * 16),
         ("max_trajectories", C.c_uint64), ("flags", C.c_uint32), ("adaptive", C.c_int32), ("max_steps", C.c_int32),
-        ("reserved", C.c_uint32),
+        ("n_stages", C.c_int32),
     ]
 
 

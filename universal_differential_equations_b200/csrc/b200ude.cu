@@ -81,6 +81,7 @@ struct b200ude_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-buffer path: the data upload overlaps the forward kernel
     cudaEvent_t data_ready = nullptr;
+    RkcHost rkc;                    // solver = B200UDE_RKC2: recurrence tables for desc.n_stages
     // fused reduce + all-reduce over NVLink peer memory (b200ude_peer_*)
     void *d_peer_buf = nullptr;     // this rank's exchange buffer (cudaMalloc, exported with CUDA IPC)
     PeerLinks peer;                 // every rank's buffer as mapped here
@@ -123,6 +124,45 @@ cudaError_t dalloc(b200ude_handle *h, T **p, size_t count)
     cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
     if (e == cudaSuccess) h->dev_bytes += count * sizeof(T);
     return e;
+}
+
+// RKC2 (Sommeijer, Shampine, Verwer 1998) recurrence coefficients, stage abscissae and the quadrature weights of the stage
+// integrands (from running the recurrence on unit impulses)
+void rkc2_tables(int s, RkcHost *out)
+{
+    const double eps = 2.0 / 13.0, w0 = 1.0 + eps / ((double)s * s);
+    double T[65], dT[65], d2T[65], b[65] = {0}, mu[65] = {0}, nu[65] = {0}, mt[65] = {0}, ga[65] = {0}, c[65] = {0};
+    static double W[65][65];
+    T[0] = 1; T[1] = w0; dT[0] = 0; dT[1] = 1; d2T[0] = 0; d2T[1] = 0;
+    for (int j = 2; j <= s; ++j) {
+        T[j] = 2 * w0 * T[j - 1] - T[j - 2];
+        dT[j] = 2 * T[j - 1] + 2 * w0 * dT[j - 1] - dT[j - 2];
+        d2T[j] = 4 * dT[j - 1] + 2 * w0 * d2T[j - 1] - d2T[j - 2];
+    }
+    const double w1 = dT[s] / d2T[s];
+    for (int j = 2; j <= s; ++j) b[j] = d2T[j] / (dT[j] * dT[j]);
+    b[0] = b[1] = b[2];
+    const double mt1 = b[1] * w1;
+    for (int j = 2; j <= s; ++j) {
+        mu[j] = 2 * b[j] * w0 / b[j - 1];
+        nu[j] = -b[j] / b[j - 2];
+        mt[j] = 2 * b[j] * w1 / b[j - 1];
+        ga[j] = -(1.0 - b[j - 1] * T[j - 1]) * mt[j];
+    }
+    memset(W, 0, sizeof W);
+    c[0] = 0; c[1] = mt1; W[1][0] = mt1;
+    for (int j = 2; j <= s; ++j) {
+        c[j] = mu[j] * c[j - 1] + nu[j] * c[j - 2] + mt[j] + ga[j];
+        for (int k = 0; k < j; ++k) W[j][k] = mu[j] * W[j - 1][k] + nu[j] * W[j - 2][k];
+        W[j][j - 1] += mt[j];
+        W[j][0] += ga[j];
+    }
+    *out = RkcHost();
+    out->s = s; out->mt1 = (float)mt1;
+    for (int j = 0; j <= s; ++j) {
+        out->mu[j] = (float)mu[j]; out->nu[j] = (float)nu[j]; out->mt[j] = (float)mt[j]; out->ga[j] = (float)ga[j]; out->c[j] = (float)c[j];
+        out->w[j] = j < s ? (float)W[s][j] : 0.0f;
+    }
 }
 
 int env_int(const char *name, int dflt)
@@ -182,6 +222,10 @@ int32_t tsit5_forward(b200ude_handle *h, const float *u0, size_t N, float *out, 
             : h->kid == K_SEIR64 ? launch_fwd_seir_adaptive(h->var, h->tab, p, h->ag, st) : launch_fwd_adaptive(h->gen, h->tab, p, h->ag, st);
         CUDA_TRY(h, e);
         h->last_out = out;
+        return B200UDE_OK;
+    }
+    if (h->desc.solver == B200UDE_RKC2) {
+        CUDA_TRY(h, launch_fwd_fkpp16_rkc(h->var, h->tab, h->rkc, p, h->D, st));
         return B200UDE_OK;
     }
     switch (h->kid) {
@@ -263,6 +307,12 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
         else CUDA_TRY(h, launch_adj_adaptive(h->gen, h->tab, p, h->ag, st, &grid));
         CUDA_TRY(h, launch_reduce(h->d_partial, grid, h->P + 1, grad_theta, loss, st));
         if (l2 && loss) CUDA_TRY(h, launch_l2_finish(h->d_block_loss, loss, st));
+        return B200UDE_OK;
+    }
+    if (h->desc.solver == B200UDE_RKC2) {
+        CUDA_TRY(h, launch_adj_fkpp16_rkc(h->var, h->tab, h->rkc, p, h->D, st, &grid));
+        if (peer) CUDA_TRY(h, launch_reduce_exchange(h->d_partial, grid, h->P + 1, h->peer, grad_theta, loss, st));
+        else CUDA_TRY(h, launch_reduce(h->d_partial, grid, h->P + 1, grad_theta, loss, st));
         return B200UDE_OK;
     }
     switch (h->kid) {
@@ -381,7 +431,8 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         return fail(nullptr, B200UDE_EINVAL, "create: struct_size %u != %zu (ABI mismatch)", d->struct_size, sizeof(b200ude_desc));
     if (d->dtype != B200UDE_F32) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only B200UDE_F32 kernels exist in this build");
     if (d->n_layers < 1 || d->n_layers > B200UDE_MAX_LAYERS) return fail(nullptr, B200UDE_EINVAL, "create: n_layers=%d out of range", d->n_layers);
-    if (d->solver != B200UDE_TSIT5 && d->solver != B200UDE_VERN7) return fail(nullptr, B200UDE_EINVAL, "create: unknown solver %d", d->solver);
+    if (d->solver != B200UDE_TSIT5 && d->solver != B200UDE_VERN7 && d->solver != B200UDE_RKC2)
+        return fail(nullptr, B200UDE_EINVAL, "create: unknown solver %d", d->solver);
     if (d->sensealg != B200UDE_INTERPOLATING_ADJOINT && d->sensealg != B200UDE_DISCRETE_ADJOINT)
         return fail(nullptr, B200UDE_EUNSUPPORTED, "create: unknown sensealg %d", d->sensealg);
     if (!(d->dt > 0) || d->n_steps < 1 || d->save_every < 1 || d->n_steps % d->save_every != 0)
@@ -401,6 +452,12 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
             return fail(nullptr, B200UDE_EUNSUPPORTED, "create: adaptive stepping is implemented for the LV / SEIR / NODE forms (chain widths <= 64)");
         // adaptive solves run on the runtime-shape kernels, except the headline chain (tensor-core kernels with CTA-uniform attempt loops)
         if (!((kid == K_LV32 || kid == K_SEIR64) && d->solver == B200UDE_TSIT5 && env_int("B200UDE_ADAPTIVE_TC", 1))) kid = K_GENERIC;
+    }
+    if (d->solver == B200UDE_RKC2) {
+        if (d->n_stages < 2 || d->n_stages > 64) return fail(nullptr, B200UDE_EINVAL, "create: RKC2 needs 2 <= n_stages <= 64 (stability interval ~ 0.65 n_stages^2 >= dt * spectral radius)");
+        if (kid != K_FKPP16 || d->state_dim % 2 != 0 || d->adaptive || d->sensealg != B200UDE_INTERPOLATING_ADJOINT || !env_int("B200UDE_FKPP_PACKED", 1))
+            return fail(nullptr, B200UDE_EUNSUPPORTED,
+                        "create: RKC2 has kernels for the Fisher-KPP UPDE with the 1-16-16-1 chain on even grids (fixed step, interpolating adjoint)");
     }
     if (d->sensealg == B200UDE_DISCRETE_ADJOINT &&
         (d->adaptive || d->solver != B200UDE_TSIT5 || !(kid == K_LV32 || kid == K_LV5P0 || kid == K_LV5P1 || kid == K_LV5P2)))
@@ -443,6 +500,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     }
     h->var.approx_tanh = (d->flags & B200UDE_FLAG_APPROX_TANH) ? 1 : 0;
     h->var.discrete = d->sensealg == B200UDE_DISCRETE_ADJOINT ? 1 : 0;
+    if (d->solver == B200UDE_RKC2) rkc2_tables(d->n_stages, &h->rkc);
     // tuning knobs for experiments (defaults are the measured-best variant)
     h->var.fwd_smem = env_int("B200UDE_FWD_SMEM", 0);
     h->var.fwd_T = env_int("B200UDE_FWD_T", 1) == 2 ? 2 : 1;

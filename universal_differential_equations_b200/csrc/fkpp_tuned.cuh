@@ -537,6 +537,85 @@ __global__ void __launch_bounds__(256) forward_kernel2(FwdParams p, Geom geo)
     }
 }
 
+// ---- RKC2 (second-order Runge-Kutta-Chebyshev): the closed-form stabilised explicit method of the ROCK2 class the north star
+// names for this stiff grid (Climate/NeuralPDE/npde.jl:61; ROCK2's own tables are not in the reference).  Recurrence per step:
+//   Y0 = u, Y1 = u + mt1 h F0,  Yj = (1 - mu_j - nu_j) u + mu_j Y_{j-1} + nu_j Y_{j-2} + mt_j h F_{j-1} + ga_j h F0,  u_next = Y_s.
+// The coefficient tables are computed on the host (b200ude.cu) for the handle's stage count.
+struct RkcTables {
+    int s;
+    float mt1;
+    float mu[65], nu[65], mt[65], ga[65], c[65], w[65];
+};
+static __constant__ RkcTables c_rkc;
+
+template <int H, int TM>
+__global__ void __launch_bounds__(256) forward_rkc_kernel2(FwdParams p, Geom geo)
+{
+    using O = Off<H>;
+    extern __shared__ __align__(16) float s_dyn[];
+    float2 *sX = reinterpret_cast<float2 *>(s_dyn);
+    const int Nx = geo.Nx, Nh = Nx >> 1, slots = geo.tpc * Nh;
+    const int slot = threadIdx.x;
+    const bool valid = slot < slots;
+    const int t_loc = valid ? slot / Nh : 0, q = valid ? slot % Nh : 0;
+    const int base = t_loc * Nh;
+    const int im = base + (q + Nh - 1) % Nh, ip = base + (q + 1) % Nh;
+    const int i0 = 2 * q;
+    const int traj = blockIdx.x * geo.tpc + t_loc;
+    const bool live = valid && traj < p.N;
+    const size_t N = (size_t)p.N, n = (size_t)(live ? traj : p.N - 1);
+    const float dt = p.dt;
+    const float w1 = c_theta[O::SX], w2 = c_theta[O::SX + 1], w3 = c_theta[O::SX + 2], D0 = c_theta[O::SX + 4];
+    float2 u = make_float2(__ldg(p.u0 + (size_t)i0 * N + n), __ldg(p.u0 + (size_t)(i0 + 1) * N + n));
+    int flip = 0;
+    auto rhs = [&](float2 g, int zsel) {
+        float2 *sU = sX + flip * slots;
+        flip ^= 1;
+        if (valid) sU[slot] = g;
+        __syncthreads();
+        const float gl = sU[im].y, gr = sU[ip].x;
+        const float2 y = chain_value2<H, TM>(g, zsel);
+        return make_float2(fmaf(D0, fmaf(w1, gl, fmaf(w2, g.x, w3 * g.y)), y.x), fmaf(D0, fmaf(w1, g.x, fmaf(w2, g.y, w3 * gr)), y.y));
+    };
+    auto store_int = [&](float *b, int row, float2 v) { if (live) *reinterpret_cast<float2 *>(&b[((size_t)row * N + n) * Nx + i0]) = v; };
+    auto store_abi = [&](float *b, int row, float2 v) {
+        if (live) { b[((size_t)row * Nx + i0) * N + n] = v.x; b[((size_t)row * Nx + i0 + 1) * N + n] = v.y; }
+    };
+    store_abi(p.out, 0, u);
+    store_int(p.ustep, 0, u);
+    const int S = c_rkc.s;
+    int isave = 1;
+#pragma unroll 1
+    for (int s = 0; s < p.n_steps; ++s) {
+        const float2 F0 = rhs(u, 0);
+        store_int(p.dense, s, F0);   // row s of the record = f(u_s): with u_s, u_{s+1}, f(u_{s+1}) the cubic-Hermite dense output
+        float2 Y0 = u, Y1 = fma2(bc(c_rkc.mt1 * dt), F0, u);
+#pragma unroll 1
+        for (int j = 2; j <= S; ++j) {
+            const float2 F = rhs(Y1, j);
+            const float mu = c_rkc.mu[j], nu = c_rkc.nu[j], mt = c_rkc.mt[j], ga = c_rkc.ga[j];
+            const float2 Y2 = fma2(bc(ga * dt), F0, fma2(bc(mt * dt), F, fma2(bc(nu), Y0, fma2(bc(mu), Y1, mul2(bc(1.0f - mu - nu), u)))));
+            Y0 = Y1;
+            Y1 = Y2;
+        }
+        u = Y1;
+        store_int(p.ustep, s + 1, u);
+        if ((s + 1) % p.save_every == 0) { store_abi(p.out, isave, u); ++isave; }
+    }
+    store_int(p.dense, p.n_steps, rhs(u, 0));
+    if (p.status) {
+        __syncthreads();
+        float *sU = s_dyn;
+        if (valid) sU[slot] = ((fabsf(u.x) <= 3.0e38f) && (fabsf(u.y) <= 3.0e38f)) ? 0.0f : 1.0f;
+        __syncthreads();
+        if (live && q == 0) {
+            float any = 0.0f;
+            for (int r = 0; r < Nh; ++r) any += sU[base + r];
+            p.status[n] = any > 0.0f ? 1 : 0;
+        }
+    }
+}
+
 template <int H>
 struct __align__(16) WarpRows2 {
     static constexpr int LD = H + 4;
@@ -544,7 +623,7 @@ struct __align__(16) WarpRows2 {
     float A[64 * LD];   // h1 rows
 };
 
-template <int H, int TM>
+template <int H, int TM, bool RKC = false>
 __global__ void __launch_bounds__(256) adjoint_kernel2(AdjParams p, Geom geo)
 {
     using O = Off<H>;
@@ -598,6 +677,105 @@ __global__ void __launch_bounds__(256) adjoint_kernel2(AdjParams p, Geom geo)
     const int n_save = p.n_steps / p.save_every + 1;
     jump(n_save - 1);
     int flip = 0;
+    // One evaluation at state x (two adjacent grid points), cotangent g: returns kn = (df/du)^T g and accumulates the theta-gradient
+    // terms with quadrature weight sc (isc = 1 / sc).
+    auto eval_core = [&](float2 x, float2 g, float sc, float isc, int zsel) -> float2 {
+        const int zb = lv32::c_zero[zsel & 7] << 2;
+        float4 *sx = sX + flip * slots;
+        flip ^= 1;
+        if (valid) sx[slot] = make_float4(x.x, x.y, g.x, g.y);
+        __syncthreads();
+        const float4 nm = sx[im], np = sx[ip];   // left neighbour thread: its .y / .w border this thread's first point
+        const float xl = nm.y, gl = nm.w, xr = np.x, gr = np.z;
+        const float2 sg = mul2(bc(lv * sc), g);
+        // ---- chain forward, activations kept ----
+        float2 h1[H], v[H];
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4) {
+            const float4 w = ldw4(zb + O::W1 + j4), b = ldw4(zb + O::B1 + j4);
+            h1[j4 + 0] = tanh2<TM>(fma2(bc(w.x), x, bc(b.x)));
+            h1[j4 + 1] = tanh2<TM>(fma2(bc(w.y), x, bc(b.y)));
+            h1[j4 + 2] = tanh2<TM>(fma2(bc(w.z), x, bc(b.z)));
+            h1[j4 + 3] = tanh2<TM>(fma2(bc(w.w), x, bc(b.w)));
+            *reinterpret_cast<float4 *>(&wr.A[(2 * lane) * LD + j4]) = make_float4(h1[j4].x, h1[j4 + 1].x, h1[j4 + 2].x, h1[j4 + 3].x);
+            *reinterpret_cast<float4 *>(&wr.A[(2 * lane + 1) * LD + j4]) = make_float4(h1[j4].y, h1[j4 + 1].y, h1[j4 + 2].y, h1[j4 + 3].y);
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4) {
+            const float4 b = ldw4(zb + O::B2 + j4);
+            v[j4] = bc(b.x); v[j4 + 1] = bc(b.y); v[j4 + 2] = bc(b.z); v[j4 + 3] = bc(b.w);
+        }
+#pragma unroll
+        for (int ii = 0; ii < H; ++ii) {
+#pragma unroll
+            for (int j4 = 0; j4 < H; j4 += 4) {
+                const float4 w = ldw4(zb + O::W2 + ii * H + j4);
+                v[j4 + 0] = fma2(bc(w.x), h1[ii], v[j4 + 0]);
+                v[j4 + 1] = fma2(bc(w.y), h1[ii], v[j4 + 1]);
+                v[j4 + 2] = fma2(bc(w.z), h1[ii], v[j4 + 2]);
+                v[j4 + 3] = fma2(bc(w.w), h1[ii], v[j4 + 3]);
+            }
+        }
+        a_b3 += sg.x + sg.y;
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4) {
+            const float4 w = ldw4(zb + O::W3 + j4);
+            const float w_[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 h2 = tanh2<TM>(v[j4 + k]);
+                a_w3[j4 + k] = fmaf(sg.x, h2.x, fmaf(sg.y, h2.y, a_w3[j4 + k]));
+                v[j4 + k] = mul2(mul2(bc(w_[k]), sg), fma2(mul2(bc(-1.0f), h2), h2, bc(1.0f)));   // q2
+                a_b2[j4 + k] += v[j4 + k].x + v[j4 + k].y;
+            }
+            *reinterpret_cast<float4 *>(&wr.Q[(2 * lane) * LD + j4]) = make_float4(v[j4].x, v[j4 + 1].x, v[j4 + 2].x, v[j4 + 3].x);
+            *reinterpret_cast<float4 *>(&wr.Q[(2 * lane + 1) * LD + j4]) = make_float4(v[j4].y, v[j4 + 1].y, v[j4 + 2].y, v[j4 + 3].y);
+        }
+        __syncwarp();
+        // ---- dW2 += q2 (x) h1 over the warp's 64 points ----
+#pragma unroll 8
+        for (int t = 0; t < 64; ++t) {
+            const float2 qq = *reinterpret_cast<const float2 *>(&wr.Q[t * LD + 2 * jt]);
+            const float4 hh = *reinterpret_cast<const float4 *>(&wr.A[t * LD + 4 * it]);
+            const float2 h01 = make_float2(hh.x, hh.y), h23 = make_float2(hh.z, hh.w);
+            acc[0] = fma2(bc(qq.x), h01, acc[0]);
+            acc[1] = fma2(bc(qq.x), h23, acc[1]);
+            acc[2] = fma2(bc(qq.y), h01, acc[2]);
+            acc[3] = fma2(bc(qq.y), h23, acc[3]);
+        }
+        __syncwarp();
+        // ---- q1 = (W2^T q2) * (1 - h1^2); first-layer gradients; dx ----
+        float2 dxa = bc(0.0f), dxb = bc(0.0f);
+#pragma unroll
+        for (int ii = 0; ii < H; ++ii) {
+            float2 s0 = bc(0.0f), s1 = bc(0.0f);
+#pragma unroll
+            for (int j4 = 0; j4 < H; j4 += 4) {
+                const float4 w = ldw4(zb + O::W2 + ii * H + j4);
+                s0 = fma2(bc(w.x), v[j4 + 0], s0);
+                s1 = fma2(bc(w.y), v[j4 + 1], s1);
+                s0 = fma2(bc(w.z), v[j4 + 2], s0);
+                s1 = fma2(bc(w.w), v[j4 + 3], s1);
+            }
+            const float2 q1 = mul2(add2(s0, s1), fma2(mul2(bc(-1.0f), h1[ii]), h1[ii], bc(1.0f)));
+            a_b1[ii] += q1.x + q1.y;
+            a_w1[ii] = fmaf(q1.x, x.x, fmaf(q1.y, x.y, a_w1[ii]));
+            const float wi = c_theta[zb + O::W1 + ii];
+            if (ii & 1) dxb = fma2(bc(wi), q1, dxb);
+            else dxa = fma2(bc(wi), q1, dxa);
+        }
+        const float2 dx = mul2(add2(dxa, dxb), bc(isc));
+        // (J^T g)_i: w1 couples i+1 -> i, w3 couples i-1 -> i
+        const float2 kn = make_float2(dx.x + D0 * fmaf(w2, g.x, fmaf(w1, g.y, w3 * gl)), dx.y + D0 * fmaf(w2, g.y, fmaf(w1, gr, w3 * g.x)));
+        // stencil-weight and D0 gradients: point 0 has neighbours (xl, x.y), point 1 has (x.x, xr)
+        a_s1 = fmaf(sg.x * D0, xl, fmaf(sg.y * D0, x.x, a_s1));
+        a_s2 = fmaf(sg.x * D0, x.x, fmaf(sg.y * D0, x.y, a_s2));
+        a_s3 = fmaf(sg.x * D0, x.y, fmaf(sg.y * D0, xr, a_s3));
+        a_D0 = fmaf(sg.x, fmaf(w1, xl, fmaf(w2, x.x, w3 * x.y)), fmaf(sg.y, fmaf(w1, x.x, fmaf(w2, x.y, w3 * xr)), a_D0));
+        return kn;
+    };
+
+    if constexpr (!RKC) {
 #pragma unroll 1
     for (int s = p.n_steps - 1; s >= 0; --s) {
         float2 kl[6];
@@ -627,93 +805,7 @@ __global__ void __launch_bounds__(256) adjoint_kernel2(AdjParams p, Geom geo)
 #undef B200UDE_FKPP_PRE
             const float2 x = fma2(bc(dt), xa, ld2(p.ustep, (size_t)s));
             const float2 g = fma2(bc(dt), ga, lam);
-            const int zb = lv32::c_zero[st] << 2;
-            float4 *sx = sX + flip * slots;
-            flip ^= 1;
-            if (valid) sx[slot] = make_float4(x.x, x.y, g.x, g.y);
-            __syncthreads();
-            const float4 nm = sx[im], np = sx[ip];   // left neighbour thread: its .y / .w border this thread's first point
-            const float xl = nm.y, gl = nm.w, xr = np.x, gr = np.z;
-            const float2 sg = mul2(bc(lv * sc), g);
-            // ---- chain forward, activations kept ----
-            float2 h1[H], v[H];
-#pragma unroll
-            for (int j4 = 0; j4 < H; j4 += 4) {
-                const float4 w = ldw4(zb + O::W1 + j4), b = ldw4(zb + O::B1 + j4);
-                h1[j4 + 0] = tanh2<TM>(fma2(bc(w.x), x, bc(b.x)));
-                h1[j4 + 1] = tanh2<TM>(fma2(bc(w.y), x, bc(b.y)));
-                h1[j4 + 2] = tanh2<TM>(fma2(bc(w.z), x, bc(b.z)));
-                h1[j4 + 3] = tanh2<TM>(fma2(bc(w.w), x, bc(b.w)));
-                *reinterpret_cast<float4 *>(&wr.A[(2 * lane) * LD + j4]) = make_float4(h1[j4].x, h1[j4 + 1].x, h1[j4 + 2].x, h1[j4 + 3].x);
-                *reinterpret_cast<float4 *>(&wr.A[(2 * lane + 1) * LD + j4]) = make_float4(h1[j4].y, h1[j4 + 1].y, h1[j4 + 2].y, h1[j4 + 3].y);
-            }
-#pragma unroll
-            for (int j4 = 0; j4 < H; j4 += 4) {
-                const float4 b = ldw4(zb + O::B2 + j4);
-                v[j4] = bc(b.x); v[j4 + 1] = bc(b.y); v[j4 + 2] = bc(b.z); v[j4 + 3] = bc(b.w);
-            }
-#pragma unroll
-            for (int ii = 0; ii < H; ++ii) {
-#pragma unroll
-                for (int j4 = 0; j4 < H; j4 += 4) {
-                    const float4 w = ldw4(zb + O::W2 + ii * H + j4);
-                    v[j4 + 0] = fma2(bc(w.x), h1[ii], v[j4 + 0]);
-                    v[j4 + 1] = fma2(bc(w.y), h1[ii], v[j4 + 1]);
-                    v[j4 + 2] = fma2(bc(w.z), h1[ii], v[j4 + 2]);
-                    v[j4 + 3] = fma2(bc(w.w), h1[ii], v[j4 + 3]);
-                }
-            }
-            a_b3 += sg.x + sg.y;
-#pragma unroll
-            for (int j4 = 0; j4 < H; j4 += 4) {
-                const float4 w = ldw4(zb + O::W3 + j4);
-                const float w_[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 h2 = tanh2<TM>(v[j4 + k]);
-                    a_w3[j4 + k] = fmaf(sg.x, h2.x, fmaf(sg.y, h2.y, a_w3[j4 + k]));
-                    v[j4 + k] = mul2(mul2(bc(w_[k]), sg), fma2(mul2(bc(-1.0f), h2), h2, bc(1.0f)));   // q2
-                    a_b2[j4 + k] += v[j4 + k].x + v[j4 + k].y;
-                }
-                *reinterpret_cast<float4 *>(&wr.Q[(2 * lane) * LD + j4]) = make_float4(v[j4].x, v[j4 + 1].x, v[j4 + 2].x, v[j4 + 3].x);
-                *reinterpret_cast<float4 *>(&wr.Q[(2 * lane + 1) * LD + j4]) = make_float4(v[j4].y, v[j4 + 1].y, v[j4 + 2].y, v[j4 + 3].y);
-            }
-            __syncwarp();
-            // ---- dW2 += q2 (x) h1 over the warp's 64 points ----
-#pragma unroll 8
-            for (int t = 0; t < 64; ++t) {
-                const float2 qq = *reinterpret_cast<const float2 *>(&wr.Q[t * LD + 2 * jt]);
-                const float4 hh = *reinterpret_cast<const float4 *>(&wr.A[t * LD + 4 * it]);
-                const float2 h01 = make_float2(hh.x, hh.y), h23 = make_float2(hh.z, hh.w);
-                acc[0] = fma2(bc(qq.x), h01, acc[0]);
-                acc[1] = fma2(bc(qq.x), h23, acc[1]);
-                acc[2] = fma2(bc(qq.y), h01, acc[2]);
-                acc[3] = fma2(bc(qq.y), h23, acc[3]);
-            }
-            __syncwarp();
-            // ---- q1 = (W2^T q2) * (1 - h1^2); first-layer gradients; dx ----
-            float2 dxa = bc(0.0f), dxb = bc(0.0f);
-#pragma unroll
-            for (int ii = 0; ii < H; ++ii) {
-                float2 s0 = bc(0.0f), s1 = bc(0.0f);
-#pragma unroll
-                for (int j4 = 0; j4 < H; j4 += 4) {
-                    const float4 w = ldw4(zb + O::W2 + ii * H + j4);
-                    s0 = fma2(bc(w.x), v[j4 + 0], s0);
-                    s1 = fma2(bc(w.y), v[j4 + 1], s1);
-                    s0 = fma2(bc(w.z), v[j4 + 2], s0);
-                    s1 = fma2(bc(w.w), v[j4 + 3], s1);
-                }
-                const float2 q1 = mul2(add2(s0, s1), fma2(mul2(bc(-1.0f), h1[ii]), h1[ii], bc(1.0f)));
-                a_b1[ii] += q1.x + q1.y;
-                a_w1[ii] = fmaf(q1.x, x.x, fmaf(q1.y, x.y, a_w1[ii]));
-                const float wi = c_theta[zb + O::W1 + ii];
-                if (ii & 1) dxb = fma2(bc(wi), q1, dxb);
-                else dxa = fma2(bc(wi), q1, dxa);
-            }
-            const float2 dx = mul2(add2(dxa, dxb), bc(isc));
-            // (J^T g)_i: w1 couples i+1 -> i, w3 couples i-1 -> i
-            const float2 kn = make_float2(dx.x + D0 * fmaf(w2, g.x, fmaf(w1, g.y, w3 * gl)), dx.y + D0 * fmaf(w2, g.y, fmaf(w1, gr, w3 * g.x)));
+            const float2 kn = eval_core(x, g, sc, isc, st);
             switch (st) {
             case 0: kl[0] = kn; break;
             case 1: kl[1] = kn; break;
@@ -722,17 +814,46 @@ __global__ void __launch_bounds__(256) adjoint_kernel2(AdjParams p, Geom geo)
             case 4: kl[4] = kn; break;
             default: kl[5] = kn; break;
             }
-            // stencil-weight and D0 gradients: point 0 has neighbours (xl, x.y), point 1 has (x.x, xr)
-            a_s1 = fmaf(sg.x * D0, xl, fmaf(sg.y * D0, x.x, a_s1));
-            a_s2 = fmaf(sg.x * D0, x.x, fmaf(sg.y * D0, x.y, a_s2));
-            a_s3 = fmaf(sg.x * D0, x.y, fmaf(sg.y * D0, xr, a_s3));
-            a_D0 = fmaf(sg.x, fmaf(w1, xl, fmaf(w2, x.x, w3 * x.y)), fmaf(sg.y, fmaf(w1, x.x, fmaf(w2, x.y, w3 * xr)), a_D0));
         }
         float2 a = bc(0.0f);
 #pragma unroll
         for (int j = 0; j < 6; ++j) a = fma2(bc((float)Tsit5::b(j)), kl[j], a);
         lam = fma2(bc(dt), a, lam);
         if (s % p.save_every == 0) jump(s / p.save_every);
+    }
+    } else {
+    // ---- RKC2 forward solve: lambda is stepped backwards with RKC2 itself; u(t) = cubic Hermite on (u_n, f_n, u_{n+1}, f_{n+1})
+    // (ustep rows n, n+1 and dense rows n, n+1 = f(u_n), f(u_{n+1})); stage k sits at t_{n+1} - c_k dt; the theta-gradient of the
+    // step is dt sum_k w_k (df/dtheta)^T(x_k) Y_k (quadrature weights from the recurrence, see the oracle) ----
+    const int S = c_rkc.s;
+#pragma unroll 1
+    for (int s = p.n_steps - 1; s >= 0; --s) {
+        const float2 y0 = ld2(p.ustep, (size_t)s), y1 = ld2(p.ustep, (size_t)s + 1), f0 = ld2(p.dense, (size_t)s), f1 = ld2(p.dense, (size_t)s + 1);
+        const float2 dy = add2(y1, mul2(bc(-1.0f), y0));
+        float2 Y0 = lam, Y1 = lam, F0 = bc(0.0f);
+#pragma unroll 1
+        for (int j = 0; j < S; ++j) {
+            const float Th = 1.0f - c_rkc.c[j];
+            // x = (1 - Th) y0 + Th y1 + Th (Th - 1) ((1 - 2 Th) (y1 - y0) + (Th - 1) dt f0 + Th dt f1)
+            const float2 inner = fma2(bc(1.0f - 2.0f * Th), dy, fma2(bc((Th - 1.0f) * dt), f0, mul2(bc(Th * dt), f1)));
+            const float2 x = fma2(bc(Th * (Th - 1.0f)), inner, fma2(bc(Th), dy, y0));
+            const float2 g = j == 0 ? lam : Y1;
+            const float sc = dt * c_rkc.w[j], isc = 1.0f / sc;
+            const float2 kn = eval_core(x, g, sc, isc, j);
+            if (j == 0) {
+                F0 = kn;
+                Y0 = lam;
+                Y1 = fma2(bc(c_rkc.mt1 * dt), F0, lam);
+            } else {
+                const float mu = c_rkc.mu[j + 1], nu = c_rkc.nu[j + 1], mt = c_rkc.mt[j + 1], ga = c_rkc.ga[j + 1];
+                const float2 Y2 = fma2(bc(ga * dt), F0, fma2(bc(mt * dt), kn, fma2(bc(nu), Y0, fma2(bc(mu), Y1, mul2(bc(1.0f - mu - nu), lam)))));
+                Y0 = Y1;
+                Y1 = Y2;
+            }
+        }
+        lam = Y1;
+        if (s % p.save_every == 0) jump(s / p.save_every);
+    }
     }
     if (p.grad_u0 && live) {
         p.grad_u0[(size_t)i0 * N + n] = lam.x;

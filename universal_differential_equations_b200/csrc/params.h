@@ -107,6 +107,14 @@ cudaError_t launch_adj_seir(const Variant &, const ConstTables &, const AdjParam
 int adj_rows_seir(int N);
 cudaError_t launch_fwd_seir_adaptive(const Variant &, const ConstTables &, const FwdParams &, const AdaptiveGrid &, cudaStream_t);
 cudaError_t launch_adj_seir_adaptive(const Variant &, const ConstTables &, const AdjParams &, const AdaptiveGrid &, cudaStream_t, int *rows_out);
+// RKC2 recurrence tables of a handle (computed on the host, b200ude.cu)
+struct RkcHost {
+    int s = 0;
+    float mt1 = 0;
+    float mu[65] = {}, nu[65] = {}, mt[65] = {}, ga[65] = {}, c[65] = {}, w[65] = {};
+};
+cudaError_t launch_fwd_fkpp16_rkc(const Variant &, const ConstTables &, const RkcHost &, const FwdParams &, int Nx, cudaStream_t);
+cudaError_t launch_adj_fkpp16_rkc(const Variant &, const ConstTables &, const RkcHost &, const AdjParams &, int Nx, cudaStream_t, int *rows_out);
 cudaError_t launch_fwd_fkpp16(const Variant &, const ConstTables &, const FwdParams &, int Nx, cudaStream_t);
 cudaError_t launch_adj_fkpp16(const Variant &, const ConstTables &, const AdjParams &, int Nx, cudaStream_t, int *rows_out);
 int adj_rows_fkpp16(int N, int Nx);

@@ -225,6 +225,42 @@ class Vern7:
     code = _lib.VERN7
 
 
+def _rkc2_beta(s):
+    """Length of the real stability interval of s-stage RKC2 (damping 2/13): (w0 + 1) T''_s(w0) / T'_s(w0) ~ 0.65 s^2."""
+    w0 = 1.0 + (2.0 / 13.0) / (s * s)
+    T0, T1, d0, d1, e0, e1 = 1.0, w0, 0.0, 1.0, 0.0, 0.0
+    for _ in range(2, s + 1):
+        T0, T1, d0, d1, e0, e1 = T1, 2 * w0 * T1 - T0, d1, 2 * T1 + 2 * w0 * d1 - d0, e1, 4 * d1 + 2 * w0 * e1 - e0
+    return (w0 + 1.0) * e1 / d1
+
+
+class RKC2:
+    """Stabilised explicit second-order Runge-Kutta-Chebyshev solver -- what this path offers where the reference calls
+    `ROCK2(eigen_est = ...)` (Climate/NeuralPDE/npde.jl:61,82; named by the north star for the stiff Fisher-KPP grid):
+    same class of method (explicit, stability interval growing with the square of the stage count), closed-form
+    coefficients (ROCK2's tables are not in the reference).  Give `stages`, or `eigen_est` (an upper bound of the spectral
+    radius of the RHS Jacobian, as the reference's ROCK2 call does) from which the stage count is chosen for the step."""
+    code = _lib.RKC2
+
+    def __init__(self, stages=None, eigen_est=None):
+        self.stages, self.eigen_est = stages, eigen_est
+
+    def n_stages(self, dt):
+        if self.stages is not None:
+            return int(self.stages)
+        if self.eigen_est is None:
+            raise ValueError("RKC2 needs stages= or eigen_est=")
+        s = 2
+        while _rkc2_beta(s) < 1.05 * dt * float(self.eigen_est):
+            s += 1
+            if s > 64:
+                raise ValueError("dt * eigen_est needs more than 64 stages: reduce dt")
+        return s
+
+
+ROCK2 = RKC2   # the name the reference's scripts use
+
+
 class ReverseDiffVJP:
     pass
 
@@ -286,6 +322,7 @@ class UDESolver:
         for i, c in enumerate(cs):
             d.consts[i] = c
         d.solver = alg.code
+        d.n_stages = alg.n_stages(float(dt)) if isinstance(alg, RKC2) else 0
         d.sensealg = sensealg.code
         d.t0, d.dt, d.n_steps, d.save_every = self.t0, self.dt, self.n_steps, self.save_every
         if loss_weights is not None:
