@@ -557,7 +557,8 @@ def concrete_solve(prob, alg, u0=None, p=None, *, saveat=None, dt=None, adaptive
         adaptive = dt is None
     abstol = 1e-6 if abstol is None else abstol
     reltol = 1e-3 if reltol is None else reltol
-    key = (id(base.f), t0, dtv, n_steps, save_every, type(alg).__name__, dev.index, tuple(loss_weights) if loss_weights else None,
+    key = (id(base.f), t0, dtv, n_steps, save_every, type(alg).__name__, getattr(alg, "stages", None), getattr(alg, "eigen_est", None),
+           type(sensealg).__name__ if sensealg is not None else None, dev.index, tuple(loss_weights) if loss_weights else None,
            bool(adaptive), abstol, reltol, max_steps)
     solver = _SOLVERS.get(key)
     if solver is None or solver.capacity < N:
