@@ -284,3 +284,54 @@ def test_rkc2_oracle_coefficients_convergence_and_adjoint(O):
     except FloatingPointError:
         blown = True
     assert blown
+
+
+def test_kat9_scenario2_multiple_shooting_loss_history_pins_trainable_rate_gradient(O, golden):
+    """KAT-9.  scenario_2.jl:57-72,112-123,141: theta = [delta; U] (delta = the predator's linear decay rate, trainable), loss =
+    1e-3 mean(theta[2:end]^2) + sum over 5 shooting segments of [ sum (x data - x_hat)^2 + |y(end) - y_hat(end)| ], ADAM(0.1).
+    Replaying ADAM with the ORACLE's interpolating-adjoint gradient reproduces the reference's stored loss history (which the
+    reference produced with Vern7 @ 1e-6 + ForwardDiffSensitivity): pins the gradient w.r.t. a physics parameter in front of
+    the chain (n_prefix = 1), the cotangent of a non-L2 loss term, and the regulariser."""
+    g = golden["scenario_2"]
+    t, X, losses = g["t"], g["X"], g["losses"]
+    m = O.lv_model((2, 5, 5, 5, 2), RBF3, n_prefix=1)
+    ty = np.arange(t[0], t[-1] + 1e-9, 6 / 5)
+    segs = [np.where((t >= ty[i] - 1e-9) & (t <= ty[i + 1] + 1e-9))[0] for i in range(len(ty) - 1)]
+    assert [len(sg) for sg in segs] == [13] * 5
+
+    def loss_grad(th, sub=16, want_grad=True):
+        l = 1e-3 * np.sum(th[1:] ** 2) / len(th[1:])
+        gth = np.zeros_like(th)
+        gth[1:] = 2e-3 * th[1:] / len(th[1:])
+        for idx in segs:
+            xs, y0, y1, n, dt = X[0, idx], X[1, idx[0]], X[1, idx[-1]], len(idx) - 1, 0.1 / sub
+            out, dense = O.solve_fixed(m, th, np.array([xs[0], y0]), dt, n * sub, save_every=sub, want_dense=True)
+            l += np.sum((xs - out[:, 0]) ** 2) + abs(y1 - out[-1, 1])
+            if want_grad:
+                cot = np.zeros_like(out)
+                cot[:, 0] = 2 * (out[:, 0] - xs)
+                cot[-1, 1] = -np.sign(y1 - out[-1, 1])
+                gth += O.adjoint_fixed(m, th, out, dense, dt, n * sub, cot, save_every=sub)[0]
+        return l, gth
+    th = g["theta_init"].copy()
+    mm, vv = np.zeros_like(th), np.zeros_like(th)
+    for it in range(1, 7):
+        l, gr = loss_grad(th)
+        assert abs(l - losses[it - 1]) < 5e-7 * losses[it - 1], (it, l, losses[it - 1])
+        mm = 0.9 * mm + 0.1 * gr
+        vv = 0.999 * vv + 0.001 * gr * gr
+        th = th - 0.1 * (mm / (1 - 0.9 ** it)) / (np.sqrt(vv / (1 - 0.999 ** it)) + 1e-8)
+    l_end, _ = loss_grad(g["theta_trained"], want_grad=False)
+    assert abs(l_end - losses[-1]) < 2e-4 * losses[-1]
+
+
+def test_kat10_hudson_bay_final_loss(O, golden):
+    """KAT-10.  hudson_bay.jl:82-91,112-115: two trainable rates in front of a FastChain with rbf, rbf, tanh; the script's
+    'equivalent L2 loss' sum(abs2, Xn - X_hat) / 21 + 1e-3 mean(theta[3:end]^2) at the stored trained parameters equals the
+    last entry of the stored loss history (Float32 data; reference solve: Vern7 @ 1e-6)."""
+    g = golden["hudson_bay"]
+    t, X, th = g["t"].astype(np.float64), g["X"].astype(np.float64), g["theta_trained"].astype(np.float64)
+    m = O.lv_model((2, 5, 5, 5, 2), ("rbf", "rbf", "tanh", "identity"), n_prefix=2)
+    out, _, _ = O.solve_adaptive(m, th, X[:, 0], t, 1e-9, 1e-9)
+    loss = np.sum((X - out.T) ** 2) / X.shape[1] + 1e-3 * np.sum(th[2:] ** 2) / len(th[2:])
+    assert abs(loss - g["losses"][-1]) < 5e-5 * g["losses"][-1]
