@@ -335,3 +335,32 @@ def test_kat10_hudson_bay_final_loss(O, golden):
     out, _, _ = O.solve_adaptive(m, th, X[:, 0], t, 1e-9, 1e-9)
     loss = np.sum((X - out.T) ** 2) / X.shape[1] + 1e-3 * np.sum(th[2:] ** 2) / len(th[2:])
     assert abs(loss - g["losses"][-1]) < 5e-5 * g["losses"][-1]
+
+
+def test_kat11_scenario3_fisher_kpp_loss_history_pins_the_pde_gradient(O, golden):
+    """KAT-11.  scenario_3.jl:96-145 (the Lux twin of FisherKPP/Fisher-KPP-CNN.jl): theta = (chain 1-5-5-5-1 rbf, 4 stencil
+    parameters, D0), objective = sum(abs2, pred - Xn) + abs(sum of the three stencil taps), ADAM(0.1) x 10 from the stored
+    initial parameters (taps = 0, D0 = 6.5).  Replaying ADAM with the ORACLE's interpolating-adjoint gradient reproduces all ten
+    stored ADAM losses to Float32 storage precision: pins the Fisher-KPP gradient -- chain, stencil weights and D0 -- against
+    the reference's own run (which used ForwardDiffSensitivity through Vern7)."""
+    g = golden["scenario_3"]
+    X, losses = g["X"].astype(np.float64), g["losses"]
+    m = O.fkpp_model(26, (1, 5, 5, 5, 1), RBF3)
+
+    def loss_grad(th, sub=40):
+        dt, n = 0.5 / sub, 10 * sub
+        out, dense = O.solve_fixed(m, th, X[:, 0], dt, n, save_every=sub, want_dense=True)
+        r = out - X.T
+        sw = th[76:79].sum()
+        gth = O.adjoint_fixed(m, th, out, dense, dt, n, 2 * r, save_every=sub)[0].copy()
+        gth[76:79] += np.sign(sw)
+        return (r ** 2).sum() + abs(sw), gth
+    th = g["theta_init"].astype(np.float64)
+    assert np.all(th[76:80] == 0) and th[80] == 6.5
+    mm, vv = np.zeros_like(th), np.zeros_like(th)
+    for it in range(1, 11):
+        l, gr = loss_grad(th)
+        assert abs(l - losses[it - 1]) < 1e-5 * losses[it - 1], (it, l, losses[it - 1])
+        mm = 0.9 * mm + 0.1 * gr
+        vv = 0.999 * vv + 0.001 * gr * gr
+        th = th - 0.1 * (mm / (1 - 0.9 ** it)) / (np.sqrt(vv / (1 - 0.999 ** it)) + 1e-8)
