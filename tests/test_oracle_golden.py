@@ -45,11 +45,12 @@ def test_kat2_forward_solve_scenario1(O, golden):
     assert np.abs(out.T - g["Xhat"]).max() < 5e-7
 
 
-def _loss_grad_s1(O, m, th, X, sub=16):
+def _loss_grad_s1(O, m, th, X, sub=16, discrete=False):
     dt, ns = 0.1 / sub, 30 * sub
     out, dense = O.solve_fixed(m, th, X[:, 0], dt, ns, save_every=sub, want_dense=True)
     r = out - X.T
-    gth, gu = O.adjoint_fixed(m, th, out, dense, dt, ns, 2 * r, save_every=sub)
+    adj = O.adjoint_discrete if discrete else O.adjoint_fixed
+    gth, gu = adj(m, th, out, dense, dt, ns, 2 * r, save_every=sub)
     return (r**2).sum(), gth
 
 
@@ -62,7 +63,8 @@ def test_kat3_loss_values_scenario1(O, golden):
     assert abs(l1 - g["losses"][-1]) < 1e-5 * g["losses"][-1]
 
 
-def test_kat4_gradient_pinned_by_adam_replay(O, golden):
+@pytest.mark.parametrize("discrete", [False, True])
+def test_kat4_gradient_pinned_by_adam_replay(O, golden, discrete):
     """The reference's stored loss history losses[k] = L(theta_k) under ADAM(0.1) (scenario_1.jl:114) is
     reproduced by replaying ADAM with the ORACLE'S interpolating-adjoint gradient: this pins d L / d theta
     (the reference computed it with ForwardDiffSensitivity; any correct gradient must agree)."""
@@ -72,7 +74,7 @@ def test_kat4_gradient_pinned_by_adam_replay(O, golden):
     mm, vv = np.zeros_like(th), np.zeros_like(th)
     b1, b2, eta, eps = 0.9, 0.999, 0.1, 1e-8
     for it in range(1, 7):
-        l, gr = _loss_grad_s1(O, m, th, g["X"])
+        l, gr = _loss_grad_s1(O, m, th, g["X"], discrete=discrete)   # discrete = ForwardDiffSensitivity's quantity (scenario_1.jl:86)
         assert abs(l - g["losses"][it - 1]) < 2e-6 * g["losses"][it - 1], (it, l, g["losses"][it - 1])  # reference solver tol 1e-6
         mm = b1 * mm + (1 - b1) * gr
         vv = b2 * vv + (1 - b2) * gr * gr
