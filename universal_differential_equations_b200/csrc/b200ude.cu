@@ -132,7 +132,7 @@ void rkc2_tables(int s, RkcHost *out)
 {
     const double eps = 2.0 / 13.0, w0 = 1.0 + eps / ((double)s * s);
     double T[65], dT[65], d2T[65], b[65] = {0}, mu[65] = {0}, nu[65] = {0}, mt[65] = {0}, ga[65] = {0}, c[65] = {0};
-    static double W[65][65];
+    double W[65][65];   // 33 KB of stack, host side only
     T[0] = 1; T[1] = w0; dT[0] = 0; dT[1] = 1; d2T[0] = 0; d2T[1] = 0;
     for (int j = 2; j <= s; ++j) {
         T[j] = 2 * w0 * T[j - 1] - T[j - 2];
