@@ -184,7 +184,8 @@ int32_t b200ude_loss_gradient_host(b200ude_handle *h, const void *theta, const v
 
 /* ON-DEVICE OPTIMISER  (replaces the ADAM phase of DiffEqFlux.sciml_train(loss, theta, ADAM(eta); cb, maxiters)
  * seir_exposure.jl:160, Fisher-KPP-CNN.jl:236, Optimization.solve(optprob, ADAM(0.1); maxiters) scenario_1.jl:114,
- * for the trajectory-matching loss  L = loss_scale * sum w (u - data)^2 + l2_reg * sum theta^2
+ * for the trajectory-matching loss  L = loss_scale * sum w (u - data)^2 + l2_reg * sum theta[n_prefix:]^2
+ * (the L2 term skips the n_prefix trainable physics rates, as scenario_2.jl:113 does with theta[2:end])
  * (scenario_1.jl:91-94; scenario_2.jl:113-116 divides by the number of points and adds the L2 term).
  * The update is Flux.ADAM: m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2,
  * theta -= eta * (m / (1 - b1^t)) / (sqrt(v / (1 - b2^t)) + eps); the moments and t live in the handle. */

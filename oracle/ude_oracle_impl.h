@@ -364,7 +364,7 @@ int FN(ude_solve_adaptive)(const ude_model *m, const REAL *th, const REAL *u0, c
     const int d = m->d, s = tb->s, order = tb->order;
     const REAL t0 = saveat[0], t1 = saveat[n_save - 1];
     /* OrdinaryDiffEq defaults: gamma=9/10, qmin=1/5, qmax=10, beta2=2/(5*order), beta1=7/(10*order),
-     * qsteady in [1, 1.2], qoldinit=1e-4 */
+     * qsteady_min = qsteady_max = 1 (explicit RK), qoldinit=1e-4 */
     const REAL gamma = (REAL)0.9, qmin = (REAL)0.2, qmax = (REAL)10;
     const REAL beta2 = (REAL)2 / ((REAL)5 * order), beta1 = (REAL)7 / ((REAL)10 * order);
     REAL qold = (REAL)1e-4;
@@ -438,7 +438,7 @@ int FN(ude_solve_adaptive)(const ude_model *m, const REAL *th, const REAL *u0, c
                 ++isave;
             }
             qold = EEst > (REAL)1e-4 ? EEst : (REAL)1e-4;
-            if (q >= (REAL)1 && q <= (REAL)1.2) q = 1;     /* qsteady band: keep dt */
+            /* qsteady_min = qsteady_max = 1 for explicit RK methods (OrdinaryDiffEq defaults; 6/5 is the implicit-solver band): no dead band */
             if (!clipped || h >= dt) dt = h / q; /* a clipped (shortened) step does not shrink the proposal */
             else { const REAL prop = h / q; if (prop > dt) dt = prop; }
             t = tn;
@@ -805,7 +805,7 @@ int FN(ude_solve_adaptive_dense)(const ude_model *m, const REAL *th, const REAL 
                 ++isave;
             }
             qold = EEst > (REAL)1e-4 ? EEst : (REAL)1e-4;
-            if (q >= (REAL)1 && q <= (REAL)1.2) q = 1;
+            /* qsteady_min = qsteady_max = 1 for explicit RK methods (OrdinaryDiffEq defaults; 6/5 is the implicit-solver band): no dead band */
             if (!clipped || h >= dt) dt = h / q;
             else { const REAL prop = h / q; if (prop > dt) dt = prop; }
             t = tn;
@@ -969,7 +969,7 @@ int FN(ude_adjoint_adaptive)(const ude_model *m, const REAL *th, const REAL *sav
         if (q > (REAL)1 / qmin) q = (REAL)1 / qmin;
         if (EEst <= (REAL)1) {
             qold = EEst > (REAL)1e-4 ? EEst : (REAL)1e-4;
-            if (q >= (REAL)1 && q <= (REAL)1.2) q = 1;
+            /* qsteady_min = qsteady_max = 1 for explicit RK methods (OrdinaryDiffEq defaults; 6/5 is the implicit-solver band): no dead band */
             if (!clipped || h >= dt) dt = h / q;
             else { const REAL prop = h / q; if (prop > dt) dt = prop; }
             t = clipped ? tstop : t - h;

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
 
 #include "params.h"
@@ -46,7 +47,7 @@ int kernel_num_params(KernelId k)
     }
 }
 
-uint64_t g_serial = 0;
+std::atomic<uint64_t> g_serial{0};   // handles may be created from several host threads (one per GPU)
 
 }  // namespace
 
@@ -345,7 +346,7 @@ struct AdamArgs {
     const float *grad, *loss;   // loss may be null
     float *loss_history;        // [..] or null; slot (t - 1 - t_base) receives the pre-update loss
     int *t;
-    int P, t_base;
+    int P, t_base, reg_from;   // the L2 term covers theta[reg_from:] (scenario_2.jl:113: sum(abs2, theta[2:end]) skips the trainable physics rate)
     float eta, beta1, beta2, eps, loss_scale, l2_reg;
 };
 
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(1024, 1) adam_kernel(AdamArgs a)
     if (threadIdx.x == 0) s_t = *a.t + 1;
     float sq = 0.0f;
     if (a.l2_reg != 0.0f)
-        for (int i = threadIdx.x; i < a.P; i += blockDim.x) sq = fmaf(a.theta[i], a.theta[i], sq);
+        for (int i = a.reg_from + threadIdx.x; i < a.P; i += blockDim.x) sq = fmaf(a.theta[i], a.theta[i], sq);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(1024, 1) adam_kernel(AdamArgs a)
     const float c2 = (float)(1.0 / (1.0 - pow((double)a.beta2, (double)t)));
     for (int i = threadIdx.x; i < a.P; i += blockDim.x) {
         const float th = a.theta[i];
-        const float g = fmaf(a.loss_scale, a.grad[i], 2.0f * a.l2_reg * th);
+        const float g = fmaf(a.loss_scale, a.grad[i], i >= a.reg_from ? 2.0f * a.l2_reg * th : 0.0f);
         const float m = fmaf(a.beta1, a.m[i], (1.0f - a.beta1) * g);
         const float v = fmaf(a.beta2, a.v[i], (1.0f - a.beta2) * g * g);
         a.m[i] = m;
@@ -387,9 +388,11 @@ int32_t ensure_adam(b200ude_handle *h)
     bool ok = dalloc(h, &h->d_adam_m, (size_t)h->P) == cudaSuccess && dalloc(h, &h->d_adam_v, (size_t)h->P) == cudaSuccess &&
               dalloc(h, &h->d_adam_t, 1) == cudaSuccess;
     if (!ok) return fail(h, B200UDE_ENOMEM, "adam: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // synchronous with respect to the host and to every stream that is used afterwards
     cudaMemset(h->d_adam_m, 0, sizeof(float) * h->P);
     cudaMemset(h->d_adam_v, 0, sizeof(float) * h->P);
     cudaMemset(h->d_adam_t, 0, sizeof(int));
+    cudaDeviceSynchronize();
     h->adam_t = 0;
     return B200UDE_OK;
 }
@@ -407,7 +410,7 @@ cudaError_t launch_adam(b200ude_handle *h, const b200ude_adam *o, const float *g
 {
     AdamArgs a;
     a.theta = h->d_theta; a.m = h->d_adam_m; a.v = h->d_adam_v; a.grad = grad; a.loss = loss; a.loss_history = hist;
-    a.t = h->d_adam_t; a.P = h->P; a.t_base = t_base;
+    a.t = h->d_adam_t; a.P = h->P; a.t_base = t_base; a.reg_from = h->desc.n_prefix > 0 ? h->desc.n_prefix : 0;
     a.eta = (float)o->eta; a.beta1 = (float)o->beta1; a.beta2 = (float)o->beta2; a.eps = (float)o->eps;
     a.loss_scale = (float)(o->loss_scale == 0.0 ? 1.0 : o->loss_scale); a.l2_reg = (float)o->l2_reg;
     adam_kernel<<<1, 1024, 0, st>>>(a);
@@ -480,6 +483,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
 
     b200ude_handle *h = new (std::nothrow) b200ude_handle();
     if (!h) return fail(nullptr, B200UDE_ENOMEM, "create: out of host memory");
+    const uint64_t serial = ++g_serial;   // taken once: gen.serial and tab.serial must agree
     h->desc = *d;
     h->kid = kid;
     h->D = d->state_dim;
@@ -492,7 +496,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         int P = d->n_prefix + d->n_suffix;
         for (int l = 0; l < d->n_layers; ++l) P += d->widths[l] * d->widths[l + 1] + d->widths[l + 1];
         h->P = P;
-        h->gen.serial = g_serial + 1;   // same serial as the tables set below
+        h->gen.serial = serial;   // same serial as the tables set below
         h->gen.model = d->model; h->gen.D = d->state_dim; h->gen.din = d->widths[0]; h->gen.dout = d->widths[d->n_layers];
         h->gen.n_layers = d->n_layers; h->gen.n_prefix = d->n_prefix; h->gen.P = P;
         for (int l = 0; l < 8; ++l) { h->gen.widths[l] = l <= d->n_layers ? d->widths[l] : 0; h->gen.acts[l] = l < d->n_layers ? d->acts[l] : 0; }
@@ -540,7 +544,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         b200ude_destroy(h);
         return B200UDE_ENOMEM;
     }
-    h->tab.serial = ++g_serial;
+    h->tab.serial = serial;
     h->ag.t0 = (float)d->t0; h->ag.save_dt = (float)(d->dt * d->save_every); h->ag.abstol = (float)d->abstol; h->ag.reltol = (float)d->reltol;
     h->ag.n_save = h->n_save; h->ag.max_steps = d->max_steps; h->ag.tgrid = h->d_tgrid; h->ag.nacc = h->d_nacc;
     h->tab.d_theta = h->d_theta;
@@ -718,6 +722,12 @@ int32_t b200ude_train_adam(b200ude_handle *h, const b200ude_adam *opt, const voi
     if (!h->d_train_out && dalloc(h, &h->d_train_out, (size_t)h->n_save * (size_t)h->D * h->cap) != cudaSuccess)
         return fail(h, B200UDE_ENOMEM, "train_adam: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;   // the legacy default stream cannot be captured
+    if (!stream) {
+        // own_stream is non-blocking: order it after everything the caller enqueued on the legacy default stream (set_params,
+        // adam_reset, the producers of u0 / data); the call synchronises own_stream before it returns
+        CUDA_TRY(h, cudaEventRecord(h->data_ready, (cudaStream_t)0));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->own_stream, h->data_ready, 0));
+    }
     const int t_base = h->adam_t;
     auto one_iteration = [&]() -> int32_t {
         int32_t r = do_forward(h, (const float *)u0, N, h->d_train_out, nullptr, st);

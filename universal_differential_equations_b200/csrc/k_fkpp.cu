@@ -71,15 +71,15 @@ static cudaError_t adj(const AdjParams &p, int Nx, cudaStream_t st, int *rows_ou
 // RKC2 forward / adjoint (packed kernels, even grids only)
 static cudaError_t upload_rkc(const RkcHost &r, uint64_t serial, cudaStream_t st)
 {
-    static uint64_t last = 0;
-    if (last == serial) return cudaSuccess;
+    static SerialCache cache;
+    if (cache.hit(serial)) return cudaSuccess;
     fkpp::RkcTables t;
     t.s = r.s; t.mt1 = r.mt1;
     for (int j = 0; j < 65; ++j) { t.mu[j] = r.mu[j]; t.nu[j] = r.nu[j]; t.mt[j] = r.mt[j]; t.ga[j] = r.ga[j]; t.c[j] = r.c[j]; t.w[j] = r.w[j]; }
     cudaError_t e = cudaMemcpyToSymbolAsync(fkpp::c_rkc, &t, sizeof(t), 0, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         e = cudaStreamSynchronize(st);   // `t` is a stack object: the copy must have left it before we return
-        last = serial;
+        cache.set(serial);
     }
     return e;
 }

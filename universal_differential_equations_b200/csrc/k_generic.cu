@@ -9,8 +9,8 @@ int adj_rows_generic(int N) { return ((N + GEN_BLOCK - 1) / GEN_BLOCK) * (GEN_BL
 
 static cudaError_t upload_gen(const GenericShape &g, cudaStream_t st)
 {
-    static uint64_t last_serial = 0;
-    if (last_serial == g.serial) return cudaSuccess;
+    static SerialCache cache;
+    if (cache.hit(g.serial)) return cudaSuccess;
     generic::GenDesc d;
     d.model = g.model; d.D = g.D; d.din = g.din; d.dout = g.dout; d.n_layers = g.n_layers; d.n_prefix = g.n_prefix; d.P = g.P;
     int off = g.n_prefix;
@@ -21,7 +21,7 @@ static cudaError_t upload_gen(const GenericShape &g, cudaStream_t st)
         if (l < g.n_layers) off += g.widths[l] * g.widths[l + 1] + g.widths[l + 1];
     }
     cudaError_t e = cudaMemcpyToSymbolAsync(generic::c_gen, &d, sizeof(d), 0, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) last_serial = g.serial;
+    if (e == cudaSuccess) cache.set(g.serial);
     return e;
 }
 

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) adaptive_forward_kernel(FwdParams
                             ++isave;
                         }
                         qold = fmaxf(EEst, 1e-4f);
-                        if (q >= 1.0f && q <= 1.2f) q = 1.0f;
+                        // qsteady_min = qsteady_max = 1 for explicit RK methods in OrdinaryDiffEq (the 6/5 band is the implicit-solver default): no dead band
                         if (!clipped || h >= dt) dt = h / q;
                         else dt = fmaxf(dt, h / q);
                         t = tn;
@@ -473,6 +473,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) adaptive_forward_kernel(FwdParams
                 }
             }
         }
+    }
+    if (bad) {   // failed solve: the unreached save points are NaN
+        for (int is = isave; is < ag.n_save; ++is) store2(p.out, is, __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
     }
     if (live) ag.nacc[n] = nacc;
     if (p.status && live) {

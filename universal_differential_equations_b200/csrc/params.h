@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace b200ude {
 
 struct FwdParams {
@@ -57,6 +59,20 @@ struct PerDeviceOnce {
         cudaGetDevice(&dev);
         return done[dev & 63];
     }
+};
+
+// "which handle's small tables are in this device's constant bank": the bank is per device, so the cache is too
+// (one host thread per GPU may create and drive handles concurrently)
+struct SerialCache {
+    std::atomic<uint64_t> last[64] = {};
+    static int dev()
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        return d & 63;
+    }
+    bool hit(uint64_t serial) const { return last[dev()].load(std::memory_order_acquire) == serial; }
+    void set(uint64_t serial) { last[dev()].store(serial, std::memory_order_release); }
 };
 
 constexpr int FWD_BLOCK = 128;      // small-chain forward kernels

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(BLOCK, 1) adaptive_forward_kernel(FwdParams p,
                             ++isave;
                         }
                         qold = fmaxf(EEst, 1e-4f);
-                        if (q >= 1.0f && q <= 1.2f) q = 1.0f;
+                        // qsteady_min = qsteady_max = 1 for explicit RK methods in OrdinaryDiffEq (the 6/5 band is the implicit-solver default): no dead band
                         if (!clipped || h >= dt) dt = h / q;
                         else dt = fmaxf(dt, h / q);
                         t = tn;
@@ -452,6 +452,11 @@ __global__ void __launch_bounds__(BLOCK, 1) adaptive_forward_kernel(FwdParams p,
                 }
             }
         }
+    }
+    if (bad && live) {   // failed solve: the unreached save points are NaN
+        for (int is = isave; is < ag.n_save; ++is)
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) p.out[((size_t)is * D + cc) * N + n] = __int_as_float(0x7fc00000);
     }
     if (live) ag.nacc[n] = nacc;
     if (p.status && live) {

@@ -379,14 +379,14 @@ static inline cudaError_t upload_tables(const ConstTables &t, cudaStream_t st)
     // theta changes every optimiser step: always re-sent (device-to-device, stream-ordered, ~5 KB).
     cudaError_t e = cudaMemcpyToSymbolAsync(c_theta, t.d_theta, sizeof(float) * t.P, 0, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
-    static uint64_t last_serial = 0;
-    if (last_serial == t.serial) return cudaSuccess;
+    static SerialCache cache;
+    if (cache.hit(t.serial)) return cudaSuccess;
     e = cudaMemcpyToSymbolAsync(c_consts, t.consts, sizeof(t.consts), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbolAsync(c_lossw, t.lossw, sizeof(t.lossw), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbolAsync(c_acts, t.acts, sizeof(t.acts), 0, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) last_serial = t.serial;
+    if (e == cudaSuccess) cache.set(t.serial);
     return e;
 }
 

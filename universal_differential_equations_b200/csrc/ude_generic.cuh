@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(BLOCK, 1) adaptive_forward_kernel(FwdParams p,
                 ++isave;
             }
             qold = fmaxf(EEst, 1e-4f);
-            if (q >= 1.0f && q <= 1.2f) q = 1.0f;
+            // qsteady_min = qsteady_max = 1 for explicit RK methods in OrdinaryDiffEq (the 6/5 band is the implicit-solver default): no dead band
             if (!clipped || h >= dt) dt = h / q;
             else dt = fmaxf(dt, h / q);
             t = tn;
@@ -490,6 +490,10 @@ __global__ void __launch_bounds__(BLOCK, 1) adaptive_forward_kernel(FwdParams p,
         } else {
             dt = h / fminf(1.0f / qmin, q11 / gamma);
         }
+    }
+    if (bad) {   // failed solve (non-finite error estimate / max_steps): the unreached save points are NaN, as a failed retcode would signal
+        for (int is = isave; is < ap.n_save; ++is)
+            for (int c = 0; c < D; ++c) p.out[((size_t)is * D + c) * N + n] = __int_as_float(0x7fc00000);
     }
     ap.nacc[n] = nacc;
     if (p.status) {
@@ -586,7 +590,7 @@ __global__ void __launch_bounds__(BLOCK, 1) vern7_adaptive_forward_kernel(FwdPar
                 ++isave;
             }
             qold = fmaxf(EEst, 1e-4f);
-            if (q >= 1.0f && q <= 1.2f) q = 1.0f;
+            // qsteady_min = qsteady_max = 1 for explicit RK methods in OrdinaryDiffEq (the 6/5 band is the implicit-solver default): no dead band
             if (!clipped || h >= dt) dt = h / q;
             else dt = fmaxf(dt, h / q);
             t = clipped ? tend : t + h;
@@ -596,6 +600,10 @@ __global__ void __launch_bounds__(BLOCK, 1) vern7_adaptive_forward_kernel(FwdPar
             dt = h / fminf(1.0f / qmin, q11 / gamma);
             have_k1 = true;    // k_1 = f(u) is still valid after a rejection
         }
+    }
+    if (bad) {   // failed solve: the unreached save points are NaN
+        for (int is = isave; is < ap.n_save; ++is)
+            for (int c = 0; c < D; ++c) p.out[((size_t)is * D + c) * N + n] = __int_as_float(0x7fc00000);
     }
     if (ap.nacc) ap.nacc[n] = nacc;
     if (p.status) {

@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import warnings
 from dataclasses import dataclass, field
 from typing import Callable, Optional, Sequence
 
@@ -258,7 +259,19 @@ class RKC2:
         return s
 
 
-ROCK2 = RKC2   # the name the reference's scripts use
+class ROCK2(RKC2):
+    """The name the reference's scripts use (npde.jl:61,82,122).  NOT the ROCK2 algorithm: ROCK2's orthogonal-polynomial
+    recurrence tables are not in the reference, so this selects RKC2 -- a different second-order stabilised explicit
+    method of the same class -- and says so once per process."""
+    _warned = False
+
+    def __init__(self, stages=None, eigen_est=None):
+        if not ROCK2._warned:
+            warnings.warn("ROCK2(...) selects RKC2 (second-order Runge-Kutta-Chebyshev), not OrdinaryDiffEq's ROCK2: same "
+                          "order and stability class, different stage recurrence; results agree to the solver tolerance, not bitwise",
+                          RuntimeWarning, stacklevel=2)
+            ROCK2._warned = True
+        super().__init__(stages, eigen_est)
 
 
 class ReverseDiffVJP:
@@ -344,6 +357,8 @@ class UDESolver:
         self.n_save = int(self._L.b200ude_num_save(h))
         self.d = f.state_dim
         self.capacity = int(max_trajectories)
+        self.adaptive, self.max_steps = bool(adaptive), int(max_steps)
+        self.generation = 0   # bumped by every set_params / forward: identifies the forward record the handle holds
 
     def close(self):
         if getattr(self, "_h", None):
@@ -368,6 +383,7 @@ class UDESolver:
             arr = theta.contiguous()
             _lib.check(self._h, self._L.b200ude_set_params(self._h, arr.data_ptr(), self.P, _lib.HOST, _stream_ptr(self.device)))
         self._theta_keepalive = theta
+        self.generation += 1
 
     def forward(self, u0: torch.Tensor, out: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None):
         """u0[d, N] (cuda float32) -> out[n_save, d, N]."""
@@ -378,6 +394,7 @@ class UDESolver:
             out = torch.empty((self.n_save, self.d, N), device=u0.device, dtype=torch.float32)
         sp = status.data_ptr() if status is not None else None
         _lib.check(self._h, self._L.b200ude_forward(self._h, u0.data_ptr(), N, out.data_ptr(), sp, _stream_ptr(self.device)))
+        self.generation += 1
         return out
 
     def adjoint(self, dL_dout: torch.Tensor, want_grad_u0=True):
@@ -410,6 +427,7 @@ class UDESolver:
         N = u0.shape[1]
         out = np.empty((self.n_save, self.d, N), np.float32)
         status = np.empty(N, np.int32)
+        self.generation += 1
         _lib.check(self._h, self._L.b200ude_solve_host(self._h, theta.ctypes.data, u0.ctypes.data, N, out.ctypes.data, status.ctypes.data))
         return out, status
 
@@ -421,6 +439,7 @@ class UDESolver:
         if grad_theta is None:
             grad_theta = np.empty(self.P, np.float32)
         loss = C.c_double(0.0)
+        self.generation += 1
         _lib.check(self._h, self._L.b200ude_loss_gradient_host(self._h, ptr(theta), ptr(u0), ptr(data), N, C.byref(loss), ptr(grad_theta),
                                                              ptr(grad_u0) if grad_u0 is not None else None))
         return loss.value, grad_theta, grad_u0
@@ -483,6 +502,7 @@ class UDESolver:
         u0, data = u0.contiguous(), data.contiguous()
         if loss_history is None:
             loss_history = torch.empty(iters, device=self.device, dtype=torch.float32)
+        self.generation += 1
         _lib.check(self._h, self._L.b200ude_train_adam(self._h, C.byref(a), u0.data_ptr(), data.data_ptr(), u0.shape[1], iters,
                                                      loss_history.data_ptr(), _stream_ptr(self.device)))
         return loss_history
@@ -494,14 +514,33 @@ class _SolveFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, theta, u0, solver):
         solver.set_params(theta)
-        out = solver.forward(u0)
+        status = torch.zeros(u0.shape[1], dtype=torch.int32, device=u0.device) if solver.adaptive else None
+        out = solver.forward(u0, status=status)
+        if status is not None:
+            # OrdinaryDiffEq reports retcode != Success (MaxIters / Unstable / DtLessThanMin) with a warning; the kernels
+            # fill the unreached save points of a failed trajectory with NaN so that the failure reaches the loss
+            nbad = int((status != 0).sum())
+            if nbad:
+                warnings.warn(f"concrete_solve: {nbad} of {u0.shape[1]} trajectories failed "
+                              f"(status 1 = non-finite, 2 = max_steps={solver.max_steps} reached); their unreached save points are NaN",
+                              RuntimeWarning, stacklevel=3)
+        # the forward record (step states, stage derivatives, theta) lives in the handle, which later calls with the same
+        # key reuse: remember which forward it holds and what produced it, so that backward can restore it
         ctx.solver = solver
+        ctx.gen = solver.generation
+        ctx.theta, ctx.u0 = theta.detach(), u0.detach()
         ctx.need_u0 = u0.requires_grad
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        gth, gu0 = ctx.solver.adjoint(gout, want_grad_u0=True)
+        solver = ctx.solver
+        if solver.generation != ctx.gen:
+            # another forward / set_params used the handle since (two predictions in one loss, multiple shooting,
+            # mini-batches): re-run this call's forward so that the adjoint reads its own record and theta
+            solver.set_params(ctx.theta)
+            solver.forward(ctx.u0)
+        gth, gu0 = solver.adjoint(gout, want_grad_u0=True)
         return gth, (gu0 if ctx.need_u0 else None), None
 
 
@@ -562,8 +601,8 @@ def concrete_solve(prob, alg, u0=None, p=None, *, saveat=None, dt=None, adaptive
            bool(adaptive), abstol, reltol, max_steps)
     solver = _SOLVERS.get(key)
     if solver is None or solver.capacity < N:
-        if solver is not None:
-            solver.close()
+        # a smaller cached solver is only dropped from the cache (not closed): autograd graphs that are still alive
+        # may hold it for their backward pass; its handle is destroyed when the last reference goes
         solver = UDESolver(base.f, t0, dtv, n_steps, save_every, max_trajectories=max(N, 1), device=dev, alg=alg,
                            sensealg=sensealg, loss_weights=loss_weights, adaptive=adaptive, abstol=abstol, reltol=reltol, max_steps=max_steps)
         _SOLVERS[key] = solver
