@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <atomic>
 #include <string>
 
@@ -63,6 +64,7 @@ struct b200ude_handle {
     bool have_forward = false;
     bool have_theta = false;
     int sm_count = 0;
+    size_t wm_fwd_max = 0, wm_adj_max = 0;   // largest ensembles the warp-collective LV kernels are chosen for (auto mode)
     // device buffers
     float *d_theta = nullptr;
     float *d_ustep = nullptr;
@@ -188,6 +190,9 @@ bool generic_ok(const b200ude_desc &d)
     return false;
 }
 
+// kernel family of the LV 2-32-32-2 chain for an ensemble of N: mode 1 = always warp-collective, 0 = never, -1 = by size
+bool use_wm(int mode, size_t N, size_t n_max) { return mode > 0 || (mode < 0 && N <= n_max); }
+
 KernelId pick_kernel(const b200ude_desc &d)
 {
     if (d.model == B200UDE_MODEL_LV && d.state_dim == 2 && d.acts[d.n_layers - 1] == B200UDE_ACT_IDENTITY) {
@@ -230,7 +235,10 @@ int32_t tsit5_forward(b200ude_handle *h, const float *u0, size_t N, float *out, 
         return B200UDE_OK;
     }
     switch (h->kid) {
-    case K_LV32: e = launch_fwd_lv32(h->var, h->tab, p, st); break;
+    case K_LV32:
+        // small / medium ensembles: the warp-collective family (latency per stage ~4x lower); large ones: tcgen05
+        e = use_wm(h->var.fwd_wm, N, h->wm_fwd_max) ? launch_fwd_lv32_wm(h->var, h->tab, p, st) : launch_fwd_lv32(h->var, h->tab, p, st);
+        break;
     case K_LV5P0: e = launch_fwd_lv5(0, h->var, h->tab, p, st); break;
     case K_LV5P1: e = launch_fwd_lv5(1, h->var, h->tab, p, st); break;
     case K_LV5P2: e = launch_fwd_lv5(2, h->var, h->tab, p, st); break;
@@ -317,7 +325,10 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
         return B200UDE_OK;
     }
     switch (h->kid) {
-    case K_LV32: e = launch_adj_lv32(h->var, h->tab, p, st, &grid); break;
+    case K_LV32:
+        e = (!h->var.discrete && use_wm(h->var.adj_wm, h->N, h->wm_adj_max)) ? launch_adj_lv32_wm(h->var, h->tab, p, st, &grid)
+                                                                              : launch_adj_lv32(h->var, h->tab, p, st, &grid);
+        break;
     case K_LV5P0: e = launch_adj_lv5(0, h->var, h->tab, p, st, &grid); break;
     case K_LV5P1: e = launch_adj_lv5(1, h->var, h->tab, p, st, &grid); break;
     case K_LV5P2: e = launch_adj_lv5(2, h->var, h->tab, p, st, &grid); break;
@@ -512,9 +523,15 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     // default: tcgen05 (3xTF32) kernels; B200UDE_FWD_TC=0 / B200UDE_ADJ_TC=0 select the FFMA2-packed CUDA-core kernels
     h->var.fwd_tc = env_int("B200UDE_FWD_TC", 1);
     h->var.adj_tc = env_int("B200UDE_ADJ_TC", 2);   // 2: gradient GEMM on mma.sync (3xTF32), 1: on the FMA pipe (FFMA2)
+    // warp-collective mma.sync family (lv32_wm.cuh): -1 = chosen per call from the ensemble size, 0 = off, 1 = always
+    h->var.fwd_wm = env_int("B200UDE_FWD_WM", -1);
+    h->var.adj_wm = env_int("B200UDE_ADJ_WM", -1);
+    h->var.wm_groups = env_int("B200UDE_WM_G", 1);
+    h->wm_fwd_max = (size_t)env_int("B200UDE_WM_FWD_MAX", 32768);
+    h->wm_adj_max = (size_t)env_int("B200UDE_WM_ADJ_MAX", 16384);
 
     const size_t N = h->cap, D = (size_t)h->D;
-    h->partial_blocks = (size_t)(kid == K_LV32 ? adj_grid_lv32((int)N) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : kid == K_SEIR64 ? adj_rows_seir((int)N) : kid == K_FKPP16 ? adj_rows_fkpp16((int)N, d->state_dim) : adj_grid_lv5((int)N));
+    h->partial_blocks = (size_t)(kid == K_LV32 ? std::max(adj_grid_lv32((int)N), adj_rows_lv32_wm((int)N)) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : kid == K_SEIR64 ? adj_rows_seir((int)N) : kid == K_FKPP16 ? adj_rows_fkpp16((int)N, d->state_dim) : adj_grid_lv5((int)N));
     bool ok = true;
     ok = ok && dalloc(h, &h->d_theta, (size_t)((h->P + 3) / 4) * 4) == cudaSuccess;
     const size_t rec_steps = h->adaptive ? (size_t)d->max_steps : (size_t)d->n_steps;   // capacity of the step record

@@ -48,6 +48,9 @@ struct Variant {
     int fwd_tc = 0;      // 1: tcgen05 (3xTF32) forward kernel
     int adj_tc = 0;      // 1: tcgen05 (3xTF32) adjoint kernel, FFMA2 gradient GEMM; 2: mma.sync gradient GEMM
     int discrete = 0;    // 1: discrete adjoint (exact gradient of the fixed-step scheme) instead of the interpolating adjoint
+    int fwd_wm = 0;      // 1: warp-collective mma.sync forward kernel (lv32_wm.cuh)
+    int adj_wm = 0;      // 1: warp-collective mma.sync adjoint kernel
+    int wm_groups = 1;   // groups of 16 trajectories per warp in the warp-collective forward kernel (1, 2 or 4)
 };
 
 // function attributes (dynamic shared-memory size) are per device: one-time flags are kept per device ordinal
@@ -103,6 +106,9 @@ cudaError_t launch_adj_lv32(const Variant &, const ConstTables &, const AdjParam
 cudaError_t launch_fwd_lv5(int n_prefix, const Variant &, const ConstTables &, const FwdParams &, cudaStream_t);
 cudaError_t launch_adj_lv5(int n_prefix, const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *grid_out);
 int adj_grid_lv32(int N);
+cudaError_t launch_fwd_lv32_wm(const Variant &, const ConstTables &, const FwdParams &, cudaStream_t);
+cudaError_t launch_adj_lv32_wm(const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *rows_out);
+int adj_rows_lv32_wm(int N);
 cudaError_t launch_fwd_lv32_adaptive(const Variant &, const ConstTables &, const FwdParams &, const AdaptiveGrid &, cudaStream_t);
 cudaError_t launch_adj_lv32_adaptive(const Variant &, const ConstTables &, const AdjParams &, const AdaptiveGrid &, cudaStream_t, int *rows_out);
 int adj_grid_lv5(int N);
