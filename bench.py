@@ -1,14 +1,17 @@
 #!/usr/bin/env python3
-"""bench.py -- ensemble trajectories/s, forward + interpolating adjoint, LV UDE (BASELINE config 2).
+"""bench.py -- ensemble trajectories/s, forward + interpolating adjoint (BASELINE.json's metric).
 
-One "step" = one pass of the hot path over one batch of synthetic input: forward Tsit5 solve of
-every trajectory (30 fixed steps of 0.1, states saved at every step) + InterpolatingAdjoint gradient
-of the L2 trajectory-matching loss, summed over the ensemble (+ one NCCL all-reduce of
-[grad_theta; loss] when N_gpus > 1).  Workload: 65 536 trajectories PER GPU (weak scaling; the
-ensemble shards across ranks with no data-path collective), 2->32->32->2
-tanh chain, Glorot theta (seed 1), u0 ~ U(0.2,1) x U(2,5) (seed 0), fp32.
+One "step" = one pass of the hot path over one batch of synthetic input: forward Tsit5 solve of every trajectory +
+InterpolatingAdjoint gradient of the L2 trajectory-matching loss, summed over the ensemble (+ the sum over ranks of
+[grad_theta; loss] when N_gpus > 1, fused into the final reduction kernel over NVLink peer memory).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config lv|seir|fkpp]
+
+--config lv (default, BASELINE config 2): 2->32->32->2 tanh chain, Glorot theta (seed 1), u0 ~ U(0.2,1) x U(2,5), 30 fixed
+  Tsit5 steps of 0.1, states saved at every step, fp32.  The headline `value` is WEAK scaling (65 536 trajectories per GPU);
+  the `strong` object of the same line is the metric's literal batch: 65 536 trajectories IN TOTAL over the N GPUs.
+--config seir (config 3): 7-state SEIR exposure UDE, 3->64->64->1 chain, 84 steps of 0.25, saved daily, loss on E, I, R.
+--config fkpp (config 4): Fisher-KPP UPDE on a 256-point grid, 1->16->16->1 reaction chain + 3-tap stencil, 200 steps.
 Under torchrun one rank per GPU.  Rank 0 prints ONE JSON line.
 """
 import argparse
@@ -19,33 +22,160 @@ import sys
 import threading
 import time
 
-import numpy as np
+# the CPU legs run the OpenMP oracle: bind its threads before any OpenMP runtime is loaded
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_PER_GPU = 65536
-N_STEPS, DT = 30, 0.1
-WIDTHS = (2, 32, 32, 2)
-P = 1218
-METRIC = "ensemble trajectories/sec fwd+adjoint, LV UDE batch 65k"
 UNIT = "trajectories/s"
-
-# algorithmic cost per trajectory (DESIGN.md "Measurement")
-FMA_RHS = 2 * 32 + 32 * 32 + 32 * 2                                  # 1152 FMA per chain evaluation
-FLOP_FWD = 2.0 * FMA_RHS * (1 + 6 * N_STEPS)                           # 181 RHS evaluations
-FLOP_ADJ = 2.0 * 3 * FMA_RHS * (6 * N_STEPS)                           # 180 backward stages x (fwd + J_u^T + J_theta^T)
-BYTES_FWD = 4.0 * (2 + 2 * (N_STEPS + 1) * 2 + (6 * N_STEPS + 1) * 2)  # u0 + out + per-step store + dense output
-BYTES_ADJ = 4.0 * ((N_STEPS + 1) * 2 * 2 + (6 * N_STEPS + 1) * 2 + 2)  # per-step store + data + dense output + grad_u0
-FP32_PEAK_TFLOPS = 72.5  # measured FFMA/FFMA2 issue peak on this pool's B200 (profiles/r01_pipes_microbench.txt)
+FP32_PEAK_TFLOPS = 72.5     # measured FFMA/FFMA2 issue peak on this pool's B200 (profiles/r01_pipes_microbench.txt)
+MUFU_PER_CLK_SM = 16.0      # measured (profiles/r01_pipes_microbench.txt): 0.499 warp instructions / clk / SM
+HMMA_PER_CLK_SM = 0.468     # measured mma.sync m16n8k8.tf32 / m16n8k16.f16 warp instructions / clk / SM (profiles/r01_mma_sync_microbench.txt)
 
 
-def synthetic(n, seed=0):
-    from helpers import glorot_theta, synthetic_ensemble
-    theta = glorot_theta(WIDTHS, seed=1)
-    u0, y = synthetic_ensemble(n, n_steps=N_STEPS, dt=DT, seed=seed)
-    return theta, u0, y
+def host_cores():
+    """Usable host cores: the affinity mask capped by the cgroup CPU quota (a 16-CPU quota on a 128-thread host
+    is what made round 1's CPU arm swing 5x between boxes: 128 threads were time-sliced onto 16 CPUs)."""
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    cores = aff if quota is None else max(1, min(aff, int(quota)))
+    return cores, aff, quota
+
+
+# ----------------------------------------------------------------------------------------------- workloads
+class LV:
+    """BASELINE config 2."""
+    name = "lv"
+    metric = "ensemble trajectories/sec fwd+adjoint, LV UDE batch 65k"
+    workload = "LV UDE ensemble, 2->32->32->2 tanh, Tsit5 dt=0.1 x30 saveat 0.1, fwd + InterpolatingAdjoint + L2 loss"
+    n_steps, dt, every, D = 30, 0.1, 1, 2
+    widths = (2, 32, 32, 2)
+    P = 1218
+    n_default = 65536
+    fma_rhs = 2 * 32 + 32 * 32 + 32 * 2                                    # 1152 FMA per chain evaluation
+    flop_fwd = 2.0 * fma_rhs * (1 + 6 * n_steps)                            # 181 RHS evaluations
+    flop_adj = 2.0 * 3 * fma_rhs * (6 * n_steps)                            # 180 backward stages x (fwd + J_u^T + J_theta^T)
+    bytes_fwd = 4.0 * (2 + 2 * (n_steps + 1) * 2 + (6 * n_steps + 1) * 2)   # u0 + out + per-step store + dense output
+    bytes_adj = 4.0 * ((n_steps + 1) * 2 * 2 + (6 * n_steps + 1) * 2 + 2)   # per-step store + data + dense output + grad_u0
+    loss_weights = None
+
+    @staticmethod
+    def synthetic(n, seed=0):
+        from helpers import glorot_theta, synthetic_ensemble
+        theta = glorot_theta(LV.widths, seed=1)
+        u0, y = synthetic_ensemble(n, n_steps=LV.n_steps, dt=LV.dt, seed=seed)
+        return theta, u0, y
+
+    @staticmethod
+    def make_solver(ude, n, dev):
+        chain = ude.FastChain(ude.FastDense(2, 32, ude.tanh), ude.FastDense(32, 32, ude.tanh), ude.FastDense(32, 2))
+        return ude.UDESolver(ude.LotkaVolterraUDE(chain), 0.0, LV.dt, LV.n_steps, LV.every, max_trajectories=n, device=dev)
+
+    @staticmethod
+    def oracle_model(O):
+        return O.lv_model(), np.ones(2, np.float32)
+
+
+class SEIR:
+    """BASELINE config 3 in the reference's own shape (seir_exposure.jl:114-130): 7 states, chain 3->64->64->1 on [S/N, I, D/N]."""
+    name = "seir"
+    metric = "ensemble trajectories/sec fwd+adjoint, SEIR exposure UDE batch 65k"
+    workload = "SEIR exposure UDE 7-state 3->64->64->1 tanh, Tsit5 dt=0.25 x84 over (0,21) saved daily, loss on E,I,R, fwd + InterpolatingAdjoint"
+    n_steps, dt, every, D = 84, 0.25, 4, 7
+    widths = (3, 64, 64, 1)
+    P = 3 * 64 + 64 + 64 * 64 + 64 + 64 + 1
+    n_default = 65536
+    fma_rhs = 3 * 64 + 64 * 64 + 64
+    flop_fwd = 2.0 * fma_rhs * (1 + 6 * n_steps)
+    flop_adj = 2.0 * 3 * fma_rhs * (6 * n_steps)
+    bytes_fwd = 4.0 * (7 + 7 * (n_steps // every + 1) + 7 * (n_steps + 1) + (6 * n_steps + 1) * 7)
+    bytes_adj = 4.0 * (7 * (n_steps + 1) + 7 * (n_steps // every + 1) + (6 * n_steps + 1) * 7 + 7)
+    loss_weights = [0, 1, 1, 1, 0, 0, 0]
+
+    @staticmethod
+    def synthetic(n, seed=0):
+        from helpers import glorot_theta
+        rng = np.random.default_rng(seed)
+        theta = glorot_theta(SEIR.widths, seed=2)
+        S0 = 14e6
+        u0 = np.zeros((7, n), np.float32)
+        u0[0] = 0.9 * S0 * rng.uniform(0.9, 1.0, n)
+        u0[1:4] = rng.uniform(0, 50, (3, n))
+        u0[4] = S0
+        y = rng.uniform(0, 100, (SEIR.n_steps // SEIR.every + 1, 7, n)).astype(np.float32)
+        return theta, u0, y
+
+    @staticmethod
+    def make_solver(ude, n, dev):
+        chain = ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1))
+        return ude.UDESolver(ude.SEIRExposureUDE(chain), 0.0, SEIR.dt, SEIR.n_steps, SEIR.every, max_trajectories=n, device=dev,
+                             loss_weights=SEIR.loss_weights)
+
+    @staticmethod
+    def oracle_model(O):
+        return O.seir_model(), np.asarray(SEIR.loss_weights, np.float32)
+
+
+class FKPP:
+    """BASELINE config 4's shape (256-point grid, 1->16->16->1 reaction chain + 3-tap periodic stencil), Tsit5."""
+    name = "fkpp"
+    metric = "ensemble trajectories/sec fwd+adjoint, Fisher-KPP UPDE 256-point grid"
+    workload = "Fisher-KPP UPDE 256-point grid, 1->16->16->1 tanh + 3-tap stencil, Tsit5 dt=1e-3 x200, fwd + InterpolatingAdjoint"
+    Nx = 256
+    n_steps, dt, every, D = 200, 1.0e-3, 20, 256
+    widths = (1, 16, 16, 1)
+    P = 16 + 16 + 256 + 16 + 16 + 1 + 5
+    n_default = 8192
+    fma_rhs = Nx * (16 + 256 + 16 + 4)
+    flop_fwd = 2.0 * fma_rhs * (1 + 6 * n_steps)
+    flop_adj = 2.0 * 3 * fma_rhs * (6 * n_steps)
+    bytes_fwd = 4.0 * Nx * (1 + (n_steps // every + 1) + (n_steps + 1) + (6 * n_steps + 1))
+    bytes_adj = 4.0 * Nx * ((n_steps + 1) + (n_steps // every + 1) + (6 * n_steps + 1) + 1)
+    loss_weights = None
+
+    @staticmethod
+    def synthetic(n, seed=0):
+        from helpers import glorot_theta
+        rng = np.random.default_rng(seed)
+        Nx = FKPP.Nx
+        D0 = 0.01 * (Nx - 1) ** 2                       # D / dx^2 with the reference's D = 0.01 (Fisher-KPP-CNN.jl:16-25)
+        theta = np.concatenate([glorot_theta(FKPP.widths, seed=3), [1.0, -2.0, 1.0, 0.0, D0]]).astype(np.float32)
+        x = np.linspace(0, 1, Nx)
+        d = rng.uniform(0.15, 0.5, n)[None, :]
+        u0 = (0.5 * (np.tanh((x[:, None] - (0.5 - d / 2)) / (d / 10)) - np.tanh((x[:, None] - (0.5 + d / 2)) / (d / 10)))).astype(np.float32)
+        y = np.repeat(u0[None], FKPP.n_steps // FKPP.every + 1, axis=0)
+        return theta, u0, y
+
+    @staticmethod
+    def make_solver(ude, n, dev):
+        layers = [ude.FastDense(1, 16, ude.tanh), ude.FastDense(16, 16, ude.tanh), ude.FastDense(16, 1)]
+        return ude.UDESolver(ude.FisherKPPUDE(ude.FastChain(*layers), FKPP.Nx), 0.0, FKPP.dt, FKPP.n_steps, FKPP.every, max_trajectories=n, device=dev)
+
+    @staticmethod
+    def oracle_model(O):
+        return O.fkpp_model(FKPP.Nx, FKPP.widths, ("tanh", "tanh", "identity")), np.ones(FKPP.Nx, np.float32)
+
+
+CONFIGS = {"lv": LV, "seir": SEIR, "fkpp": FKPP}
+HOST = None
 
 
 class ClockSampler:
@@ -86,20 +216,58 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline_run(theta, u0, y, sample, threads, reps=1):
-    """The oracle port (C99/OpenMP, fp32, same algorithm) on a bounded sample of the same workload."""
+def cpu_pass(cfg, theta, u0, y, threads):
+    """One pass of the oracle port (C99/OpenMP, fp32, same algorithm) over the given trajectories; returns seconds."""
     from oracle import oracle as O
-    m = O.lv_model()
-    th = theta.astype(np.float32)
-    u0s, ys = np.ascontiguousarray(u0[:, :sample]), np.ascontiguousarray(y[:, :, :sample])
-    w = np.ones(2, np.float32)
-    best = float("inf")
-    O.ensemble_loss_grad(m, th, u0s[:, :256], ys[:, :, :256], w, DT, N_STEPS, n_threads=threads, want_gu0=True)  # warm
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        O.ensemble_loss_grad(m, th, u0s, ys, w, DT, N_STEPS, n_threads=threads, want_gu0=True)
-        best = min(best, time.perf_counter() - t0)
-    return sample / best, best
+    m, w = cfg.oracle_model(O)
+    t0 = time.perf_counter()
+    O.ensemble_loss_grad(m, theta.astype(np.float32), u0, y, w, cfg.dt, cfg.n_steps, save_every=cfg.every, n_threads=threads, want_gu0=True)
+    return time.perf_counter() - t0
+
+
+def reference_arm(a, cfg):
+    """The reference's own path (OrdinaryDiffEq.jl + SciMLSensitivity.jl) needs Julia, which this image does not have
+    (BASELINE.md section 2): the CPU arm is the oracle port on the usable host cores."""
+    cores, aff, quota = HOST
+    n = a.n_per_gpu or cfg.n_default          # the SAME batch as the GPU arm's per-step workload (one GPU's share)
+    if cfg is not LV and not a.n_per_gpu:
+        n = min(n, 4096 if cfg is SEIR else 256)   # secondary configs: bounded sample (SEIR ~30x, FKPP ~1000x the LV cost per trajectory)
+    theta, u0, y = cfg.synthetic(n)
+    for _ in range(max(1, min(a.warmup, 2))):
+        k = min(n, 1024)
+        cpu_pass(cfg, theta, np.ascontiguousarray(u0[:, :k]), np.ascontiguousarray(y[:, :, :k]), cores)
+    times = [cpu_pass(cfg, theta, u0, y, cores) for _ in range(max(3, a.steps))]
+    med = float(np.median(times))
+    value = n / med
+    same = (cfg is LV and n == N_PER_GPU)
+    print(json.dumps({
+        "impl": "reference", "metric": cfg.metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": len(times),
+        "warmup": a.warmup, "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg.workload, "trajectories_per_step": n, "same_batch_as_gpu_arm": same,
+                   "statistic": "median over the timed passes"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} trajectories per step x {len(times)} steps (median), oracle C99/OpenMP fp32, {cores} threads "
+                                   f"(affinity {aff}, cgroup quota {quota}), OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}",
+                         "pass_seconds": [round(t, 4) for t in times]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def kernel_names(run_step, torch):
+    """Names of the kernels one step launches, observed with CUPTI (torch.profiler) on an untimed step."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run_step()
+            torch.cuda.synchronize()
+        names = []
+        for e in prof.events():
+            if str(getattr(e, "device_type", "")).endswith("CUDA") and not e.name.startswith(("Memcpy", "Memset")):
+                names.append(e.name)
+        return names, "torch.profiler (CUPTI) on one untimed step"
+    except Exception as ex:  # noqa: BLE001
+        return None, f"profiler unavailable: {ex}"
 
 
 def main():
@@ -108,41 +276,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--config", default="lv", choices=sorted(CONFIGS))
+    ap.add_argument("--n-per-gpu", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories in the in-line CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     a = ap.parse_args()
+    cfg = CONFIGS[a.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
+    global HOST
+    HOST = host_cores()   # before NCCL / CUDA initialisation can narrow the calling thread's affinity
     if a.impl == "reference":
-        # The reference's own path (OrdinaryDiffEq.jl + SciMLSensitivity.jl) needs Julia, which this image
-        # does not have: the CPU arm is the oracle port, all host cores, bounded sample.
-        if rank != 0:
-            return
-        theta, u0, y = synthetic(8192)
-        sample = a.cpu_sample or 8192
-        vals = []
-        for _ in range(max(1, a.warmup)):
-            cpu_baseline_run(theta, u0, y, min(sample, 1024), cores)
-        t_all = 0.0
-        for _ in range(a.steps):
-            v, t = cpu_baseline_run(theta, u0, y, sample, cores)
-            vals.append(v)
-            t_all += t
-        value = sample * a.steps / t_all
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * t_all / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "LV UDE ensemble, 2->32->32->2 tanh, Tsit5 dt=0.1 x30, fwd+InterpolatingAdjoint",
-                       "sample_trajectories_per_step": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} trajectories per step x {a.steps} steps, oracle C99/OpenMP fp32, {cores} threads"},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        if rank == 0:
+            reference_arm(a, cfg)
         return
 
     import torch
@@ -153,18 +302,12 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = a.n_per_gpu
-    theta, u0, y = synthetic(n, seed=rank)   # every rank owns a different shard of the (world * n) ensemble
-    chain = ude.FastChain(ude.FastDense(2, 32, ude.tanh), ude.FastDense(32, 32, ude.tanh), ude.FastDense(32, 2))
-    f = ude.LotkaVolterraUDE(chain)
-    solver = ude.UDESolver(f, 0.0, DT, N_STEPS, 1, max_trajectories=n, device=dev)
-    th_d = torch.from_numpy(theta).to(dev)
-    u0_d = torch.from_numpy(u0).to(dev)
-    y_d = torch.from_numpy(y).to(dev)
-    out_d = torch.empty((N_STEPS + 1, 2, n), device=dev)
-    buf = torch.zeros(P + 1, device=dev)          # [grad_theta ; loss] -- the one all-reduced message
+    n = a.n_per_gpu or cfg.n_default
+    P, D = cfg.P, cfg.D
+    n_save = cfg.n_steps // cfg.every + 1
+    solver = cfg.make_solver(ude, n, dev)
+    assert solver.P == P, (solver.P, P)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    solver.set_params(th_d)
     # multi-GPU: the sum over ranks of [grad_theta; loss] runs inside the final reduction kernel over NVLink peer memory
     # (b200ude_adjoint_l2_allreduce); NCCL all-reduce only if the peer mapping cannot be set up on every rank
     peer = None
@@ -181,47 +324,110 @@ def main():
                 solver.peer_detach()
             peer = None
 
-    def step(ev=None, collective=True):
-        solver.set_params(th_d)
+    class Shard:
+        """One rank's share of an ensemble, resident in HBM."""
+
+        def __init__(self, n_local, seed):
+            self.n = n_local
+            self.theta, self.u0, self.y = cfg.synthetic(n_local, seed=seed)
+            self.th_d = torch.from_numpy(self.theta).to(dev)
+            self.u0_d = torch.from_numpy(self.u0).to(dev)
+            self.y_d = torch.from_numpy(self.y).to(dev)
+            self.out_d = torch.empty((n_save, D, n_local), device=dev)
+            self.buf = torch.zeros(P + 1, device=dev)          # [grad_theta ; loss] -- the one all-reduced message
+
+    def step(sh, ev=None, collective=True):
+        solver.set_params(sh.th_d)
         if ev:
             ev[0].record()
-        solver.forward(u0_d, out=out_d)
+        solver.forward(sh.u0_d, out=sh.out_d)
         if ev:
             ev[1].record()
         if peer is not None and collective:
-            solver.adjoint_l2_allreduce(y_d, want_grad_u0=False, grad_theta=buf[:P], loss=buf[P:])
+            solver.adjoint_l2_allreduce(sh.y_d, want_grad_u0=False, grad_theta=sh.buf[:P], loss=sh.buf[P:])
             if ev:
                 ev[2].record()
         else:
-            solver.adjoint_l2(y_d, want_grad_u0=False, grad_theta=buf[:P], loss=buf[P:])
+            solver.adjoint_l2(sh.y_d, want_grad_u0=False, grad_theta=sh.buf[:P], loss=sh.buf[P:])
             if ev:
                 ev[2].record()
             if collective:
-                ude.allreduce_loss_grad(buf)
+                ude.allreduce_loss_grad(sh.buf)
         if ev:
             ev[3].record()
 
+    def timed(sh):
+        """W warm-up steps, then K steps timed with CUDA events on the launch stream; L2 flushed between iterations;
+        barrier + synchronize on both sides; max over ranks."""
+        for _ in range(a.warmup):
+            step(sh)
+        torch.cuda.synchronize()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(a.steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(a.steps):
+            flush.zero_()                          # evict L2 between timed iterations (untimed)
+            step(sh, evs[i])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_step = [e[0].elapsed_time(e[3]) for e in evs]
+        total_ms = float(sum(t_step))
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t)
+        return {"total_ms": total_ms, "fwd_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in evs])),
+                "adj_ms": float(np.mean([e[1].elapsed_time(e[2]) for e in evs])), "step_ms": float(np.mean(t_step))}
+
     clk = ClockSampler(local)
-    clk.__enter__()                                  # samples run from the warm-up through the timed region
-    for _ in range(a.warmup):
-        step()
-    torch.cuda.synchronize()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(a.steps)]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    for i in range(a.steps):
-        flush.zero_()                          # evict L2 between timed iterations (untimed)
-        step(evs[i])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    # the timed region of the default run lasts ~0.1 s, shorter than nvidia-smi's sampling period: keep the
-    # same step running (untimed) until the sampler has seen the GPU under this load a few times
+    clk.__enter__()                                  # samples run from the warm-up through the timed regions
+    weak = Shard(n, seed=rank)                       # every rank owns a different shard of the (world * n) ensemble
+    tw = timed(weak)
+    value = world * n * a.steps / (tw["total_ms"] * 1e-3)
+
+    # ---- the metric's literal batch: 65 536 trajectories in total, sharded over the ranks (strong scaling) ----
+    strong = None
+    if cfg is LV and not a.no_strong:
+        total = N_PER_GPU
+        lo, hi = ude.shard_range(total, rank, world)
+        if world == 1 and n == total:
+            ts, ns = tw, n
+        else:
+            sh = Shard(hi - lo, seed=1000 + rank)
+            ts, ns = timed(sh), hi - lo
+            del sh
+        strong = {"global_trajectories": total, "trajectories_per_gpu": ns, "value": total * a.steps / (ts["total_ms"] * 1e-3),
+                  "unit": UNIT, "ms_per_step": ts["total_ms"] / a.steps, "scaling": "strong",
+                  "kernel_ms": {"forward": ts["fwd_ms"], "adjoint_plus_reduce": ts["adj_ms"]},
+                  "note": "BASELINE.json's literal batch: the 65 536 trajectories are sharded over the GPUs; same timing protocol as the headline value"}
+
+    # ---- one-shot untimed check of the fused all-reduce against NCCL (the sums every rank must hold) ----
+    allreduce_check = None
+    if world > 1 and peer is not None:
+        ref = torch.zeros(P + 1, device=dev)
+        solver.set_params(weak.th_d)
+        solver.forward(weak.u0_d, out=weak.out_d)
+        solver.adjoint_l2(weak.y_d, want_grad_u0=False, grad_theta=ref[:P], loss=ref[P:])
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        solver.adjoint_l2_allreduce(weak.y_d, want_grad_u0=False, grad_theta=weak.buf[:P], loss=weak.buf[P:])
+        torch.cuda.synchronize()
+        err = ((weak.buf - ref).abs().max() / ref.abs().max()).reshape(1)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        same = weak.buf.clone()
+        dist.broadcast(same, src=0)
+        ident = torch.tensor([1.0 if torch.equal(same, weak.buf) else 0.0], device=dev)
+        dist.all_reduce(ident, op=dist.ReduceOp.MIN)
+        allreduce_check = {"max_abs_diff_vs_nccl_rel": float(err), "bitwise_identical_on_all_ranks": bool(float(ident) == 1.0),
+                           "entries": P + 1}
+
+    # the timed region of the default run is shorter than nvidia-smi's sampling period: keep the same step running
+    # (untimed) until the sampler has seen the GPU under this load a few times
     t_probe = time.perf_counter()
     while rank == 0 and len(clk.rows) < 6 and time.perf_counter() - t_probe < 4.0:
-        step(collective=False)                 # rank-local: no collective outside the lock-stepped region
+        step(weak, collective=False)           # rank-local: no collective outside the lock-stepped region
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -229,20 +435,16 @@ def main():
     clocks = clk.summary() if rank == 0 else None
     if clocks:
         clocks["window"] = "warm-up + timed steps + post-run probe of the same step (untimed)"
-    t_step = [e[0].elapsed_time(e[3]) for e in evs]
-    t_fwd = [e[0].elapsed_time(e[1]) for e in evs]
-    t_adj = [e[1].elapsed_time(e[2]) for e in evs]
-    total_ms = float(sum(t_step))
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t)
-    value = world * n * a.steps / (total_ms * 1e-3)
+
+    # kernels of one step, observed (rank 0, untimed, no collective)
+    names, names_src = (None, None)
+    if rank == 0:
+        names, names_src = kernel_names(lambda: step(weak, collective=False), torch)
 
     # ---- end-to-end through the host-buffer C-ABI call: pinned host inputs, H2D + kernels + D2H every step ----
-    th_h = torch.from_numpy(theta).pin_memory()
-    u0_h = torch.from_numpy(u0).pin_memory()
-    y_h = torch.from_numpy(y).pin_memory()
+    th_h = torch.from_numpy(weak.theta).pin_memory()
+    u0_h = torch.from_numpy(weak.u0).pin_memory()
+    y_h = torch.from_numpy(weak.y).pin_memory()
     g_h = torch.empty(P).pin_memory()
     for _ in range(4):
         solver.loss_gradient_host(th_h, u0_h, y_h, grad_theta=g_h)
@@ -254,9 +456,9 @@ def main():
     for _ in range(e2e_steps):
         l_h, _, _ = solver.loss_gradient_host(th_h, u0_h, y_h, grad_theta=g_h)
         if world > 1:
-            buf[:P].copy_(g_h, non_blocking=True)
-            buf[P] = l_h
-            ude.allreduce_loss_grad(buf)
+            weak.buf[:P].copy_(g_h, non_blocking=True)
+            weak.buf[P] = l_h
+            ude.allreduce_loss_grad(weak.buf)
             torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -264,7 +466,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t)
     e2e_value = world * n * e2e_steps / e2e_s
-    h2d = 4 * (P + u0.size + y.size)
+    h2d = 4 * (P + weak.u0.size + weak.y.size)
     d2h = 4 * (P + 1)
 
     if rank != 0:
@@ -278,60 +480,96 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    adj_ms = float(np.mean(t_adj))
-    fwd_ms = float(np.mean(t_fwd))
+    adj_ms, fwd_ms = tw["adj_ms"], tw["fwd_ms"]
+    adj_name = next((k for k in (names or []) if "adjoint" in k), "adjoint kernel")
+    fwd_name = next((k for k in (names or []) if "forward" in k), "forward kernel")
+    traffic, traffic_src = None, "no ncu capture of this kernel committed for this round"
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from this round's ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        ent = tj.get(cfg.name, {})
+        if ent and ent.get("trajectories"):
+            traffic = float(ent["dram_bytes"]) * (n / float(ent["trajectories"]))
+            traffic_src = ent.get("source", "profiles/r02_ncu_traffic.json")
+    except Exception:
+        pass
     roofline = {
-        "kernel": "lv32::tc::adjoint_kernel (+ the ~5 us fixed-order reduce; events bracket both)",
-        "bound": "hbm", "achieved": n * BYTES_ADJ / (adj_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": n * BYTES_ADJ / (adj_ms * 1e-3) / 1e9 / hbm_peak,
+        "kernel": f"{adj_name} (+ the ~5 us fixed-order reduce; events bracket both)",
+        "bound": "hbm", "achieved": n * cfg.bytes_adj / (adj_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": n * cfg.bytes_adj / (adj_ms * 1e-3) / 1e9 / hbm_peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
-        "traffic": 132.5e6 * (n / 65536.0),
-        "traffic_source": "ncu --set full capture of this kernel at N=65536: dram read 127.5 MB + write 5.0 MB (profiles/r01b_ncu_kernel_summaries.txt); algorithmic bytes %.1f MB" % (65536 * BYTES_ADJ / 1e6),
-        "note": "the path is compute-bound by construction (SURVEY.md 8d, ~430 FLOP/B): roofline_fp32 (CUDA-core FP32 peak, which the tensor-core kernels bypass for the 32x32 layers) and roofline_xu (MUFU, the nearest bound of the tensor-core forward kernel) are the informative ones",
+        "algorithmic_bytes_per_trajectory": cfg.bytes_adj, "traffic": traffic, "traffic_source": traffic_src,
+        "note": "the path is compute-bound by construction (SURVEY.md 8d, ~430 FLOP/B for config 2): roofline_pipes grades the kernels against the pipes they actually use",
     }
-    roofline_fp32 = {
-        "kernel_adjoint": {"achieved": n * FLOP_ADJ / (adj_ms * 1e-3) / 1e12, "ms": adj_ms},
-        "kernel_forward": {"achieved": n * FLOP_FWD / (fwd_ms * 1e-3) / 1e12, "ms": fwd_ms},
-        "step": {"achieved": n * (FLOP_FWD + FLOP_ADJ) / (float(np.mean(t_step)) * 1e-3) / 1e12},
-        "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-        "frac_adjoint": n * FLOP_ADJ / (adj_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
-        "frac_step": n * (FLOP_FWD + FLOP_ADJ) / (float(np.mean(t_step)) * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
-        "peak_source": "measured FFMA2 issue peak, tools/microbench/pipes.cu on this pool (profiles/r01_pipes_microbench.txt)",
-        "flop_per_trajectory": FLOP_FWD + FLOP_ADJ,
-    }
-    # MUFU (XU pipe) roofline: 2 MUFU per tanh, 64 tanh per chain evaluation; measured peak 16 lanes/clk/SM
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    xu_peak = 148 * 16 * sm_clock * 1e6
-    roofline_xu = {
-        "forward": {"achieved": n * 128.0 * (1 + 6 * N_STEPS) / (fwd_ms * 1e-3), "frac": n * 128.0 * (1 + 6 * N_STEPS) / (fwd_ms * 1e-3) / xu_peak},
-        "adjoint": {"achieved": n * 128.0 * 6 * N_STEPS / (adj_ms * 1e-3), "frac": n * 128.0 * 6 * N_STEPS / (adj_ms * 1e-3) / xu_peak},
-        "peak": xu_peak, "unit": "MUFU op/s",
-        "peak_source": "16 MUFU lanes/clk/SM measured by tools/microbench/pipes.cu (profiles/r01_pipes_microbench.txt) x 148 SMs x sampled SM clock",
+    line_extra = {}
+    if cfg is LV:
+        wm = any("wm::" in k for k in (names or []))
+        # per-trajectory pipe work of the kernels that ran: MUFU lane-ops, legacy tensor-pipe (HMMA) warp
+        # instructions, FMA-pipe cycles and issue slots (static SASS counts of the stage loop bodies, cuobjdump), HBM bytes
+        ev_f, ev_a = 1 + 6 * cfg.n_steps, 6 * cfg.n_steps
+        mufu = 80.0 if wm else 128.0                       # per chain evaluation: 64 tanh x 1.25 (batched inversion) / x 2
+        fam = {   # per trajectory and stage evaluation: (forward, adjoint)
+            "hmma": (24.0 / 16.0, 96.0 / 16.0) if wm else (0.0, 96.0 / 32.0),          # warp-level mma.sync instructions
+            "fma_cyc": (279.0 / 16.0, 500.0 / 16.0) if wm else (600.0 / 32.0, 1700.0 / 32.0),   # FMA-pipe cycles (FFMA2 = 2), per scheduler
+            "issue": (500.0 / 16.0, 950.0 / 16.0) if wm else (887.0 / 32.0, 2268.0 / 32.0),     # warp instructions issued
+        }
+        clk_hz = sm_clock * 1e6
+
+        def pipes(ms, evals, which, nbytes):
+            t = ms * 1e-3
+            b = {"mufu": n * evals * mufu / (148 * MUFU_PER_CLK_SM * clk_hz),
+                 "tensor_mma_sync": n * evals * fam["hmma"][which] / (148 * HMMA_PER_CLK_SM * clk_hz),
+                 "fma_pipe": n * evals * fam["fma_cyc"][which] / (148 * 4 * clk_hz),
+                 "issue_slots": n * evals * fam["issue"][which] / (148 * 4 * clk_hz),
+                 "hbm": n * nbytes / (hbm_peak * 1e9)}
+            tmin = max(b.values())
+            return {"ms": ms, "t_min_ms": 1e3 * tmin, "binding_pipe": max(b, key=b.get), "frac": tmin / t,
+                    "pipe_ms": {k: 1e3 * v for k, v in b.items()}}
+        line_extra["roofline_pipes"] = {
+            "forward": pipes(fwd_ms, ev_f, 0, cfg.bytes_fwd), "adjoint": pipes(adj_ms, ev_a, 1, cfg.bytes_adj),
+            "kernel_family": "warp-collective mma.sync (lv32_wm.cuh)" if wm else "tcgen05 (lv32_tc.cuh)",
+            "peaks": {"mufu_lanes_per_clk_sm": MUFU_PER_CLK_SM, "mma_sync_warp_instr_per_clk_sm": HMMA_PER_CLK_SM, "issue_slots_per_clk_sm": 4, "fma_pipe_cycles_per_clk_sm": 4,
+                      "hbm_gbs": hbm_peak, "sm_mhz": sm_clock},
+            "peak_source": "tools/microbench (profiles/r01_pipes_microbench.txt, r01_mma_sync_microbench.txt), MEASURED_PEAKS.json",
+            "note": "t_min = max over pipes of (work / measured pipe peak); frac = t_min / measured time; the tcgen05 pipe of the tensor-core family is far from binding and not listed",
+        }
+    line_extra["roofline_fp32"] = {
+        "step_achieved_tflops": n * (cfg.flop_fwd + cfg.flop_adj) / (tw["step_ms"] * 1e-3) / 1e12, "peak": FP32_PEAK_TFLOPS,
+        "note": "algorithmic FLOP rate for context only: most of these FLOPs run on tensor cores, so this is not a roofline fraction",
+        "flop_per_trajectory": cfg.flop_fwd + cfg.flop_adj,
     }
     cpu = None
-    if not a.no_cpu_baseline:
-        sample = a.cpu_sample or 4096
-        v, t = cpu_baseline_run(theta, u0, y, min(sample, n), cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{min(sample, n)} of the {n} trajectories, one pass ({t:.2f} s), oracle C99/OpenMP fp32 with {cores} threads"}
+    if not a.no_cpu_baseline and world == 1:   # the in-line CPU leg is an N = 1 item (rank 0 of a multi-rank run has been re-pinned by NCCL)
+        cores, aff, quota = HOST
+        sample = min(a.cpu_sample or (8192 if cfg is LV else 512 if cfg is SEIR else 32), n)
+        u0s, ys = np.ascontiguousarray(weak.u0[:, :sample]), np.ascontiguousarray(weak.y[:, :, :sample])
+        k = min(sample, 256)
+        cpu_pass(cfg, weak.theta, np.ascontiguousarray(u0s[:, :k]), np.ascontiguousarray(ys[:, :, :k]), cores)   # warm
+        times = [cpu_pass(cfg, weak.theta, u0s, ys, cores) for _ in range(3)]
+        med = float(np.median(times))
+        cpu = {"value": sample / med, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sample} of the {n} trajectories, median of 3 passes, oracle C99/OpenMP fp32 with {cores} threads "
+                         f"(affinity {aff}, cgroup quota {quota})", "pass_seconds": [round(t, 4) for t in times]}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": cfg.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": tw["total_ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LV UDE ensemble, 2->32->32->2 tanh, Tsit5 dt=0.1 x30 saveat 0.1, fwd + InterpolatingAdjoint + L2 loss",
-                   "trajectories_per_gpu": n, "global_trajectories": world * n, "parallelism": f"ensemble-sharded x{world}",
+        "config": {"workload": cfg.workload, "trajectories_per_gpu": n, "global_trajectories": world * n, "parallelism": f"ensemble-sharded x{world}",
                    "l2": "flushed between timed iterations (256 MiB memset, untimed)",
                    "timing": "CUDA events per step on the launch stream, summed over steps, max over ranks",
                    "allreduce": ("none (1 GPU)" if world == 1 else
                                  "fused into the final reduction kernel over NVLink peer memory (CUDA IPC, b200ude_adjoint_l2_allreduce)" if peer is not None
-                                 else "NCCL all-reduce of [grad_theta; loss] (4.9 KB)")},
+                                 else "NCCL all-reduce of [grad_theta; loss]")},
+        "strong": strong,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "b200ude_loss_gradient_host: pinned host theta/u0/data -> H2D -> kernels -> D2H grad+loss, wall clock"},
-        "gpu_launches": 3 * a.steps,
-        "kernels_per_step": ["lv32::tc::forward_kernel", "lv32::tc::adjoint_kernel", "ude_reduce_exchange_kernel" if peer is not None else "ude_reduce_kernel"],
-        "clocks": clocks, "roofline": roofline, "roofline_fp32": roofline_fp32, "roofline_xu": roofline_xu, "cpu_baseline": cpu,
-        "kernel_ms": {"forward": fwd_ms, "adjoint_plus_reduce": adj_ms, "step": float(np.mean(t_step))},
+        "gpu_launches": (len(names) if names else 3) * a.steps,
+        "kernels_per_step": names, "kernels_source": names_src,
+        "allreduce_check": allreduce_check,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "kernel_ms": {"forward": fwd_ms, "adjoint_plus_reduce": adj_ms, "step": tw["step_ms"]},
     }
+    line.update(line_extra)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

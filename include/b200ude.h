@@ -227,6 +227,11 @@ int32_t b200ude_peer_detach(b200ude_handle *h);
 int32_t b200ude_adjoint_l2_allreduce(b200ude_handle *h, const void *data, void *loss, void *grad_theta, void *grad_u0,
                                      void *stream);
 
+/* SELF-TEST of a device building block (no reference counterpart): y[i] = the kernels' tanh (1 - 2 / (1 + 2^(2 log2(e) x)) with one
+ * reciprocal per four values, the variant the warp-collective LV kernels use) for n device floats; the parity tests compare it
+ * with tanh in fp64.  device = CUDA ordinal. */
+int32_t b200ude_selftest_tanh(int32_t device, const void *x, void *y, size_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,8 +40,37 @@ def _run(solver, theta, u0, data, want_gu0=True):
     return out.cpu().numpy(), float(loss), g.cpu().numpy(), (gu.cpu().numpy() if gu is not None else None), status.cpu().numpy()
 
 
+def test_device_tanh_vs_fp64():
+    """The kernels' tanh (MUFU.EX2 + one MUFU.RCP per four values): absolute error against tanh in fp64."""
+    from universal_differential_equations_b200 import _lib
+    x = np.concatenate([np.linspace(-12, 12, 200001), np.random.default_rng(0).normal(0, 2, 200000), [0.0, 1e-8, -1e-8, 20.0, -20.0, 88.0, -88.0, 1e4, -1e4]]).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    rc = _lib.lib().b200ude_selftest_tanh(0, xd.data_ptr(), yd.data_ptr(), x.size, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    err = np.abs(yd.cpu().numpy().astype(np.float64) - np.tanh(x.astype(np.float64)))
+    rms, ymax = float(np.sqrt(np.mean(err ** 2))), float(np.abs(yd.cpu().numpy()).max())
+    print(f"device tanh: max abs err {err.max():.3e}, rms {rms:.3e}, max |y| - 1 = {ymax - 1.0:.3e}")
+    assert err.max() <= 6e-7, err.max()       # measured 4.8e-7 (near tanh = -1, where the error of 1/(1+e^2x) doubles)
+    assert rms <= 2e-7, rms
+    assert ymax <= 1.0 + 2.5e-7, ymax         # the batched inversion may overshoot +-1 by one or two ulp
+
+
+def _family(monkeypatch, family, rows=0, groups=1):
+    """Select the kernel family of the LV 2-32-32-2 chain: "wm" = warp-collective mma.sync (lv32_wm.cuh), "tc" = tcgen05
+    (lv32_tc.cuh), "auto" = the library's own choice; read by b200ude_create."""
+    if family != "auto":
+        monkeypatch.setenv("B200UDE_FWD_WM", "1" if family == "wm" else "0")
+        monkeypatch.setenv("B200UDE_ADJ_WM", "1" if family == "wm" else "0")
+    monkeypatch.setenv("B200UDE_WM_R", str(rows))
+    monkeypatch.setenv("B200UDE_WM_G", str(groups))
+
+
+@pytest.mark.parametrize("family", ["wm", "tc"])
 @pytest.mark.parametrize("N", [1, 2, 31, 64, 65, 1000, 4097])
-def test_lv32_forward_adjoint_vs_oracle(O, N):
+def test_lv32_forward_adjoint_vs_oracle(O, N, family, monkeypatch):
+    _family(monkeypatch, family)
     ude = _ude()
     theta = glorot_theta((2, 32, 32, 2), seed=1)
     u0, y = synthetic_ensemble(N)
@@ -56,6 +85,64 @@ def test_lv32_forward_adjoint_vs_oracle(O, N):
     assert np.abs(gu - gu64).max() <= 2e-3 * np.abs(gu64).max()
     l32, g32, gu32 = O.ensemble_loss_grad(m, theta.astype(np.float32), u0, y, np.ones(2, np.float32), 0.1, 30)
     assert np.linalg.norm(g - g32) <= 2e-3 * np.linalg.norm(g64)
+    solver.close()
+
+
+@pytest.mark.parametrize("rows,groups,N", [(1, 1, 7), (1, 1, 8), (1, 1, 1001), (2, 1, 15), (2, 1, 16), (2, 2, 1001), (2, 2, 33)])
+def test_lv32_warp_collective_variants_vs_oracle(O, rows, groups, N, monkeypatch):
+    """The warp-collective family's launch variants: 8 or 16 trajectories per warp group, 1 or 2 groups per warp, ragged tails."""
+    _family(monkeypatch, "wm", rows, groups)
+    ude = _ude()
+    theta = glorot_theta((2, 32, 32, 2), seed=4)
+    u0, y = synthetic_ensemble(N, seed=3)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    out, loss, g, gu, status = _run(solver, theta, u0, y)
+    m = O.lv_model()
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.1, 30, want_out=True)
+    assert (status == 0).all()
+    assert np.all(np.abs(out - out64) <= 1e-4 * (1 + np.abs(out64)))
+    assert abs(loss - l64) <= 1e-5 * abs(l64)
+    assert np.linalg.norm(g - g64) <= 2e-5 * np.linalg.norm(g64)      # measured 3e-7 ... 6e-7
+    assert np.abs(gu - gu64).max() <= 2e-5 * np.abs(gu64).max()
+    solver.close()
+
+
+@pytest.mark.parametrize("fwd,adj", [("1", "0"), ("0", "1")])
+def test_lv32_families_share_the_forward_record(O, fwd, adj, monkeypatch):
+    """Either family's adjoint follows either family's forward (same ustep / dense layout)."""
+    monkeypatch.setenv("B200UDE_FWD_WM", fwd)
+    monkeypatch.setenv("B200UDE_ADJ_WM", adj)
+    ude = _ude()
+    N = 1000
+    theta = glorot_theta((2, 32, 32, 2), seed=1)
+    u0, y = synthetic_ensemble(N)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    out, loss, g, gu, status = _run(solver, theta, u0, y)
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(O.lv_model(), theta.astype(np.float64), u0, y, np.ones(2), 0.1, 30, want_out=True)
+    assert np.all(np.abs(out - out64) <= 3e-4 * (1 + np.abs(out64)))
+    assert np.linalg.norm(g - g64) <= 1e-4 * np.linalg.norm(g64)
+    assert np.abs(gu - gu64).max() <= 1e-4 * np.abs(gu64).max()
+    solver.close()
+
+
+@pytest.mark.parametrize("family", ["auto", "tc"])
+def test_full_size_oracle_parity(O, family, monkeypatch):
+    """The benchmarked size itself (N = 65 536, every SM loaded, several CTAs per SM sharing tensor memory): all trajectories,
+    the loss, the full grad_theta and all of grad_u0 against the fp64 oracle."""
+    _family(monkeypatch, family)
+    ude = _ude()
+    N = 65536
+    theta = glorot_theta((2, 32, 32, 2), seed=1)
+    u0, y = synthetic_ensemble(N)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    out, loss, g, gu, status = _run(solver, theta, u0, y)
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(O.lv_model(), theta.astype(np.float64), u0, y, np.ones(2), 0.1, 30, want_out=True)
+    assert (status == 0).all()
+    assert np.all(np.abs(out - out64) <= 3e-4 * (1 + np.abs(out64)))
+    assert abs(loss - l64) <= 1e-5 * abs(l64)
+    assert np.linalg.norm(g - g64) <= 1e-4 * np.linalg.norm(g64)
+    assert np.abs(g - g64).max() <= 1e-4 * np.abs(g64).max()
+    assert np.abs(gu - gu64).max() <= 1e-4 * np.abs(gu64).max()
     solver.close()
 
 
@@ -481,10 +568,11 @@ def test_adaptive_tensor_core_lv32_vs_oracle_and_runtime_shape(O, N, tol, monkey
     assert np.abs(out - o2).max() <= 50 * tol * (1 + np.abs(o2).max()) + 3e-5
     assert np.linalg.norm(gth - g2) <= 5e-3 * np.linalg.norm(g2)
     if N == 300:
-        # step budget exhausted -> status 2 (no hang, no crash), and the adjoint of the truncated record still runs
+        # step budget exhausted -> status 2 (no hang, no crash); the failure reaches the loss: the unreached save points are
+        # NaN (as a failed retcode would signal), hence so is the gradient
         s3 = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N, adaptive=True, abstol=1e-7, reltol=1e-7, max_steps=3)
-        _, _, g3, _, st3 = _run(s3, theta, u0, y)
-        assert (st3 == 2).all() and np.isfinite(g3).all()
+        o3, _, g3, _, st3 = _run(s3, theta, u0, y)
+        assert (st3 == 2).all() and np.isnan(g3).all() and np.isnan(o3[-1]).all() and np.isfinite(o3[0]).all()
         # a diverging start -> status 1 for that trajectory only
         ub = u0.copy(); ub[:, 5] = 3e38
         s4 = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N, adaptive=True, abstol=tol, reltol=tol, max_steps=256)
@@ -810,6 +898,23 @@ def test_two_devices_in_one_process_interleaved():
         assert np.array_equal(r[0], res[0][0]) and r[1] == res[0][1] and np.array_equal(r[2], res[0][2])
     for sv in solvers:
         sv.close()
+
+
+def test_peer_allreduce_two_ranks_vs_nccl():
+    """Two ranks (one process per GPU, torchrun): the sums of the fused reduce + all-reduce over NVLink peer memory equal NCCL's
+    all-reduce of the per-rank results and are bitwise identical on both ranks; the on-device multi-GPU ADAM loop keeps the
+    replicas identical.  (Needs >= 2 GPUs; bench.py carries the same check in its JSON line for the 2/4/8-GPU runs.)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", os.path.join(root, "tools", "peer_allreduce_check.py")], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "fused all-reduce OK" in r.stdout, r.stdout[-2000:]
+    assert "replicas identical=True" in r.stdout, r.stdout[-2000:]
 
 
 @pytest.mark.parametrize("nx,N,stages,dt,n_steps", [(64, 9, 6, 0.05, 20), (256, 3, 8, 0.0125, 16)])

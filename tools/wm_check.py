@@ -14,14 +14,14 @@ theta = glorot_theta((2, 32, 32, 2), seed=1)
 m = O.lv_model()
 
 
-def make(N, fwd, adj, G=1, **kw):
-    os.environ["B200UDE_FWD_WM"] = str(fwd); os.environ["B200UDE_ADJ_WM"] = str(adj); os.environ["B200UDE_WM_G"] = str(G)
+def make(N, fwd, adj, G=1, R=0, **kw):
+    os.environ["B200UDE_FWD_WM"] = str(fwd); os.environ["B200UDE_ADJ_WM"] = str(adj); os.environ["B200UDE_WM_G"] = str(G); os.environ["B200UDE_WM_R"] = str(R)
     return ude.UDESolver(f, 0.0, 0.1, 30, 1, max_trajectories=N, **kw)
 
 
-def parity(N, fwd, adj, G=1):
+def parity(N, fwd, adj, G=1, R=0):
     u0, y = synthetic_ensemble(N)
-    s = make(N, fwd, adj, G)
+    s = make(N, fwd, adj, G, R)
     s.set_params(torch.from_numpy(theta).cuda())
     st = torch.full((N,), -1, dtype=torch.int32, device="cuda")
     out = s.forward(torch.from_numpy(u0).cuda(), status=st)
@@ -29,7 +29,7 @@ def parity(N, fwd, adj, G=1):
     torch.cuda.synchronize()
     l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.ones(2), 0.1, 30, want_out=True)
     o = out.cpu().numpy()
-    r = dict(N=N, fwd=fwd, adj=adj, G=G, out=float((np.abs(o - out64) / (1 + np.abs(out64))).max()), loss=abs(float(loss) - l64) / l64,
+    r = dict(N=N, fwd=fwd, adj=adj, G=G, R=R, out=float((np.abs(o - out64) / (1 + np.abs(out64))).max()), loss=abs(float(loss) - l64) / l64,
              g=float(np.linalg.norm(g.cpu().numpy() - g64) / np.linalg.norm(g64)), gu=float(np.abs(gu.cpu().numpy() - gu64).max() / np.abs(gu64).max()),
              status=int((st != 0).sum()))
     # per-block relative errors of the gradient
@@ -40,9 +40,9 @@ def parity(N, fwd, adj, G=1):
     s.close()
 
 
-def timing(N, fwd, adj, G=1, reps=20):
+def timing(N, fwd, adj, G=1, R=0, reps=20):
     u0, y = synthetic_ensemble(N)
-    s = make(N, fwd, adj, G)
+    s = make(N, fwd, adj, G, R)
     s.set_params(torch.from_numpy(theta).cuda())
     u0d, yd = torch.from_numpy(u0).cuda(), torch.from_numpy(y).cuda()
     out = torch.empty((31, 2, N), device="cuda")
@@ -53,7 +53,7 @@ def timing(N, fwd, adj, G=1, reps=20):
     for _ in range(reps):
         ev[0].record(); s.forward(u0d, out=out); ev[1].record(); s.adjoint_l2(yd); ev[2].record(); torch.cuda.synchronize()
         tf += ev[0].elapsed_time(ev[1]); ta += ev[1].elapsed_time(ev[2])
-    print(json.dumps(dict(N=N, fwd=fwd, adj=adj, G=G, fwd_ms=round(tf / reps, 4), adj_ms=round(ta / reps, 4), Mtraj_s=round(N / ((tf + ta) / reps * 1e-3) / 1e6, 2))))
+    print(json.dumps(dict(N=N, fwd=fwd, adj=adj, G=G, R=R, fwd_ms=round(tf / reps, 4), adj_ms=round(ta / reps, 4), Mtraj_s=round(N / ((tf + ta) / reps * 1e-3) / 1e6, 2))))
     sys.stdout.flush()
     s.close()
 
@@ -61,11 +61,12 @@ def timing(N, fwd, adj, G=1, reps=20):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "parity"):
-        for N in (1, 15, 16, 17, 33, 257, 1000, 4097):
-            parity(N, 1, 1)
-        parity(1000, 1, 0); parity(1000, 0, 1); parity(1000, 0, 0)
-        parity(1000, 1, 1, G=2); parity(1000, 1, 1, G=4); parity(37, 1, 1, G=4)
+        for N in (1, 7, 8, 9, 17, 257, 1000, 4097):
+            parity(N, 1, 1, R=1)
+        for N in (1, 15, 16, 17, 1000, 4097):
+            parity(N, 1, 1, R=2)
+        parity(1000, 1, 0, R=1); parity(1000, 0, 1, R=1); parity(1000, 1, 1, G=2, R=2)
     if what in ("all", "timing"):
-        for N in (1024, 8192, 16384, 32768, 65536):
-            for (fw, ad, G) in ((0, 0, 1), (1, 1, 1), (1, 1, 2)):
-                timing(N, fw, ad, G)
+        for N in (1024, 4096, 8192, 12288, 16384, 32768, 65536):
+            for (fw, ad, G, R) in ((1, 1, 1, 1), (1, 1, 1, 2)):
+                timing(N, fw, ad, G, R)

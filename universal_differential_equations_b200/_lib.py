@@ -29,7 +29,7 @@ EXPORTS = [
     "b200ude_num_params", "b200ude_num_save", "b200ude_device_bytes", "b200ude_set_params",
     "b200ude_forward", "b200ude_adjoint", "b200ude_adjoint_l2", "b200ude_solve_host",
     "b200ude_loss_gradient_host", "b200ude_get_params", "b200ude_adam_reset", "b200ude_adam_step", "b200ude_train_adam",
-    "b200ude_peer_export", "b200ude_peer_attach", "b200ude_peer_detach", "b200ude_adjoint_l2_allreduce",
+    "b200ude_peer_export", "b200ude_peer_attach", "b200ude_peer_detach", "b200ude_adjoint_l2_allreduce", "b200ude_selftest_tanh",
 ]
 PEER_HANDLE_BYTES = 64
 
@@ -125,6 +125,8 @@ def lib():
     L.b200ude_peer_detach.argtypes = [vp]
     L.b200ude_adjoint_l2_allreduce.restype = i32
     L.b200ude_adjoint_l2_allreduce.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.b200ude_selftest_tanh.restype = i32
+    L.b200ude_selftest_tanh.argtypes = [i32, vp, vp, sz, vp]
     if L.b200ude_version() != ABI_VERSION:
         raise RuntimeError("libb200ude.so ABI version mismatch")
     _lib = L

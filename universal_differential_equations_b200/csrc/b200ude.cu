@@ -527,8 +527,10 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->var.fwd_wm = env_int("B200UDE_FWD_WM", -1);
     h->var.adj_wm = env_int("B200UDE_ADJ_WM", -1);
     h->var.wm_groups = env_int("B200UDE_WM_G", 1);
-    h->wm_fwd_max = (size_t)env_int("B200UDE_WM_FWD_MAX", 32768);
-    h->wm_adj_max = (size_t)env_int("B200UDE_WM_ADJ_MAX", 16384);
+    h->var.wm_rows = env_int("B200UDE_WM_R", 0);
+    h->var.wm_r1_max = env_int("B200UDE_WM_R1_MAX", 4736);
+    h->wm_fwd_max = (size_t)env_int("B200UDE_WM_FWD_MAX", 1 << 26);
+    h->wm_adj_max = (size_t)env_int("B200UDE_WM_ADJ_MAX", 1 << 26);
 
     const size_t N = h->cap, D = (size_t)h->D;
     h->partial_blocks = (size_t)(kid == K_LV32 ? std::max(adj_grid_lv32((int)N), adj_rows_lv32_wm((int)N)) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : kid == K_SEIR64 ? adj_rows_seir((int)N) : kid == K_FKPP16 ? adj_rows_fkpp16((int)N, d->state_dim) : adj_grid_lv5((int)N));
@@ -842,6 +844,14 @@ int32_t b200ude_adjoint_l2_allreduce(b200ude_handle *h, const void *data, void *
 {
     if (!h) return B200UDE_EINVAL;
     return do_adjoint(h, true, (const float *)data, (float *)loss, (float *)grad_theta, (float *)grad_u0, (cudaStream_t)stream, true);
+}
+
+int32_t b200ude_selftest_tanh(int32_t device, const void *x, void *y, size_t n, void *stream)
+{
+    if (!x || !y || n == 0) return fail(nullptr, B200UDE_EINVAL, "selftest_tanh: null pointer or n == 0");
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    CUDA_TRY(nullptr, launch_tanh_selftest((const float *)x, (float *)y, n, (cudaStream_t)stream));
+    return B200UDE_OK;
 }
 
 }  // extern "C"

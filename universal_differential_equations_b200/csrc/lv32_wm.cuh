@@ -142,30 +142,44 @@ __device__ __forceinline__ Lane make_lane()
     L.fg = lane >> 2; L.tig = lane & 3; L.comp = L.tig & 1; L.rsel = L.tig >> 1; L.quad = lane & ~3;
     return L;
 }
+// R = rows per lane: 2 -> a group is 16 trajectories (rows fg, fg + 8 of the MMA tile), every lane owns one (row, component);
+//                    1 -> a group is 8 trajectories (rows 8..15 of the tile are zero): half the element-wise work per warp for
+//                         the latency-bound small ensembles; lanes with tig >= 2 shadow the (row, component) of tig - 2.
 
-// every lane contributes the value of the (row, component) it owns; returns x[r][c] for both rows of the group
-__device__ __forceinline__ void gather4(const Lane &L, float own, float (&x)[2][2])
+// every lane contributes the value of the (row, component) it owns; returns x[r][c] for the rows of the group
+template <int R>
+__device__ __forceinline__ void gather4(const Lane &L, float own, float (&x)[R][2])
 {
     x[0][0] = __shfl_sync(0xffffffffu, own, L.quad + 0);
     x[0][1] = __shfl_sync(0xffffffffu, own, L.quad + 1);
-    x[1][0] = __shfl_sync(0xffffffffu, own, L.quad + 2);
-    x[1][1] = __shfl_sync(0xffffffffu, own, L.quad + 3);
+    if constexpr (R == 2) {
+        x[1][0] = __shfl_sync(0xffffffffu, own, L.quad + 2);
+        x[1][1] = __shfl_sync(0xffffffffu, own, L.quad + 3);
+    }
 }
-// y[r][c] partial sums over the quad's 4 lanes -> the total for the (row, component) this lane owns (3 shuffles)
-__device__ __forceinline__ float scatter_sum(const Lane &L, const float (&y)[2][2])
+// y[r][c] partial sums over the quad's 4 lanes -> the total for the (row, component) this lane owns
+template <int R>
+__device__ __forceinline__ float scatter_sum(const Lane &L, const float (&y)[R][2])
 {
-    const bool c1 = L.comp != 0, r1 = L.rsel != 0;
-    float ka = c1 ? y[0][1] : y[0][0], sa = c1 ? y[0][0] : y[0][1];
-    float kb = c1 ? y[1][1] : y[1][0], sb = c1 ? y[1][0] : y[1][1];
+    const bool c1 = L.comp != 0;
+    float ka = c1 ? y[0][1] : y[0][0];
+    const float sa = c1 ? y[0][0] : y[0][1];
     ka += __shfl_xor_sync(0xffffffffu, sa, 1);
-    kb += __shfl_xor_sync(0xffffffffu, sb, 1);
-    const float keep = r1 ? kb : ka, send = r1 ? ka : kb;
-    return keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    if constexpr (R == 2) {
+        const bool r1 = L.rsel != 0;
+        float kb = c1 ? y[1][1] : y[1][0];
+        const float sb = c1 ? y[1][0] : y[1][1];
+        kb += __shfl_xor_sync(0xffffffffu, sb, 1);
+        const float keep = r1 ? kb : ka, send = r1 ? ka : kb;
+        return keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    } else {
+        return ka + __shfl_xor_sync(0xffffffffu, ka, 2);
+    }
 }
 
 // layer 1 of the chain for G groups: h[g][r][q] = tanh(W1 x + b1) at the lane's units (8q + 2 tig, +1)
-template <int TM, int G>
-__device__ __forceinline__ void layer1(const SmemW &w, const Lane &L, const float (&x)[G][2][2], float2 (&h)[G][2][4])
+template <int TM, int G, int R>
+__device__ __forceinline__ void layer1(const SmemW &w, const Lane &L, const float (&x)[G][R][2], float2 (&h)[G][R][4])
 {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -173,12 +187,12 @@ __device__ __forceinline__ void layer1(const SmemW &w, const Lane &L, const floa
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
-            for (int r = 0; r < 2; ++r) h[g][r][q] = fma2(w0, bc(x[g][r][0]), fma2(w1, bc(x[g][r][1]), bb));
+            for (int r = 0; r < R; ++r) h[g][r][q] = fma2(w0, bc(x[g][r][0]), fma2(w1, bc(x[g][r][1]), bb));
     }
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < R; ++r) {
             tanh_quad<TM>(h[g][r][0], h[g][r][1]);
             tanh_quad<TM>(h[g][r][2], h[g][r][3]);
         }
@@ -188,8 +202,8 @@ __device__ __forceinline__ void layer1(const SmemW &w, const Lane &L, const floa
 __device__ __forceinline__ void mma16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
     asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // (hi, lo) fp16 pairs of a float2: hi = the value truncated to 10 mantissa bits (exact in fp16), lo = fp16(x - hi): 22 bits
 __device__ __forceinline__ void split_h2(float2 v, uint32_t &hi, uint32_t &lo)
@@ -198,12 +212,14 @@ __device__ __forceinline__ void split_h2(float2 v, uint32_t &hi, uint32_t &lo)
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(hy), "f"(hx));
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y - hy), "f"(v.x - hx));
 }
-// d[g][nt] += A[g] B (B fragments from a staged fp16 copy of W2 or W2^T) as 2-way-split fp16 (hi hi + lo hi + hi lo: 22-bit operands, fp32 accumulate):
-// half the tensor-pipe time of 3xTF32.  For operands bounded like the tanh outputs (|a| <= 1) and weights below 65504
-// (beyond that the fp16 copy is inf and the trajectory's status word reports the non-finite result).
-template <int G>
+// d[g][nt] += A[g] B (B fragments from a staged fp16 copy of W2 or W2^T) as a 2-way-split fp16 product (hi hi + lo hi + hi lo:
+// 22-bit operands, fp32 accumulate): half the tensor-pipe time of 3xTF32.  For operands bounded like the tanh outputs
+// (|a| <= 1; the cotangent rows are scaled into that range by the caller) and weights below 65504 (beyond that the fp16
+// copy is inf and the trajectory's status word reports the non-finite result).  A = a[g][r][q]: the D-fragment layout is
+// the A-fragment layout under the k permutation (k = 2 tig, 2 tig + 1 <-> units 16 s + 2 tig, + 1; k + 8 <-> units + 8).
+template <int G, int R>
 __device__ __forceinline__ void gemm32h(const uint32_t *__restrict__ bhi, const uint32_t *__restrict__ blo, const Lane &L,
-                                        const float2 (&a)[G][2][4], float (&d)[G][4][4])
+                                        const float2 (&a)[G][R][4], float (&d)[G][4][4])
 {
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -211,9 +227,13 @@ __device__ __forceinline__ void gemm32h(const uint32_t *__restrict__ bhi, const 
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             split_h2(a[g][0][2 * s], ah[g][0], al[g][0]);
-            split_h2(a[g][1][2 * s], ah[g][1], al[g][1]);
             split_h2(a[g][0][2 * s + 1], ah[g][2], al[g][2]);
-            split_h2(a[g][1][2 * s + 1], ah[g][3], al[g][3]);
+            if constexpr (R == 2) {
+                split_h2(a[g][1][2 * s], ah[g][1], al[g][1]);
+                split_h2(a[g][1][2 * s + 1], ah[g][3], al[g][3]);
+            } else {
+                ah[g][1] = ah[g][3] = al[g][1] = al[g][3] = 0u;
+            }
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -231,16 +251,16 @@ __device__ __forceinline__ void gemm32h(const uint32_t *__restrict__ bhi, const 
 
 // UDE right-hand side for G groups; gv[g] = this lane's (row, component) of the stage argument, returns the same
 // component of du/dt.  du1 = p1 u1 + NN1(u), du2 = -p4 u2 + NN2(u)  (scenario_1.jl:71-72): pc = p1 / -p4 by component.
-template <int TM, int G>
+template <int TM, int G, int R>
 __device__ __forceinline__ void rhs_wm(const SmemW *wp, float pc, const float (&gv)[G], float (&kout)[G])
 {
     const SmemW &w = *wp;
     const Lane L = make_lane();
-    float x[G][2][2];
+    float x[G][R][2];
 #pragma unroll
-    for (int g = 0; g < G; ++g) gather4(L, gv[g], x[g]);
-    float2 h[G][2][4];
-    layer1<TM, G>(w, L, x, h);
+    for (int g = 0; g < G; ++g) gather4<R>(L, gv[g], x[g]);
+    float2 h[G][R][4];
+    layer1<TM, G, R>(w, L, x, h);
     float d[G][4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
@@ -248,13 +268,13 @@ __device__ __forceinline__ void rhs_wm(const SmemW *wp, float pc, const float (&
 #pragma unroll
         for (int g = 0; g < G; ++g) { d[g][nt][0] = bias.x; d[g][nt][1] = bias.y; d[g][nt][2] = bias.x; d[g][nt][3] = bias.y; }
     }
-    gemm32h<G>(w.w2h_hi, w.w2h_lo, L, h, d);
+    gemm32h<G, R>(w.w2h_hi, w.w2h_lo, L, h, d);
     const float b3c = w.b3[L.comp];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        float y[2][2];
+        float y[R][2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < R; ++r) {
             float2 v[4];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) v[nt] = make_float2(d[g][nt][2 * r], d[g][nt][2 * r + 1]);
@@ -269,7 +289,7 @@ __device__ __forceinline__ void rhs_wm(const SmemW *wp, float pc, const float (&
             y[r][0] = s0.x + s0.y;
             y[r][1] = s1.x + s1.y;
         }
-        kout[g] = fmaf(pc, gv[g], scatter_sum(L, y) + b3c);
+        kout[g] = fmaf(pc, gv[g], scatter_sum<R>(L, y) + b3c);
     }
 }
 
@@ -288,8 +308,8 @@ struct Consts {
     float lw0, lw1;     // L2 loss weights per component
 };
 
-// ---- forward: fixed-step Tsit5, WPC warps per CTA, G groups of 16 trajectories per warp --------------------------------
-template <int TM, int G, int WPC>
+// ---- forward: fixed-step Tsit5, WPC warps per CTA, G groups of 8 R trajectories per warp -------------------------------
+template <int TM, int G, int R, int WPC>
 __global__ void __launch_bounds__(32 * WPC) forward_kernel(FwdParams p, Consts cs)
 {
     __shared__ SmemW w;
@@ -305,9 +325,9 @@ __global__ void __launch_bounds__(32 * WPC) forward_kernel(FwdParams p, Consts c
     float u[G], k[G][7];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        const long n = (long)(wg * G + g) * 16 + L.fg + 8 * L.rsel;
-        live[g] = n < (long)N;
-        idx[g] = (size_t)L.comp * N + (size_t)(live[g] ? n : (long)N - 1);   // padding lanes shadow the last trajectory; stores masked
+        const long n = (long)(wg * G + g) * (8 * R) + L.fg + (R == 2 ? 8 * L.rsel : 0);
+        live[g] = n < (long)N && (R == 2 || L.rsel == 0);                     // R = 1: lanes tig >= 2 only shadow
+        idx[g] = (size_t)L.comp * N + (size_t)(n < (long)N ? n : (long)N - 1);   // padding lanes shadow the last trajectory; stores masked
         u[g] = __ldg(p.u0 + idx[g]);
 #pragma unroll
         for (int j = 0; j < 7; ++j) k[g][j] = 0.0f;
@@ -346,7 +366,7 @@ __global__ void __launch_bounds__(32 * WPC) forward_kernel(FwdParams p, Consts c
                 if (i == 6) u[g] = gv[g];   // stage 7's argument is u_{n+1} (row 7 = b, FSAL)
             }
             float kk[G];
-            rhs_wm<TM, G>(&w, pc, gv, kk);
+            rhs_wm<TM, G, R>(&w, pc, gv, kk);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 switch (i) {
@@ -380,15 +400,16 @@ __global__ void __launch_bounds__(32 * WPC) forward_kernel(FwdParams p, Consts c
     }
 }
 
-// ---- adjoint: interpolating adjoint on the fixed grid, one group of 16 trajectories per warp ---------------------------
+// ---- adjoint: interpolating adjoint on the fixed grid, one group of 8 R trajectories per warp --------------------------
+template <int R>
 struct __align__(16) WarpTiles {
-    float q2[16 * WS];    // q2[t][j] of the current stage (transposed operand of dW2 += q2^T h1)
-    float h1[16 * WS];    // h1[t][i]
-    float sum[32 * 32];   // running dW2 sums of this warp, element k*32 + lane <-> accumulator register k of that lane
+    float q2[8 * R * WS];   // q2[t][j] of the current stage (transposed operand of dW2 += q2^T h1)
+    float h1[8 * R * WS];   // h1[t][i]
+    float sum[32 * 32];     // running dW2 sums of this warp, element k*32 + lane <-> accumulator register k of that lane
 };
 
-template <int TM, int WPC>
-__global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts cs)
+template <int TM, int R, int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) adjoint_kernel(AdjParams p, Consts cs)
 {
     __shared__ SmemW w;
     __shared__ SmemT wt;
@@ -396,16 +417,16 @@ __global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts c
     stage_weights(p.theta, w, &wt, threadIdx.x, 32 * WPC);
     const Lane L = make_lane();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpTiles &T = reinterpret_cast<WarpTiles *>(s_raw)[warp];
+    WarpTiles<R> &T = reinterpret_cast<WarpTiles<R> *>(s_raw)[warp];
 #pragma unroll
     for (int q = 0; q < 32; ++q) T.sum[q * 32 + lane] = 0.0f;
     __syncthreads();
 
     const size_t N = (size_t)p.N;
     const int wg = blockIdx.x * WPC + warp;
-    const long n = (long)wg * 16 + L.fg + 8 * L.rsel;
-    const bool live = n < (long)N;
-    const size_t idx = (size_t)L.comp * N + (size_t)(live ? n : (long)N - 1);
+    const long n = (long)wg * (8 * R) + L.fg + (R == 2 ? 8 * L.rsel : 0);
+    const bool live = n < (long)N && (R == 2 || L.rsel == 0);   // R = 1: lanes tig >= 2 shadow tig - 2 (weight 0, stores masked)
+    const size_t idx = (size_t)L.comp * N + (size_t)(n < (long)N ? n : (long)N - 1);
     const float lv = live ? 1.0f : 0.0f;
     const float pc = L.comp ? -cs.p4 : cs.p1;
     const float lw = L.comp ? cs.lw1 : cs.lw0;
@@ -418,7 +439,7 @@ __global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts c
         for (int b = 0; b < 4; ++b)
 #pragma unroll
             for (int c = 0; c < 4; ++c) macc[a][b][c] = 0.0f;
-    // thin-layer gradients: sums over the lane's two trajectories at its 8 units, reduced over fg at the end
+    // thin-layer gradients: sums over the lane's trajectories at its 8 units, reduced over fg at the end
     float2 gW3a[4], gW3b[4], gB2[4], gB1[4], gW1a[4], gW1b[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) { gW3a[q] = gW3b[q] = gB2[q] = gB1[q] = gW1a[q] = gW1b[q] = bc(0.0f); }
@@ -439,17 +460,17 @@ __global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts c
 
     // one backward stage: xo = own component of u(t), go = own component of the stage's lambda argument, sc = dt b_i
     auto eval = [&](float xo, float go, float sc, float isc) -> float {
-        float x[1][2][2], sg[2][2];
-        gather4(L, xo, x[0]);
+        float x[1][R][2], sg[R][2];
+        gather4<R>(L, xo, x[0]);
         const float sgo = lv * sc * go;
-        gather4(L, sgo, sg);
+        gather4<R>(L, sgo, sg);
         gb3 += sgo;
-        float2 h1[1][2][4];
-        layer1<TM, 1>(w, L, x, h1);
+        float2 h1[1][R][4];
+        layer1<TM, 1, R>(w, L, x, h1);
         // transposed operand of the gradient product: h1 rows
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int q = 0; q < 4; ++q) *reinterpret_cast<float2 *>(&T.h1[(L.fg + 8 * r) * WS + 8 * q + 2 * L.tig]) = h1[0][r][q];
         float d[1][4][4];
@@ -458,17 +479,22 @@ __global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts c
             const float2 bias = lds2(w.b2 + 8 * nt + 2 * L.tig);
             d[0][nt][0] = bias.x; d[0][nt][1] = bias.y; d[0][nt][2] = bias.x; d[0][nt][3] = bias.y;
         }
-        gemm32h<1>(w.w2h_hi, w.w2h_lo, L, h1, d);
-        // h2 = tanh(.), q2 = (W3^T sg) (1 - h2^2); dW3 += sg (x) h2, db2 += q2
-        float2 q2[1][2][4];
+        gemm32h<1, R>(w.w2h_hi, w.w2h_lo, L, h1, d);
+        // h2 = tanh(.), q2 = (W3^T sg) (1 - h2^2); dW3 += sg (x) h2, db2 += q2.  Every cotangent row is also scaled by a power
+        // of two into fp16's range for the W2^T q2 product (|q2[t][j]| <= max|W3| (|sg_t0| + |sg_t1|) =: B_t; scale 2^-e(B_t),
+        // undone on the product -- both exact)
+        float2 q2s[1][R][4], unscale[R];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < R; ++r) {
             float2 v[4];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) v[nt] = make_float2(d[0][nt][2 * r], d[0][nt][2 * r + 1]);
             tanh_quad<TM>(v[0], v[1]);
             tanh_quad<TM>(v[2], v[3]);
             const float2 s0 = bc(sg[r][0]), s1 = bc(sg[r][1]);
+            const uint32_t eb = (__float_as_uint(wt.w3max * (fabsf(sg[r][0]) + fabsf(sg[r][1]))) >> 23) & 0xFFu;   // biased exponent of B_t
+            const float2 sc2 = bc(__uint_as_float((254u - eb) << 23));
+            unscale[r] = bc(__uint_as_float(eb << 23));
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const float2 w3a = lds2(w.w3a + 8 * nt + 2 * L.tig), w3b = lds2(w.w3b + 8 * nt + 2 * L.tig);
@@ -476,35 +502,22 @@ __global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts c
                 gW3b[nt] = fma2(s1, v[nt], gW3b[nt]);
                 const float2 t = fma2(w3b, s1, mul2(w3a, s0));
                 const float2 om = fma2(make_float2(-v[nt].x, -v[nt].y), v[nt], bc(1.0f));
-                q2[0][r][nt] = mul2(t, om);
-                gB2[nt] = add2(gB2[nt], q2[0][r][nt]);
-                *reinterpret_cast<float2 *>(&T.q2[(L.fg + 8 * r) * WS + 8 * nt + 2 * L.tig]) = q2[0][r][nt];
+                const float2 q2 = mul2(t, om);
+                q2s[0][r][nt] = mul2(q2, sc2);
+                gB2[nt] = add2(gB2[nt], q2);
+                *reinterpret_cast<float2 *>(&T.q2[(L.fg + 8 * r) * WS + 8 * nt + 2 * L.tig]) = q2;
             }
         }
         __syncwarp();
-        // W2^T q2 as a 2-way-split fp16 product: every cotangent row is scaled by a power of two into fp16's range first
-        // (|q2[t][j]| <= max|W3| (|sg_t0| + |sg_t1|) =: B_t;  scale 2^-e(B_t), undone on the product -- both exact)
         float e[1][4][4];
-        float2 unscale[2];
-        {
-            float2 q2s[1][2][4];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const uint32_t eb = (__float_as_uint(wt.w3max * (fabsf(sg[r][0]) + fabsf(sg[r][1]))) >> 23) & 0xFFu;   // biased exponent of B_t
-                const float2 sc2 = bc(__uint_as_float((254u - eb) << 23));
-                unscale[r] = bc(__uint_as_float(eb << 23));
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) q2s[0][r][nt] = mul2(q2[0][r][nt], sc2);
-            }
+            for (int c = 0; c < 4; ++c) e[0][nt][c] = 0.0f;
+        gemm32h<1, R>(wt.w2t_hi, wt.w2t_lo, L, q2s, e);
+        // dW2 += q2^T h1 : M = j (2 tiles), N = i (4 tiles), K = the group's trajectories (R k-steps of 8), 3xTF32
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) e[0][nt][c] = 0.0f;
-            gemm32h<1>(wt.w2t_hi, wt.w2t_lo, L, q2s, e);
-        }
-        // dW2 += q2^T h1 : M = j (2 tiles), N = i (4 tiles), K = the 16 trajectories (2 k-steps), 3xTF32
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+        for (int ks = 0; ks < R; ++ks) {
             uint32_t ah[2][4], al[2][4];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
@@ -527,9 +540,9 @@ __global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts c
             }
         }
         // q1 = (W2^T q2) (1 - h1^2); (df/du)^T g; dW1 += q1 (x) x, db1 += q1
-        float y[2][2];
+        float y[R][2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < R; ++r) {
             float2 s0 = bc(0.0f), s1 = bc(0.0f);
             const float2 x0 = bc(x[0][r][0]), x1 = bc(x[0][r][1]);
 #pragma unroll
@@ -546,7 +559,7 @@ __global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts c
             y[r][0] = s0.x + s0.y;
             y[r][1] = s1.x + s1.y;
         }
-        const float dxo = scatter_sum(L, y);
+        const float dxo = scatter_sum<R>(L, y);
         return fmaf(pc, go, dxo * isc);   // LV physics: diag(p1, -p4)
     };
 
@@ -585,8 +598,8 @@ __global__ void __launch_bounds__(32 * WPC) adjoint_kernel(AdjParams p, Consts c
         for (int j = 0; j < 6; ++j) a = fmaf((float)Tsit5::b(j), kl[j], a);
         lam = fmaf(dt, a, lam);
         if (s % p.save_every == 0) jump(s / p.save_every);
-        // the tensor core adds into its accumulator with truncation: keep the chains one step (36 MMAs) long and add them
-        // into the running sums with round-to-nearest
+        // the tensor core adds into its accumulator with truncation: keep the chains one step long and add them into
+        // the running sums with round-to-nearest
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll

@@ -50,7 +50,9 @@ struct Variant {
     int discrete = 0;    // 1: discrete adjoint (exact gradient of the fixed-step scheme) instead of the interpolating adjoint
     int fwd_wm = 0;      // 1: warp-collective mma.sync forward kernel (lv32_wm.cuh)
     int adj_wm = 0;      // 1: warp-collective mma.sync adjoint kernel
-    int wm_groups = 1;   // groups of 16 trajectories per warp in the warp-collective forward kernel (1, 2 or 4)
+    int wm_groups = 1;   // groups per warp in the warp-collective forward kernel (1 or 2)
+    int wm_rows = 0;     // trajectories per group / 8: 1, 2, or 0 = by ensemble size (<= wm_r1_max -> 1)
+    int wm_r1_max = 4736;   // 8 trajectories per warp while that still leaves one warp per scheduler (148 x 4 x 8)
 };
 
 // function attributes (dynamic shared-memory size) are per device: one-time flags are kept per device ordinal
@@ -109,6 +111,7 @@ int adj_grid_lv32(int N);
 cudaError_t launch_fwd_lv32_wm(const Variant &, const ConstTables &, const FwdParams &, cudaStream_t);
 cudaError_t launch_adj_lv32_wm(const Variant &, const ConstTables &, const AdjParams &, cudaStream_t, int *rows_out);
 int adj_rows_lv32_wm(int N);
+cudaError_t launch_tanh_selftest(const float *x, float *y, size_t n, cudaStream_t);
 cudaError_t launch_fwd_lv32_adaptive(const Variant &, const ConstTables &, const FwdParams &, const AdaptiveGrid &, cudaStream_t);
 cudaError_t launch_adj_lv32_adaptive(const Variant &, const ConstTables &, const AdjParams &, const AdaptiveGrid &, cudaStream_t, int *rows_out);
 int adj_grid_lv5(int N);
