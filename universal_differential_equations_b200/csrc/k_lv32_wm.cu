@@ -20,9 +20,9 @@ static int pick_rows(const Variant &v, int N) { return v.wm_rows == 1 || v.wm_ro
 template <int TM, int G, int R>
 static cudaError_t launch_fwd(const ConstTables &t, const FwdParams &p, cudaStream_t st)
 {
-    constexpr int WPC = 1;
+    constexpr int WPC = 2;   // two warps share one staged copy of the weights (11.8 KB of shared memory per CTA)
     const int warps = (p.N + 8 * R * G - 1) / (8 * R * G);
-    lv32::wm::forward_kernel<TM, G, R, WPC><<<(warps + WPC - 1) / WPC, 32 * WPC, 0, st>>>(p, make_consts(t));
+    lv32::wm::forward_kernel<TM, G, R, WPC><<<(warps + WPC - 1) / WPC, 32 * WPC, lv32::wm::RAW_FLOATS * 4, st>>>(p, make_consts(t));
     return cudaGetLastError();
 }
 
@@ -45,7 +45,7 @@ static cudaError_t launch_adj(const ConstTables &t, const AdjParams &p, int *row
     // N = 65536 and 35 % slower at N = 8192 (spill code in the stage loop)
     constexpr int WPC = 1;
     auto kern = lv32::wm::adjoint_kernel<TM, R, WPC, 1>;
-    constexpr size_t smem = sizeof(lv32::wm::WarpTiles<R>) * WPC;
+    constexpr size_t smem = lv32::wm::RAW_FLOATS * 4 + sizeof(lv32::wm::WarpTiles<R>) * WPC;
     static PerDeviceOnce once;
     bool &attr_set = once.flag();
     if (!attr_set) {

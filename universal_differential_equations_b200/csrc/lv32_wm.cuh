@@ -19,8 +19,8 @@
 //   * adjoint: the ensemble-summed dW2 += q2^T h1 (K = the group's 16 trajectories) is a third 3xTF32 mma.sync product whose
 //     operands are transposed through a per-warp shared-memory tile; thin-layer gradients are per-lane register sums reduced
 //     once at the end of the kernel.
-// No tensor memory, no mbarrier, no CTA-wide barrier inside the time loops; theta comes from the handle's device copy
-// (no constant bank: handles are independent, any number can be in flight on a device).
+// No tensor memory and no CTA-wide barrier inside the time loops; theta is bulk-copied by the TMA from the handle's device copy
+// into shared memory once per CTA (no constant bank: handles are independent, any number can be in flight on a device).
 //
 // Reference semantics replaced: RHS scenario_1.jl:69-76; Tsit5 perform_step! and InterpolatingAdjoint as in
 // ude_common.cuh / ude_adjoint.cuh (same record layout: ustep / dense rows, so either family's adjoint follows either
@@ -49,45 +49,60 @@ struct __align__(16) SmemW {
     float b3[4];
 };
 
-// all threads of the CTA; the caller synchronises afterwards
-__device__ __forceinline__ void stage_weights(const float *__restrict__ theta, SmemW &w, SmemT *t, int tid, int nthreads)
+constexpr int RAW_FLOATS = ((P + 3) / 4) * 4;   // the handle's device copy of theta is padded to 16 bytes (b200ude_create)
+
+// Weights into shared memory.  One elected thread bulk-copies theta (4.9 KB) with the TMA (1-D cp.async.bulk, completion on an
+// mbarrier's transaction count -- SASS UBLKCP); then all threads of the CTA cut it into the operand layouts: fp16 hi/lo pairs
+// of W2 in B-fragment order (and of W2^T for the adjoint), the thin layers as contiguous rows.  `raw` is RAW_FLOATS floats of
+// (dynamic) shared memory, free again after the call returns.  Ends with a CTA barrier.
+__device__ __forceinline__ void stage_weights(const float *__restrict__ theta, float *raw, SmemW &w, SmemT *t, int tid, int nthreads)
 {
-    if (t) {
-        for (int e = tid; e < 32 * 16; e += nthreads) {
-            const int i = e >> 4, r = e & 15, s_ = r >> 3, tg = (r >> 1) & 3, b = r & 1;
-            const int j0 = 16 * s_ + 8 * b + 2 * tg;
-            const float x0 = __ldg(theta + OFF_W2 + i * 32 + j0), x1 = __ldg(theta + OFF_W2 + i * 32 + j0 + 1);
-            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-            const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-            t->w2t_hi[i * WSH + r] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            t->w2t_lo[i * WSH + r] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-        }
-        if (tid < 32) {   // warp 0: max |W3| over the 64 entries
-            float m = fmaxf(fabsf(__ldg(theta + OFF_W3 + tid)), fabsf(__ldg(theta + OFF_W3 + 32 + tid)));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (tid == 0) t->w3max = m;
-        }
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar), dst_a = (uint32_t)__cvta_generic_to_shared(raw);
+    constexpr uint32_t bytes = RAW_FLOATS * 4;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a), "l"(theta),
+                     "r"(bytes), "r"(bar_a)
+                     : "memory");
     }
-    // fp16 hi/lo copy of W2 for the chain-forward product: word (j, s, tig, b) = (W2[j][16 s + 8 b + 2 tig], W2[j][.. + 1])
-    for (int e = tid; e < 32 * 16; e += nthreads) {
-        const int j = e >> 4, r = e & 15, s_ = r >> 3, tg = (r >> 1) & 3, b = r & 1;
-        const int i0 = 16 * s_ + 8 * b + 2 * tg;
-        const float x0 = __ldg(theta + OFF_W2 + i0 * 32 + j), x1 = __ldg(theta + OFF_W2 + (i0 + 1) * 32 + j);
+    __syncthreads();   // the barrier is initialised (and armed) before anybody polls it
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar_a) : "memory");
+    auto pack = [](float x0, float x1, uint32_t &hi, uint32_t &lo) {
         const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
         const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-        w.w2h_hi[j * WSH + r] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        w.w2h_lo[j * WSH + r] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    };
+    // theta[OFF_W2 + i*32 + j] = W2[j][i]
+    for (int e = tid; e < 32 * 16; e += nthreads) {
+        const int a = e >> 4, r = e & 15, s_ = r >> 3, tg = (r >> 1) & 3, b = r & 1;
+        const int c0 = 16 * s_ + 8 * b + 2 * tg;
+        // forward copy: word (j = a, s, tig, b) = (W2[j][c0], W2[j][c0 + 1])
+        pack(raw[OFF_W2 + c0 * 32 + a], raw[OFF_W2 + (c0 + 1) * 32 + a], w.w2h_hi[a * WSH + r], w.w2h_lo[a * WSH + r]);
+        // transposed copy: word (i = a, s, tig, b) = (W2[c0][i], W2[c0 + 1][i])
+        if (t) pack(raw[OFF_W2 + a * 32 + c0], raw[OFF_W2 + a * 32 + c0 + 1], t->w2t_hi[a * WSH + r], t->w2t_lo[a * WSH + r]);
     }
     for (int f = tid; f < 32; f += nthreads) {
-        w.w1a[f] = __ldg(theta + OFF_W1 + f);
-        w.w1b[f] = __ldg(theta + OFF_W1 + H + f);
-        w.b1[f] = __ldg(theta + OFF_B1 + f);
-        w.b2[f] = __ldg(theta + OFF_B2 + f);
-        w.w3a[f] = __ldg(theta + OFF_W3 + 2 * f);
-        w.w3b[f] = __ldg(theta + OFF_W3 + 2 * f + 1);
+        w.w1a[f] = raw[OFF_W1 + f];
+        w.w1b[f] = raw[OFF_W1 + H + f];
+        w.b1[f] = raw[OFF_B1 + f];
+        w.b2[f] = raw[OFF_B2 + f];
+        w.w3a[f] = raw[OFF_W3 + 2 * f];
+        w.w3b[f] = raw[OFF_W3 + 2 * f + 1];
     }
-    if (tid < 2) w.b3[tid] = __ldg(theta + OFF_B3 + tid);
+    if (tid < 2) w.b3[tid] = raw[OFF_B3 + tid];
+    if (t && tid < 32) {   // warp 0: max |W3| over the 64 entries
+        float m = fmaxf(fabsf(raw[OFF_W3 + tid]), fabsf(raw[OFF_W3 + 32 + tid]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (tid == 0) t->w3max = m;
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ float2 lds2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
@@ -313,8 +328,8 @@ template <int TM, int G, int R, int WPC>
 __global__ void __launch_bounds__(32 * WPC) forward_kernel(FwdParams p, Consts cs)
 {
     __shared__ SmemW w;
-    stage_weights(p.theta, w, nullptr, threadIdx.x, 32 * WPC);
-    __syncthreads();
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    stage_weights(p.theta, reinterpret_cast<float *>(s_raw), w, nullptr, threadIdx.x, 32 * WPC);
     const Lane L = make_lane();
     const size_t N = (size_t)p.N;
     const int wg = blockIdx.x * WPC + (threadIdx.x >> 5);
@@ -413,14 +428,14 @@ __global__ void __launch_bounds__(32 * WPC, MINB) adjoint_kernel(AdjParams p, Co
 {
     __shared__ SmemW w;
     __shared__ SmemT wt;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    stage_weights(p.theta, w, &wt, threadIdx.x, 32 * WPC);
+    extern __shared__ __align__(16) unsigned char s_raw[];   // [raw theta (staging only)] [WarpTiles x WPC]
+    stage_weights(p.theta, reinterpret_cast<float *>(s_raw), w, &wt, threadIdx.x, 32 * WPC);
     const Lane L = make_lane();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpTiles<R> &T = reinterpret_cast<WarpTiles<R> *>(s_raw)[warp];
+    WarpTiles<R> &T = reinterpret_cast<WarpTiles<R> *>(s_raw + RAW_FLOATS * 4)[warp];
 #pragma unroll
     for (int q = 0; q < 32; ++q) T.sum[q * 32 + lane] = 0.0f;
-    __syncthreads();
+    __syncwarp();
 
     const size_t N = (size_t)p.N;
     const int wg = blockIdx.x * WPC + warp;
