@@ -274,6 +274,78 @@ def test_reference_shapes_adjoint_vs_oracle(golden, O, rates, acts):
     solver.close()
 
 
+def test_script_call_surface_seir_exposure(O):
+    """SEIR_exposure/seir_exposure.jl:114-161 transcribed: ann / initial_params / ODEProblem / predict(theta) =
+    concrete_solve(prob_nn, Vern7(), u0, theta, saveat, abstol, reltol, sensealg = InterpolatingAdjoint(autojacvec = ReverseDiffVJP()))
+    / loss returning (l, pred) / callback(theta, l, pred) / sciml_train(ADAM) -> sciml_train(BFGS).  The only line that differs from
+    the script is the one that builds prob_nn (it names the UDE form); the same dispatch is what julia/B200UDE.jl adds on the
+    reference side.  fp32 kernels: tolerances 1e-4 instead of the script's 1e-6 (Float64)."""
+    ude = _ude()
+    from universal_differential_equations_b200 import (ADAM, BFGS, FastChain, FastDense, InterpolatingAdjoint, ODEProblem, ReverseDiffVJP,
+                                                        SEIRExposureUDE, Vern7, concrete_solve, initial_params, sciml_train)
+    ann = FastChain(FastDense(3, 64, ude.tanh), FastDense(64, 64, ude.tanh), FastDense(64, 1))
+    p = initial_params(ann, np.random.default_rng(0))
+    p_ = O.SEIR_CONSTS
+    u0 = np.array([14e6 - 1e3, 0.0, 100.0, 0.0, 14e6, 0.0, 0.0], np.float32)      # seir_exposure.jl:31-32 scale
+    tspan, solution_t = (0.0, 21.0), np.arange(0.0, 22.0, 1.0)
+    prob_nn = ODEProblem(SEIRExposureUDE(ann, p_), u0, tspan, p)                       # <- the changed line (seir_exposure.jl:131)
+    noisy_data = torch.from_numpy(O.solve_fixed(O.seir_model(), np.zeros(len(p)), u0.astype(np.float64), 0.25, 84, save_every=4).T.astype(np.float32)).cuda()
+
+    def predict(theta):
+        return concrete_solve(prob_nn, Vern7(), u0, theta, saveat=solution_t, abstol=1e-4, reltol=1e-4,
+                              sensealg=InterpolatingAdjoint(autojacvec=ReverseDiffVJP()))
+
+    def loss(theta):
+        pred = predict(theta)
+        return ((noisy_data[1:4, :] - pred[1:4, :]) ** 2).sum(), pred
+
+    losses = []
+
+    def callback(theta, l, pred):
+        losses.append(l)
+        assert pred.shape == (7, 22)
+        return False
+
+    res1 = sciml_train(loss, p, ADAM(0.01), cb=callback, maxiters=6)
+    res2 = sciml_train(loss, res1.minimizer, BFGS(initial_stepnorm=0.01), cb=callback, maxiters=2)
+    assert len(losses) >= 7 and np.isfinite(losses).all()
+    assert res2.minimum <= losses[0]                       # training makes progress from the initial parameters
+    assert float(loss(res2.minimizer)[0]) == pytest.approx(res2.minimum, rel=1e-3)
+
+
+def test_script_call_surface_fisher_kpp(O):
+    """FisherKPP/Fisher-KPP-CNN.jl:89-143,236-238 transcribed (26-point grid, reaction chain 1-10-20-10-1, theta = [p1; conv taps;
+    conv bias; D0], predict_rd = concrete_solve(prob_nn, Tsit5(), rho0, theta, saveat = dt, sensealg = InterpolatingAdjoint(...)),
+    loss with the |sum of the taps| penalty, sciml_train(ADAM))."""
+    ude = _ude()
+    from universal_differential_equations_b200 import (ADAM, FastChain, FastDense, FisherKPPUDE, InterpolatingAdjoint, ODEProblem,
+                                                        ReverseDiffVJP, Tsit5, concrete_solve, initial_params, sciml_train)
+    Nx, T, dt_save = 26, 5.0, 0.5
+    X = 1.0
+    dx = X / (Nx - 1)
+    x = np.linspace(0.0, X, Nx)
+    rho0 = (0.5 * (np.tanh((x - 0.4) / 0.02) - np.tanh((x - 0.6) / 0.02))).astype(np.float32)     # Fisher-KPP-CNN.jl:27-31 shape
+    rx_nn = FastChain(FastDense(1, 10, ude.tanh), FastDense(10, 20, ude.tanh), FastDense(20, 10, ude.tanh), FastDense(10, 1))
+    p1 = initial_params(rx_nn, np.random.default_rng(1))
+    p = np.concatenate([p1, [1.1, -2.5, 1.0], [0.0], [6.5]]).astype(np.float32)      # init_w, conv bias, D0 (:100-108)
+    prob_nn = ODEProblem(FisherKPPUDE(rx_nn, Nx), rho0, (0.0, T), p)                  # <- the changed line (:131)
+    m = O.fkpp_model(Nx, (1, 10, 20, 10, 1), ("tanh", "tanh", "tanh", "identity"))
+    ode_data = torch.from_numpy((0.9 * O.solve_fixed(m, p.astype(np.float64), rho0.astype(np.float64), 0.0125, 400, save_every=40).T).astype(np.float32)).cuda()
+
+    def predict_rd(theta):
+        return concrete_solve(prob_nn, Tsit5(), rho0, theta, saveat=dt_save, dt=0.0125,
+                              sensealg=InterpolatingAdjoint(autojacvec=ReverseDiffVJP()))
+
+    def loss_rd(theta):
+        pred = predict_rd(theta)
+        return ((ode_data - pred) ** 2).sum() + 10 ** 2 * theta[-5:-2].sum().abs(), pred     # :140-143
+
+    losses = []
+    res1 = sciml_train(loss_rd, p, ADAM(0.001), cb=lambda th, l, pred: (losses.append(l), False)[1], maxiters=8)
+    assert len(losses) == 8 and np.isfinite(losses).all() and min(losses) < losses[0]
+    assert res1.minimizer.shape == (len(p),)
+
+
 def test_error_behaviour():
     ude = _ude()
     from universal_differential_equations_b200._lib import B200UDEError, EINVAL, ESTATE, EUNSUPPORTED
@@ -370,8 +442,14 @@ def test_seir_exposure_ude_vs_oracle(O):
     assert (status == 0).all() and out.shape == (22, 7, N)
     scale = np.abs(out64).max(axis=(0, 2), keepdims=True)
     assert np.all(np.abs(out - out64) <= 2e-5 * scale + 1e-3)
-    assert abs(loss - l64) <= 2e-3 * abs(l64)
-    assert np.linalg.norm(gth - g64) <= 1e-2 * np.linalg.norm(g64)
+    # error budget of this configuration: the targets are the model's own solution for a 5 % perturbed theta, so the loss
+    # cotangent 2 (u - y) is a difference of nearly equal fp32 numbers (residual rms 0.018 on states of 130: 4e-4 relative per
+    # entry from fp32 storage alone); the fp32 ORACLE differs from the fp64 one by 3.6e-5 (loss) and 3.3e-5 (grad norm).
+    l32, g32, _ = O.ensemble_loss_grad(m, theta.astype(np.float32), u0, y, w.astype(np.float32), dt, n_steps, save_every=every)
+    e_l, e_g, e_g32 = abs(loss - l64) / abs(l64), np.linalg.norm(gth - g64) / np.linalg.norm(g64), np.linalg.norm(gth - g32) / np.linalg.norm(g64)
+    print(f"SEIR: loss rel {e_l:.2e}, grad vs fp64 oracle {e_g:.2e}, vs fp32 oracle {e_g32:.2e} (fp32 oracle vs fp64: {np.linalg.norm(g32 - g64) / np.linalg.norm(g64):.2e})")
+    assert e_l <= 2e-3
+    assert e_g <= 1e-2
     solver.close()
 
 
@@ -651,6 +729,38 @@ def test_vern7_fixed_step_forward_vs_oracle(golden, O):
     assert abs(loss - l64) <= 1e-4 * abs(l64)
     assert np.linalg.norm(gth - g64) <= 2e-3 * np.linalg.norm(g64)
     assert np.abs(gu - gu64).max() <= 2e-3 * np.abs(gu64).max()
+    solver.close()
+
+
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_vern7_seir_tensor_core_forward_vs_oracle(O, tc, monkeypatch):
+    """BASELINE config 3 as stated: the SEIR exposure UDE solved with Vern7 (seir_exposure.jl:138) -- fixed step on the tcgen05
+    kernels (seir::vern7_forward_kernel) and, for comparison, on the runtime-shape kernels -- against the oracle's Vern7; the
+    interpolating adjoint of the Vern7 handle (a Tsit5 re-solve on the same kernels) against the oracle's Tsit5 adjoint."""
+    monkeypatch.setenv("B200UDE_SEIR_VERN7_TC", tc)
+    ude = _ude()
+    rng = np.random.default_rng(4)
+    N = 300
+    chain = ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1))
+    theta = glorot_theta((3, 64, 64, 1), seed=2)
+    S0 = 14e6
+    u0 = np.zeros((7, N), np.float32)
+    u0[0] = 0.9 * S0 * rng.uniform(0.9, 1.0, N)
+    u0[1:4] = rng.uniform(0, 50, (3, N)); u0[4] = S0; u0[5] = rng.uniform(0, 10, N); u0[6] = rng.uniform(0, 100, N)
+    dt, n_steps, every = 0.5, 42, 2
+    w = [0, 1, 1, 1, 0, 0, 0]
+    solver = ude.UDESolver(ude.SEIRExposureUDE(chain), 0.0, dt, n_steps, every, max_trajectories=N, loss_weights=w, alg=ude.Vern7())
+    y = rng.uniform(0, 100, (22, 7, N)).astype(np.float32)
+    out, loss, gth, gu, status = _run(solver, theta, u0, y)
+    m = O.seir_model()
+    assert (status == 0).all()
+    for k in range(0, N, 37):
+        ref = O.solve_fixed(m, theta.astype(np.float64), u0[:, k].astype(np.float64), dt, n_steps, solver=O.VERN7, save_every=every)
+        scale = np.abs(ref).max(axis=0, keepdims=True)
+        assert np.all(np.abs(out[:, :, k] - ref) <= 2e-5 * scale + 1e-3)
+    l64, g64, gu64 = O.ensemble_loss_grad(m, theta.astype(np.float64), u0, y, np.asarray(w, float), dt, n_steps, save_every=every)
+    assert abs(loss - l64) <= 1e-3 * abs(l64)      # loss of the Tsit5 re-solve vs the oracle's Tsit5: same scheme
+    assert np.linalg.norm(gth - g64) <= 1e-3 * np.linalg.norm(g64)
     solver.close()
 
 

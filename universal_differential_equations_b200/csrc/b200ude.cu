@@ -266,6 +266,7 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
         p.u0 = u0; p.out = out; p.ustep = nullptr; p.dense = nullptr; p.status = status; p.theta = h->d_theta;
         p.N = (int)N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P; p.dt = (float)h->desc.dt;
         if (h->adaptive) CUDA_TRY(h, launch_fwd_vern7_adaptive(h->gen, h->tab, p, h->ag, st));
+        else if (h->kid == K_SEIR64) CUDA_TRY(h, launch_fwd_seir_vern7(h->var, h->tab, p, st));   // tensor-core kernels (seir_tc.cuh)
         else CUDA_TRY(h, launch_fwd_vern7(h->gen, h->tab, p, st));
         if (!h->d_u0_keep && dalloc(h, &h->d_u0_keep, (size_t)h->D * h->cap) != cudaSuccess)
             return fail(h, B200UDE_ENOMEM, "forward: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -457,7 +458,9 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     if (d->solver == B200UDE_VERN7) {
         if (!generic_ok(*d) || d->model == B200UDE_MODEL_FKPP)
             return fail(nullptr, B200UDE_EUNSUPPORTED, "create: Vern7 kernels exist for the LV / SEIR / NODE forms only");
-        kid = K_GENERIC;
+        // fixed-step Vern7 of the SEIR 3-64-64-1 chain runs on the tensor-core kernels (and so does the Tsit5 re-solve its
+        // adjoint uses); every other Vern7 configuration on the runtime-shape kernels
+        if (!(kid == K_SEIR64 && !d->adaptive && env_int("B200UDE_SEIR_VERN7_TC", 1))) kid = K_GENERIC;
     }
     if (d->adaptive) {
         if (!(d->abstol > 0) || !(d->reltol > 0) || d->max_steps < 1)

@@ -73,7 +73,7 @@ static __global__ void tanh_selftest_kernel(const float *__restrict__ x, float *
     float v[4];
     for (int k = 0; k < 4; ++k) v[k] = i + k < n ? x[i + k] : 0.0f;
     float2 a = make_float2(v[0], v[1]), b = make_float2(v[2], v[3]);
-    lv32::wm::tanh_quad<0>(a, b);
+    lv32::tanh_quad<0>(a, b);
     const float r[4] = {a.x, a.y, b.x, b.y};
     for (int k = 0; k < 4; ++k)
         if (i + k < n) y[i + k] = r[k];

@@ -75,6 +75,25 @@ cudaError_t launch_fwd_seir(const Variant &v, const ConstTables &t, const FwdPar
     return v.approx_tanh ? launch_fwd<1>(p, st) : launch_fwd<0>(p, st);
 }
 
+template <int TM>
+static cudaError_t launch_fwd_vern7_t(const FwdParams &p, cudaStream_t st)
+{
+    auto kern = seir::vern7_forward_kernel<TM>;
+    constexpr size_t smem = 2 * seir::HS * seir::HS * sizeof(float);
+    static PerDeviceOnce once;
+    cudaError_t e = set_smem(kern, smem, &once.flag());
+    if (e != cudaSuccess) return e;
+    kern<<<(p.N + seir::BLOCK - 1) / seir::BLOCK, seir::BLOCK, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_seir_vern7(const Variant &v, const ConstTables &t, const FwdParams &p, cudaStream_t st)
+{
+    cudaError_t e = upload_tables(t, st);
+    if (e != cudaSuccess) return e;
+    return v.approx_tanh ? launch_fwd_vern7_t<1>(p, st) : launch_fwd_vern7_t<0>(p, st);
+}
+
 cudaError_t launch_adj_seir(const Variant &v, const ConstTables &t, const AdjParams &p, cudaStream_t st, int *rows_out)
 {
     cudaError_t e = upload_tables(t, st);

@@ -69,6 +69,43 @@ __device__ __forceinline__ float2 tanh2(float2 x)
     }
 }
 
+constexpr float TANH_ZMAX = 30.0f;   // clamp of 2 log2(e) x: tanh is 1.0f beyond x = 9.02, and (2^30 + 1)^4 < FLT_MAX
+// tanh of four values with one reciprocal (TM = 0); tanh.approx (TM = 1)
+template <int TM>
+__device__ __forceinline__ void tanh_quad(float2 &a, float2 &b)
+{
+    if constexpr (TM == 1) {
+        a = make_float2(tanh_dev<1>(a.x), tanh_dev<1>(a.y));
+        b = make_float2(tanh_dev<1>(b.x), tanh_dev<1>(b.y));
+    } else {
+        float2 za = mul2(a, bc(2.885390081777927f)), zb = mul2(b, bc(2.885390081777927f));
+        za.x = fminf(za.x, TANH_ZMAX); za.y = fminf(za.y, TANH_ZMAX);
+        zb.x = fminf(zb.x, TANH_ZMAX); zb.y = fminf(zb.y, TANH_ZMAX);
+        float2 ea, eb;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea.x) : "f"(za.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea.y) : "f"(za.y));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb.x) : "f"(zb.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb.y) : "f"(zb.y));
+        const float2 da = add2(ea, bc(1.0f)), db = add2(eb, bc(1.0f));   // 1 + e^{2x} in [1, 2^30 + 1]
+        const float2 pp = mul2(da, db);
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(pp.x * pp.y));
+        const float2 ip = make_float2(r * pp.y, r * pp.x);   // 1 / (da.x db.x), 1 / (da.y db.y)
+        const float2 ia = mul2(ip, db), ib = mul2(ip, da);   // 1 / da, 1 / db
+        a = fma2(bc(-2.0f), ia, bc(1.0f));
+        b = fma2(bc(-2.0f), ib, bc(1.0f));
+    }
+}
+
+// the same for four scalars
+template <int TM>
+__device__ __forceinline__ void tanh_quad_s(float &a, float &b, float &c, float &d)
+{
+    float2 p = make_float2(a, b), q = make_float2(c, d);
+    tanh_quad<TM>(p, q);
+    a = p.x; b = p.y; c = q.x; d = q.y;
+}
+
 struct Pair2 {
     float2 c0, c1;  // the two state components, each holding trajectories (a, b)
 };

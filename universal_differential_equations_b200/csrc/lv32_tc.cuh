@@ -209,7 +209,8 @@ __device__ __noinline__ float2 rhs_tc(TcCtx *cp, const float *sBhi, const float 
         const float4 wb1 = ldw4(zb + OFF_B1 + j4), w10 = ldw4(zb + OFF_W1 + j4), w11 = ldw4(zb + OFF_W1 + H + j4);
         const float b_[4] = {wb1.x, wb1.y, wb1.z, wb1.w}, w0_[4] = {w10.x, w10.y, w10.z, w10.w}, w1_[4] = {w11.x, w11.y, w11.z, w11.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[j4 + k] = tanh_dev<TM>(fmaf(w1_[k], x1, fmaf(w0_[k], x0, b_[k])));
+        for (int k = 0; k < 4; ++k) h[j4 + k] = fmaf(w1_[k], x1, fmaf(w0_[k], x0, b_[k]));
+        tanh_quad_s<TM>(h[j4], h[j4 + 1], h[j4 + 2], h[j4 + 3]);   // one reciprocal per four values (lv32_packed.cuh)
     }
     gemm128x32x32(c, h, sBhi, sBlo, a2);
     float y0 = c_theta[zb + OFF_B3], y1 = c_theta[zb + OFF_B3 + 1];
@@ -219,10 +220,14 @@ __device__ __noinline__ float2 rhs_tc(TcCtx *cp, const float *sBhi, const float 
         const float b_[4] = {b2.x, b2.y, b2.z, b2.w};
         const float w3_[8] = {w3a.x, w3a.y, w3a.z, w3a.w, w3b.x, w3b.y, w3b.z, w3b.w};   // (w0j, w1j) pairs
 #pragma unroll
+        float v_[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v_[k] = a2[j4 + k] + b_[k];
+        tanh_quad_s<TM>(v_[0], v_[1], v_[2], v_[3]);
+#pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float v = tanh_dev<TM>(a2[j4 + k] + b_[k]);
-            y0 = fmaf(w3_[2 * k], v, y0);
-            y1 = fmaf(w3_[2 * k + 1], v, y1);
+            y0 = fmaf(w3_[2 * k], v_[k], y0);
+            y1 = fmaf(w3_[2 * k + 1], v_[k], y1);
         }
     }
     cp->parity = c.parity;
@@ -608,7 +613,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p, Adapt
             const float4 wb1 = ldw4(zb + OFF_B1 + j4), w10 = ldw4(zb + OFF_W1 + j4), w11 = ldw4(zb + OFF_W1 + H + j4);
             const float b_[4] = {wb1.x, wb1.y, wb1.z, wb1.w}, w0_[4] = {w10.x, w10.y, w10.z, w10.w}, w1_[4] = {w11.x, w11.y, w11.z, w11.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[j4 + k] = tanh_dev<TM>(fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k])));
+            for (int k = 0; k < 4; ++k) v[j4 + k] = fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k]));
+            tanh_quad_s<TM>(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
             *reinterpret_cast<float4 *>(rowB2 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // h1 row
         }
         tc_issue(c, v, sWf_hi, sWf_lo);
@@ -621,10 +627,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) adjoint_kernel(AdjParams p, Adapt
             const float w3_[8] = {w3a.x, w3a.y, w3a.z, w3a.w, w3b.x, w3b.y, w3b.z, w3b.w};
             float h2[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                h2[k] = tanh_dev<TM>(v[j4 + k] + b_[k]);
-                v[j4 + k] = fmaf(w3_[2 * k + 1], sg1, w3_[2 * k] * sg0) * fmaf(-h2[k], h2[k], 1.0f);
-            }
+            for (int k = 0; k < 4; ++k) h2[k] = v[j4 + k] + b_[k];
+            tanh_quad_s<TM>(h2[0], h2[1], h2[2], h2[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[j4 + k] = fmaf(w3_[2 * k + 1], sg1, w3_[2 * k] * sg0) * fmaf(-h2[k], h2[k], 1.0f);
             *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(h2[0], h2[1], h2[2], h2[3]);
         }
         __syncwarp();

@@ -36,7 +36,6 @@ namespace wm {
 
 constexpr int WS = 40;    // row stride (floats) of the staged W2 and of the transpose tiles: conflict-free fragment accesses
 constexpr int WSH = 24;   // row stride (32-bit words) of the fp16 copy of W2: 16 words per output unit + 8 padding -> conflict-free LDS.64
-constexpr float TANH_ZMAX = 30.0f;   // clamp of 2 log2(e) x: tanh is 1.0f beyond x = 9.02, and (2^30 + 1)^4 < FLT_MAX
 
 struct __align__(16) SmemT {                // adjoint only: operand of W2^T q2, fp16 pairs over the contraction index j
     uint32_t w2t_hi[32 * WSH], w2t_lo[32 * WSH];   // word (i, s, tig, b) = (W2[16 s + 8 b + 2 tig][i], W2[.. + 1][i])
@@ -117,33 +116,6 @@ __device__ __forceinline__ void mma8(float (&d)[4], const uint32_t (&a)[4], uint
 // 3xTF32 split of a run-time operand: the tensor core ignores the low 13 mantissa bits of a .tf32 register, so the value
 // itself is its own "hi" part (truncation) and only the residual has to be formed
 __device__ __forceinline__ uint32_t tf32_lo(float x) { return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
-
-// tanh of four values with one reciprocal (TM = 0); tanh.approx (TM = 1)
-template <int TM>
-__device__ __forceinline__ void tanh_quad(float2 &a, float2 &b)
-{
-    if constexpr (TM == 1) {
-        a = make_float2(tanh_dev<1>(a.x), tanh_dev<1>(a.y));
-        b = make_float2(tanh_dev<1>(b.x), tanh_dev<1>(b.y));
-    } else {
-        float2 za = mul2(a, bc(2.885390081777927f)), zb = mul2(b, bc(2.885390081777927f));
-        za.x = fminf(za.x, TANH_ZMAX); za.y = fminf(za.y, TANH_ZMAX);
-        zb.x = fminf(zb.x, TANH_ZMAX); zb.y = fminf(zb.y, TANH_ZMAX);
-        float2 ea, eb;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea.x) : "f"(za.x));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea.y) : "f"(za.y));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb.x) : "f"(zb.x));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb.y) : "f"(zb.y));
-        const float2 da = add2(ea, bc(1.0f)), db = add2(eb, bc(1.0f));   // 1 + e^{2x} in [1, 2^30 + 1]
-        const float2 pp = mul2(da, db);
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(pp.x * pp.y));
-        const float2 ip = make_float2(r * pp.y, r * pp.x);   // 1 / (da.x db.x), 1 / (da.y db.y)
-        const float2 ia = mul2(ip, db), ib = mul2(ip, da);   // 1 / da, 1 / db
-        a = fma2(bc(-2.0f), ia, bc(1.0f));
-        b = fma2(bc(-2.0f), ib, bc(1.0f));
-    }
-}
 
 // per-lane constants of a warp
 struct Lane {

@@ -12,6 +12,7 @@
 // shared-memory rows with an 8 x 4 register tile per thread, run while the second sweep's MMAs are in flight;
 // the thin layers are thread-owned column sums.  Deterministic: per-group partials, fixed-order final reduce.
 #pragma once
+#include "vern7.cuh"
 #include "lv32_tc.cuh"
 
 namespace b200ude {
@@ -161,7 +162,8 @@ __device__ __noinline__ State7 rhs_seir(GrpCtx *cp, const float *sWhi, const flo
         const float4 wb = ldw4(zb + OFF_B1 + j4), w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
         const float b_[4] = {wb.x, wb.y, wb.z, wb.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[j4 + k] = tanh_dev<TM>(fmaf(w2_[k], x[2], fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k]))));
+        for (int k = 0; k < 4; ++k) h[j4 + k] = fmaf(w2_[k], x[2], fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k])));
+        lv32::tanh_quad_s<TM>(h[j4], h[j4 + 1], h[j4 + 2], h[j4 + 3]);   // one reciprocal per four values (lv32_packed.cuh)
     }
     tc_issue64(c, h, sWhi, sWlo, issuer);
     tc_collect64(c, h);
@@ -170,8 +172,12 @@ __device__ __noinline__ State7 rhs_seir(GrpCtx *cp, const float *sWhi, const flo
     for (int j4 = 0; j4 < HS; j4 += 4) {
         const float4 b2 = ldw4(zb + OFF_B2 + j4), w3 = ldw4(zb + OFF_W3 + j4);
         const float b_[4] = {b2.x, b2.y, b2.z, b2.w}, w3_[4] = {w3.x, w3.y, w3.z, w3.w};
+        float t_[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) z = fmaf(w3_[k], tanh_dev<TM>(h[j4 + k] + b_[k]), z);
+        for (int k = 0; k < 4; ++k) t_[k] = h[j4 + k] + b_[k];
+        lv32::tanh_quad_s<TM>(t_[0], t_[1], t_[2], t_[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z = fmaf(w3_[k], t_[k], z);
     }
     cp->parity = c.parity;
     // consts = F, beta0, alpha, kappa, mu, sigma, gamma, d, lambda (seir_exposure.jl:33)
@@ -271,6 +277,78 @@ __global__ void __launch_bounds__(BLOCK, 1) forward_kernel(FwdParams p)
             ++isave;
         }
         k[0] = k[6];
+    }
+    if (p.status && live) {
+        bool ok = true;
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) ok = ok && (fabsf(u.v[cc]) <= 3.0e38f);
+        p.status[n] = ok ? 0 : 1;
+    }
+    cta_teardown(tmem_base);
+}
+
+// ---- Vern7 forward kernel (fixed step): the reference's solver for this model (seir_exposure.jl:138, Vern7()), 9 stages per step
+// (the 10th only feeds the error estimate of the adaptive controller), saved states only -- Vern7's lazy dense output is not
+// available, so the interpolating adjoint of a Vern7 handle runs over a Tsit5 re-solve on these same
+// tensor-core kernels.  Stage loop fully unrolled: the tableau entries are FFMA immediates, the right-hand side stays one function.
+template <int TM>
+__global__ void __launch_bounds__(BLOCK, 1) vern7_forward_kernel(FwdParams p)
+{
+    extern __shared__ __align__(1024) float s_dyn[];
+    float *sWf_hi = s_dyn, *sWf_lo = s_dyn + HS * HS;
+    __shared__ __align__(8) uint64_t mbars[GROUPS];
+    __shared__ uint32_t tmem_slot;
+    GrpCtx c = cta_setup(mbars, &tmem_slot);
+    const uint32_t tmem_base = tmem_slot;
+    stage_weights64<false>(p.theta, sWf_hi, sWf_lo, threadIdx.x, BLOCK);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const bool issuer = (threadIdx.x % GROUP) == 0;
+    const size_t N = (size_t)p.N;
+    const int gid = blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = gid < p.N;
+    const size_t n = live ? (size_t)gid : (size_t)(p.N - 1);
+    const float dt = p.dt;
+    State7 u;
+#pragma unroll
+    for (int cc = 0; cc < D; ++cc) u.v[cc] = __ldg(p.u0 + (size_t)cc * N + n);
+    auto store = [&](float *base, int row, const State7 &v) {
+        if (live) {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) base[((size_t)row * D + cc) * N + n] = v.v[cc];
+        }
+    };
+    store(p.out, 0, u);
+    int isave = 1;
+#pragma unroll 1
+    for (int s = 0; s < p.n_steps; ++s) {
+        State7 k[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            State7 g;
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) {
+                float a = 0.0f;
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                    if (Vern7::a(i, j) != 0.0) a = fmaf((float)Vern7::a(i, j), k[j].v[cc], a);
+                g.v[cc] = fmaf(dt, a, u.v[cc]);
+            }
+            k[i] = rhs_seir<TM>(&c, sWf_hi, sWf_lo, g, i, issuer);
+        }
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (Vern7::b(j) != 0.0) a = fmaf((float)Vern7::b(j), k[j].v[cc], a);
+            u.v[cc] = fmaf(dt, a, u.v[cc]);
+        }
+        if ((s + 1) % p.save_every == 0) {
+            store(p.out, isave, u);
+            ++isave;
+        }
     }
     if (p.status && live) {
         bool ok = true;
@@ -546,7 +624,8 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p, Adaptive
             const float4 wb = ldw4(zb + OFF_B1 + j4), w0 = ldw4(zb + OFF_W1 + j4), w1 = ldw4(zb + OFF_W1 + HS + j4), w2 = ldw4(zb + OFF_W1 + 2 * HS + j4);
             const float b_[4] = {wb.x, wb.y, wb.z, wb.w}, w0_[4] = {w0.x, w0.y, w0.z, w0.w}, w1_[4] = {w1.x, w1.y, w1.z, w1.w}, w2_[4] = {w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[j4 + k] = tanh_dev<TM>(fmaf(w2_[k], x[2], fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k]))));
+            for (int k = 0; k < 4; ++k) v[j4 + k] = fmaf(w2_[k], x[2], fmaf(w1_[k], x[1], fmaf(w0_[k], x[0], b_[k])));
+            lv32::tanh_quad_s<TM>(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
             *reinterpret_cast<float4 *>(rowB2 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);   // h1 row
         }
         tc_issue64(c, v, sWf_hi, sWf_lo, issuer);
@@ -558,10 +637,10 @@ __global__ void __launch_bounds__(BLOCK, 1) adjoint_kernel(AdjParams p, Adaptive
             const float b_[4] = {b2.x, b2.y, b2.z, b2.w}, w3_[4] = {w3.x, w3.y, w3.z, w3.w};
             float h2[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                h2[k] = tanh_dev<TM>(v[j4 + k] + b_[k]);
-                v[j4 + k] = w3_[k] * sg * fmaf(-h2[k], h2[k], 1.0f);
-            }
+            for (int k = 0; k < 4; ++k) h2[k] = v[j4 + k] + b_[k];
+            lv32::tanh_quad_s<TM>(h2[0], h2[1], h2[2], h2[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[j4 + k] = w3_[k] * sg * fmaf(-h2[k], h2[k], 1.0f);
             *reinterpret_cast<float4 *>(rowB1 + j4) = make_float4(h2[0], h2[1], h2[2], h2[3]);
         }
         group_sync(c.bar_id);
