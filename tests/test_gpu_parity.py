@@ -279,7 +279,7 @@ def test_script_call_surface_seir_exposure(O):
     concrete_solve(prob_nn, Vern7(), u0, theta, saveat, abstol, reltol, sensealg = InterpolatingAdjoint(autojacvec = ReverseDiffVJP()))
     / loss returning (l, pred) / callback(theta, l, pred) / sciml_train(ADAM) -> sciml_train(BFGS).  The only line that differs from
     the script is the one that builds prob_nn (it names the UDE form); the same dispatch is what julia/B200UDE.jl adds on the
-    reference side.  fp32 kernels: tolerances 1e-4 instead of the script's 1e-6 (Float64)."""
+    reference side."""
     ude = _ude()
     from universal_differential_equations_b200 import (ADAM, BFGS, FastChain, FastDense, InterpolatingAdjoint, ODEProblem, ReverseDiffVJP,
                                                         SEIRExposureUDE, Vern7, concrete_solve, initial_params, sciml_train)
@@ -292,7 +292,10 @@ def test_script_call_surface_seir_exposure(O):
     noisy_data = torch.from_numpy(O.solve_fixed(O.seir_model(), np.zeros(len(p)), u0.astype(np.float64), 0.25, 84, save_every=4).T.astype(np.float32)).cuda()
 
     def predict(theta):
-        return concrete_solve(prob_nn, Vern7(), u0, theta, saveat=solution_t, abstol=1e-4, reltol=1e-4,
+        # fixed-step Vern7 (dt = 0.25) instead of the script's abstol = reltol = 1e-6: the 7(6) pair's error estimator is
+        # round-off limited near 1e-4 relative in fp32 (states of 1.4e7 next to states of 10), so the PI controller cannot
+        # work at the script's Float64 tolerances in this arithmetic (the adaptive fp32 path is exercised with Tsit5 elsewhere)
+        return concrete_solve(prob_nn, Vern7(), u0, theta, saveat=solution_t, dt=0.25,
                               sensealg=InterpolatingAdjoint(autojacvec=ReverseDiffVJP()))
 
     def loss(theta):
@@ -448,8 +451,9 @@ def test_seir_exposure_ude_vs_oracle(O):
     l32, g32, _ = O.ensemble_loss_grad(m, theta.astype(np.float32), u0, y, w.astype(np.float32), dt, n_steps, save_every=every)
     e_l, e_g, e_g32 = abs(loss - l64) / abs(l64), np.linalg.norm(gth - g64) / np.linalg.norm(g64), np.linalg.norm(gth - g32) / np.linalg.norm(g64)
     print(f"SEIR: loss rel {e_l:.2e}, grad vs fp64 oracle {e_g:.2e}, vs fp32 oracle {e_g32:.2e} (fp32 oracle vs fp64: {np.linalg.norm(g32 - g64) / np.linalg.norm(g64):.2e})")
-    assert e_l <= 2e-3
-    assert e_g <= 1e-2
+    assert e_l <= 5e-4       # measured 9.5e-5
+    assert e_g <= 5e-4       # measured 6.8e-5 (round 1 allowed 1e-2 without a budget)
+    assert e_g32 <= 3e-4     # measured 3.5e-5: against the fp32 oracle the kernels sit at the arithmetic's own noise
     solver.close()
 
 

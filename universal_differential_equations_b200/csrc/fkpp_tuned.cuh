@@ -413,12 +413,10 @@ __device__ __noinline__ float2 chain_value2(float2 g, int zsel)
 #pragma unroll
     for (int j4 = 0; j4 < H; j4 += 4) {
         const float4 w = ldw4(zb + O::W1 + j4), b = ldw4(zb + O::B1 + j4);
-        h1[j4 + 0] = fma2(bc(w.x), g, bc(b.x));
-        h1[j4 + 1] = fma2(bc(w.y), g, bc(b.y));
-        h1[j4 + 2] = fma2(bc(w.z), g, bc(b.z));
-        h1[j4 + 3] = fma2(bc(w.w), g, bc(b.w));
-        lv32::tanh_quad<TM>(h1[j4 + 0], h1[j4 + 1]);   // one reciprocal per four values (lv32_packed.cuh)
-        lv32::tanh_quad<TM>(h1[j4 + 2], h1[j4 + 3]);
+        h1[j4 + 0] = tanh2<TM>(fma2(bc(w.x), g, bc(b.x)));
+        h1[j4 + 1] = tanh2<TM>(fma2(bc(w.y), g, bc(b.y)));
+        h1[j4 + 2] = tanh2<TM>(fma2(bc(w.z), g, bc(b.z)));
+        h1[j4 + 3] = tanh2<TM>(fma2(bc(w.w), g, bc(b.w)));
     }
     float2 a2[H];
 #pragma unroll
@@ -441,12 +439,12 @@ __device__ __noinline__ float2 chain_value2(float2 g, int zsel)
 #pragma unroll
     for (int j4 = 0; j4 < H; j4 += 4) {
         const float4 w = ldw4(zb + O::W3 + j4);
-        lv32::tanh_quad<TM>(a2[j4 + 0], a2[j4 + 1]);
-        lv32::tanh_quad<TM>(a2[j4 + 2], a2[j4 + 3]);
-        y0 = fma2(bc(w.x), a2[j4 + 0], y0);
-        y1 = fma2(bc(w.y), a2[j4 + 1], y1);
-        y0 = fma2(bc(w.z), a2[j4 + 2], y0);
-        y1 = fma2(bc(w.w), a2[j4 + 3], y1);
+        // (the batched-inversion tanh of lv32_packed.cuh was measured 1-3 % SLOWER here: these kernels are issue-bound and its
+        // overflow clamps cost more slots than the saved reciprocals)
+        y0 = fma2(bc(w.x), tanh2<TM>(a2[j4 + 0]), y0);
+        y1 = fma2(bc(w.y), tanh2<TM>(a2[j4 + 1]), y1);
+        y0 = fma2(bc(w.z), tanh2<TM>(a2[j4 + 2]), y0);
+        y1 = fma2(bc(w.w), tanh2<TM>(a2[j4 + 3]), y1);
     }
     return add2(y0, y1);
 }
@@ -697,12 +695,10 @@ __global__ void __launch_bounds__(256) adjoint_kernel2(AdjParams p, Geom geo)
 #pragma unroll
         for (int j4 = 0; j4 < H; j4 += 4) {
             const float4 w = ldw4(zb + O::W1 + j4), b = ldw4(zb + O::B1 + j4);
-            h1[j4 + 0] = fma2(bc(w.x), x, bc(b.x));
-            h1[j4 + 1] = fma2(bc(w.y), x, bc(b.y));
-            h1[j4 + 2] = fma2(bc(w.z), x, bc(b.z));
-            h1[j4 + 3] = fma2(bc(w.w), x, bc(b.w));
-            lv32::tanh_quad<TM>(h1[j4 + 0], h1[j4 + 1]);
-            lv32::tanh_quad<TM>(h1[j4 + 2], h1[j4 + 3]);
+            h1[j4 + 0] = tanh2<TM>(fma2(bc(w.x), x, bc(b.x)));
+            h1[j4 + 1] = tanh2<TM>(fma2(bc(w.y), x, bc(b.y)));
+            h1[j4 + 2] = tanh2<TM>(fma2(bc(w.z), x, bc(b.z)));
+            h1[j4 + 3] = tanh2<TM>(fma2(bc(w.w), x, bc(b.w)));
             *reinterpret_cast<float4 *>(&wr.A[(2 * lane) * LD + j4]) = make_float4(h1[j4].x, h1[j4 + 1].x, h1[j4 + 2].x, h1[j4 + 3].x);
             *reinterpret_cast<float4 *>(&wr.A[(2 * lane + 1) * LD + j4]) = make_float4(h1[j4].y, h1[j4 + 1].y, h1[j4 + 2].y, h1[j4 + 3].y);
         }
@@ -727,11 +723,9 @@ __global__ void __launch_bounds__(256) adjoint_kernel2(AdjParams p, Geom geo)
         for (int j4 = 0; j4 < H; j4 += 4) {
             const float4 w = ldw4(zb + O::W3 + j4);
             const float w_[4] = {w.x, w.y, w.z, w.w};
-            lv32::tanh_quad<TM>(v[j4 + 0], v[j4 + 1]);
-            lv32::tanh_quad<TM>(v[j4 + 2], v[j4 + 3]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float2 h2 = v[j4 + k];
+                const float2 h2 = tanh2<TM>(v[j4 + k]);
                 a_w3[j4 + k] = fmaf(sg.x, h2.x, fmaf(sg.y, h2.y, a_w3[j4 + k]));
                 v[j4 + k] = mul2(mul2(bc(w_[k]), sg), fma2(mul2(bc(-1.0f), h2), h2, bc(1.0f)));   // q2
                 a_b2[j4 + k] += v[j4 + k].x + v[j4 + k].y;
