@@ -32,8 +32,12 @@
  *    seir_exposure.jl:115, Flux.destructure Fisher-KPP-CNN.jl:106).
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls taking a
  *    stream are asynchronous with respect to the host unless stated otherwise.
- *  - a handle is not thread-safe; use one handle per host thread and device.  Kernels read the active handle's theta and
- *    tables from the constant bank, so work of DIFFERENT handles on one device must be stream-ordered (not concurrent).
+ *  - a handle is not thread-safe; use one handle per host thread and device.  The default kernels of the LV 2-32-32-2 chain
+ *    (warp-collective family) and the fp64 kernels read theta from the handle's own device copy: any number of such handles
+ *    can be in flight on a device.  The other kernel families read the active handle's theta and tables from the constant
+ *    bank, so work of DIFFERENT handles of those kinds on one device must be stream-ordered (not concurrent).
+ *  - the interpolating adjoint of a Vern7 handle runs over a Tsit5 re-solve from the same u0 with the same step / tolerances
+ *    (Vern7's lazy dense output is not available): with the fused L2 entry point the reported loss is that of the re-solve.
  */
 #ifndef B200UDE_H
 #define B200UDE_H
@@ -49,7 +53,11 @@ extern "C" {
 
 /* dtype */
 #define B200UDE_F32 0
-#define B200UDE_F64 1 /* reserved; kernels are fp32 in this version */
+#define B200UDE_F64 1 /* double precision: EVERY device array of the calls (theta, u0, out, data, dL_dout, grad_theta, grad_u0, loss) is
+                        * double.  Runtime-shape kernels for the LV / SEIR / NODE forms, Tsit5 and Vern7, fixed step and adaptive,
+                        * interpolating adjoint -- the precision the reference's scenario 1 / 2 and SEIR scripts run in (Float64,
+                        * abstol = reltol = 1e-6).  Entry points: create / set_params / get_params / forward / adjoint / adjoint_l2;
+                        * the host-buffer, ADAM and peer entry points return B200UDE_EUNSUPPORTED for such handles. */
 
 /* model kinds: the UDE right-hand sides of the reference */
 #define B200UDE_MODEL_LV 0   /* du1 = a1*u1 + NN1(u), du2 = -a2*u2 + NN2(u)   scenario_1.jl:69-73,
@@ -109,7 +117,7 @@ typedef struct b200ude_handle b200ude_handle;
 typedef struct b200ude_desc {
     uint32_t struct_size; /* = sizeof(b200ude_desc); checked */
     int32_t device;       /* CUDA device ordinal */
-    int32_t dtype;        /* B200UDE_F32 */
+    int32_t dtype;        /* B200UDE_F32 | B200UDE_F64 */
     int32_t model;        /* B200UDE_MODEL_* */
     int32_t state_dim;    /* d */
     int32_t n_layers;     /* dense layers of the embedded chain */

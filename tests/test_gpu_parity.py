@@ -292,10 +292,9 @@ def test_script_call_surface_seir_exposure(O):
     noisy_data = torch.from_numpy(O.solve_fixed(O.seir_model(), np.zeros(len(p)), u0.astype(np.float64), 0.25, 84, save_every=4).T.astype(np.float32)).cuda()
 
     def predict(theta):
-        # fixed-step Vern7 (dt = 0.25) instead of the script's abstol = reltol = 1e-6: the 7(6) pair's error estimator is
-        # round-off limited near 1e-4 relative in fp32 (states of 1.4e7 next to states of 10), so the PI controller cannot
-        # work at the script's Float64 tolerances in this arithmetic (the adaptive fp32 path is exercised with Tsit5 elsewhere)
-        return concrete_solve(prob_nn, Vern7(), u0, theta, saveat=solution_t, dt=0.25,
+        # the script's call; tolerances 1e-4 instead of 1e-6 in the fp32 kernels (test_f64_seir_script_call_vern7_1e6 runs it
+        # at the script's own Float64 / 1e-6)
+        return concrete_solve(prob_nn, Vern7(), u0, theta, saveat=solution_t, abstol=1e-4, reltol=1e-4,
                               sensealg=InterpolatingAdjoint(autojacvec=ReverseDiffVJP()))
 
     def loss(theta):
@@ -347,6 +346,143 @@ def test_script_call_surface_fisher_kpp(O):
     res1 = sciml_train(loss_rd, p, ADAM(0.001), cb=lambda th, l, pred: (losses.append(l), False)[1], maxiters=8)
     assert len(losses) == 8 and np.isfinite(losses).all() and min(losses) < losses[0]
     assert res1.minimizer.shape == (len(p),)
+
+
+# ---- double precision (dtype = B200UDE_F64): the precision the reference's LV scenario 1 / 2 and SEIR scripts run in ----
+def _run64(solver, theta, u0, data, want_gu0=True):
+    th = torch.from_numpy(np.asarray(theta, np.float64)).cuda()
+    solver.set_params(th)
+    status = torch.full((u0.shape[1],), -1, dtype=torch.int32, device="cuda")
+    out = solver.forward(torch.from_numpy(np.asarray(u0, np.float64)).cuda(), status=status)
+    loss, g, gu = solver.adjoint_l2(torch.from_numpy(np.asarray(data, np.float64)).cuda(), want_grad_u0=want_gu0)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), float(loss), g.cpu().numpy(), (gu.cpu().numpy() if gu is not None else None), status.cpu().numpy()
+
+
+@pytest.mark.parametrize("rates,acts", [(0, ("rbf", "rbf", "rbf")), (1, ("rbf", "rbf", "rbf")), (2, ("rbf", "rbf", "tanh"))])
+def test_f64_lv_reference_shapes_vs_oracle(golden, O, rates, acts):
+    """fp64 kernels, the reference's own LV shapes (scenario 1 / 2 / Hudson Bay: 2-5-5-5-2, 0 / 1 / 2 trainable rates), fixed-step
+    Tsit5 + interpolating adjoint: the oracle is the same algorithm in C doubles -> agreement at round-off level."""
+    ude = _ude()
+    rng = np.random.default_rng(rates)
+    N = 77
+    f = _lv5(ude, acts, rates)
+    P = 87 + rates
+    theta = rng.normal(scale=0.3, size=P)
+    if rates:
+        theta[:rates] = rng.uniform(0.5, 2.0, rates)
+    u0 = np.stack([rng.uniform(0.2, 1.0, N), rng.uniform(2.0, 5.0, N)])
+    y = rng.normal(size=(31, 2, N))
+    solver = ude.UDESolver(f, 0.0, 0.1, 30, 1, max_trajectories=N, dtype=torch.float64)
+    out, loss, g, gu, status = _run64(solver, theta, u0, y)
+    m = O.lv_model((2, 5, 5, 5, 2), acts + ("identity",), n_prefix=rates)
+    l64, g64, gu64, out64 = O.ensemble_loss_grad(m, theta, u0, y, np.ones(2), 0.1, 30, want_out=True)
+    assert (status == 0).all()
+    assert np.abs(out - out64).max() <= 1e-11 * (1 + np.abs(out64).max())
+    assert abs(loss - l64) <= 1e-11 * abs(l64)
+    assert np.linalg.norm(g - g64) <= 1e-10 * np.linalg.norm(g64)
+    assert np.abs(gu - gu64).max() <= 1e-10 * np.abs(gu64).max()
+    # generic cotangent entry point
+    cot = torch.from_numpy(2.0 * (out - y)).cuda()
+    g2, gu2 = solver.adjoint(cot)
+    assert np.linalg.norm(g2.cpu().numpy() - g) <= 1e-12 * np.linalg.norm(g)
+    solver.close()
+
+
+def test_f64_reference_call_scenario_1_vern7_1e6(golden, O):
+    """The reference's own call in its own arithmetic: solve(prob, Vern7(); saveat = 0:0.05:3, abstol = reltol = 1e-6) in Float64
+    (scenario_1.jl:41,84-85) from the stored start and trained parameters, against the reference's stored solution X-hat (KAT-2:
+    the committed artefact was produced by exactly this call) and against the oracle; gradient (adaptive Tsit5 re-solve at the
+    same tolerances) against the oracle's replay adjoint."""
+    ude = _ude()
+    g = golden["scenario_1"]
+    f = _lv5(ude)
+    theta = g["theta_trained"].astype(np.float64)
+    N = 5
+    u0 = np.repeat(g["X"][:, :1], N, axis=1).astype(np.float64)
+    ts = np.linspace(0.0, 3.0, 61)
+    solver = ude.UDESolver(f, 0.0, 0.05, 60, 1, max_trajectories=N, alg=ude.Vern7(), adaptive=True, abstol=1e-6, reltol=1e-6, max_steps=512,
+                           dtype=torch.float64)
+    rng = np.random.default_rng(0)
+    y = rng.normal(size=(61, 2, N))
+    out, loss, gth, gu, status = _run64(solver, theta, u0, y)
+    assert (status == 0).all()
+    assert np.abs(out[:, :, 0].T - g["Xhat"]).max() <= 2e-6          # the reference's own Vern7 @ 1e-6 solution (fp32 kernels: 3e-4)
+    m = O.lv_model((2, 5, 5, 5, 2), ("rbf", "rbf", "rbf", "identity"))
+    o64, _, _ = O.solve_adaptive(m, theta, u0[:, 0], ts, 1e-6, 1e-6, solver=O.VERN7)
+    assert np.abs(out[:, :, 0] - o64).max() <= 1e-7                  # same controller, same arithmetic up to libm's pow
+    g_ref = np.zeros(87)
+    for k in range(N):
+        od, rec = O.solve_adaptive_dense(m, theta, u0[:, k], ts, 1e-6, 1e-6)
+        gk, _ = O.adjoint_replay(m, theta, ts, rec, 2 * (od - y[:, :, k]))
+        g_ref += gk
+    assert np.linalg.norm(gth - g_ref) <= 1e-7 * np.linalg.norm(g_ref)
+    solver.close()
+
+
+def test_f64_seir_script_call_vern7_1e6(O):
+    """seir_exposure.jl:137-141 in its own arithmetic: concrete_solve(prob_nn, Vern7(), u0, theta, saveat = 0:21, abstol = reltol =
+    1e-6, sensealg = InterpolatingAdjoint(...)) in Float64 with populations of 1.4e7, against the oracle's Vern7 and, for the
+    gradient, the oracle's replay adjoint of the adaptive Tsit5 solve."""
+    ude = _ude()
+    ann = ude.FastChain(ude.FastDense(3, 64, ude.tanh), ude.FastDense(64, 64, ude.tanh), ude.FastDense(64, 1))
+    p = ude.initial_params(ann, np.random.default_rng(0)).astype(np.float64)
+    u0 = np.array([14e6 - 1e3, 0.0, 100.0, 0.0, 14e6, 0.0, 0.0])[:, None]
+    ts = np.arange(0.0, 22.0, 1.0)
+    w = [0, 1, 1, 1, 0, 0, 0]
+    solver = ude.UDESolver(ude.SEIRExposureUDE(ann), 0.0, 1.0, 21, 1, max_trajectories=1, alg=ude.Vern7(), adaptive=True, abstol=1e-6, reltol=1e-6,
+                           max_steps=512, loss_weights=w, dtype=torch.float64)
+    m = O.seir_model()
+    data = O.solve_fixed(m, 0.9 * p, u0[:, 0], 0.25, 84, save_every=4)[:, :, None]
+    out, loss, gth, gu, status = _run64(solver, p, u0, data)
+    assert (status == 0).all()
+    o64, _, _ = O.solve_adaptive(m, p, u0[:, 0], ts, 1e-6, 1e-6, solver=O.VERN7)
+    scale = np.abs(o64).max(axis=0, keepdims=True) + 1.0
+    assert np.all(np.abs(out[:, :, 0] - o64) <= 1e-9 * scale)
+    od, rec = O.solve_adaptive_dense(m, p, u0[:, 0], ts, 1e-6, 1e-6)
+    cot = 2 * np.asarray(w)[None, :] * (od - data[:, :, 0])
+    g_ref, gu_ref = O.adjoint_replay(m, p, ts, rec, cot)
+    assert np.linalg.norm(gth - g_ref) <= 1e-6 * np.linalg.norm(g_ref)
+    assert np.abs(gu[:, 0] - gu_ref).max() <= 1e-6 * np.abs(gu_ref).max()
+    solver.close()
+
+
+def test_f64_adam_replays_reference_loss_history(golden):
+    """KAT-4 on the GPU in the reference's arithmetic: sciml_train(loss, theta_init, ADAM(0.1)) with loss = sum(abs2, X - X-hat)
+    (scenario_1.jl:91-94,114), predictions and gradients from the fp64 kernels (16 Tsit5 substeps per save interval), replays the
+    stored losses[0..5] -- which pins the GPU gradient against the reference's own run."""
+    ude = _ude()
+    g = golden["scenario_1"]
+    f = _lv5(ude)
+    X = torch.from_numpy(g["X"].astype(np.float64)).cuda()
+    prob = ude.ODEProblem(f, g["X"][:, 0].astype(np.float64), (0.0, 3.0), None)
+    seen = []
+
+    def loss(th):
+        pred = ude.concrete_solve(prob, ude.Tsit5(), p=th, saveat=0.1, dt=0.1 / 16, sensealg=ude.InterpolatingAdjoint(), dtype=torch.float64)
+        return ((X - pred) ** 2).sum()
+
+    def cb(th, l):
+        seen.append(l)
+        return len(seen) >= 6
+    th0 = torch.from_numpy(theta_scenario1_init(g)).cuda()
+    ude.sciml_train(loss, th0, ude.ADAM(0.1), cb=cb, maxiters=10)
+    ref = g["losses"][:6]
+    assert np.all(np.abs(np.array(seen) - ref) <= 2e-6 * ref), (seen, ref)
+
+
+def test_f64_unsupported_entry_points_fail_loudly():
+    ude = _ude()
+    from universal_differential_equations_b200 import _lib
+    s = ude.UDESolver(_lv5(ude), 0.0, 0.1, 30, 1, max_trajectories=4, dtype=torch.float64)
+    with pytest.raises(_lib.B200UDEError) as e:
+        s.solve_host(np.zeros(87), np.ones((2, 4)))
+    assert e.value.code == _lib.EUNSUPPORTED
+    with pytest.raises(_lib.B200UDEError):
+        s.adam_reset()
+    with pytest.raises(_lib.B200UDEError):
+        ude.UDESolver(ude.FisherKPPUDE(ude.FastChain(ude.FastDense(1, 16, ude.tanh), ude.FastDense(16, 1)), 26), 0.0, 0.01, 10, 1, dtype=torch.float64)
+    s.close()
 
 
 def test_error_behaviour():

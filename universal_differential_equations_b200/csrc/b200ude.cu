@@ -33,7 +33,7 @@ thread_local std::string g_create_error;
 //   K_FKPP     Fisher-KPP UPDE: pointwise chain 1 -> ... -> 1 + 3-tap periodic stencil (Fisher-KPP-CNN.jl:111-126)
 //   K_SEIR64   SEIR exposure UDE 3 -> 64 -> 64 -> 1 tanh, tensor-core kernels (k_seir.cu)      BASELINE config 3
 //   K_FKPP16   Fisher-KPP UPDE with the 1 -> 16 -> 16 -> 1 tanh reaction chain (k_fkpp.cu)                BASELINE config 4
-enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2, K_GENERIC, K_FKPP, K_SEIR64, K_FKPP16 };
+enum KernelId { K_NONE = 0, K_LV32, K_LV5P0, K_LV5P1, K_LV5P2, K_GENERIC, K_FKPP, K_SEIR64, K_FKPP16, K_F64 };
 
 int kernel_num_params(KernelId k)
 {
@@ -95,6 +95,11 @@ struct b200ude_handle {
     float *d_adam_m = nullptr, *d_adam_v = nullptr, *d_train_out = nullptr;
     int *d_adam_t = nullptr;
     int adam_t = 0;   // host mirror of the step counter
+    // double-precision path (dtype = B200UDE_F64, kid = K_F64): every device array of the handle and of the callers is double
+    Shape64Host sh64{};
+    double *q_theta = nullptr, *q_ustep = nullptr, *q_dense = nullptr, *q_partial = nullptr, *q_tgrid = nullptr, *q_cot = nullptr;
+    double *q_u0_keep = nullptr, *q_aux_out = nullptr;
+    const double *q_last_out = nullptr;
     size_t dev_bytes = 0;
     std::string err;
 };
@@ -396,6 +401,7 @@ __global__ void __launch_bounds__(1024, 1) adam_kernel(AdamArgs a)
 
 int32_t ensure_adam(b200ude_handle *h)
 {
+    if (h->kid == K_F64) return fail(h, B200UDE_EUNSUPPORTED, "adam: not available for B200UDE_F64 handles (update theta on the host side)");
     if (h->d_adam_m) return B200UDE_OK;
     bool ok = dalloc(h, &h->d_adam_m, (size_t)h->P) == cudaSuccess && dalloc(h, &h->d_adam_v, (size_t)h->P) == cudaSuccess &&
               dalloc(h, &h->d_adam_t, 1) == cudaSuccess;
@@ -429,6 +435,85 @@ cudaError_t launch_adam(b200ude_handle *h, const b200ude_adam *o, const float *g
     return cudaGetLastError();
 }
 
+// ---- double-precision path (kid = K_F64) ----------------------------------------------------------------------------------
+Adapt64Host adapt64(const b200ude_handle *h)
+{
+    return Adapt64Host{h->desc.t0, h->desc.dt * h->desc.save_every, h->desc.abstol, h->desc.reltol, h->n_save, h->desc.max_steps, h->q_tgrid, h->d_nacc};
+}
+
+int32_t tsit5_forward64(b200ude_handle *h, const double *u0, size_t N, double *out, int32_t *status, cudaStream_t st)
+{
+    Fwd64Host p{u0, out, h->q_ustep, h->q_dense, status, (int)N, h->desc.n_steps, h->desc.save_every, h->desc.dt};
+    const Adapt64Host a = adapt64(h);
+    CUDA_TRY(h, launch_fwd_f64(h->sh64, p, 0, h->adaptive ? &a : nullptr, st));
+    h->q_last_out = out;
+    return B200UDE_OK;
+}
+
+int32_t do_forward64(b200ude_handle *h, const double *u0, size_t N, double *out, int32_t *status, cudaStream_t st)
+{
+    CUDA_TRY(h, cudaSetDevice(h->desc.device));
+    if (!h->have_theta) return fail(h, B200UDE_ESTATE, "forward: set_params has not been called");
+    if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "forward: N=%zu outside (0, max_trajectories=%zu]", N, h->cap);
+    if (!u0 || !out) return fail(h, B200UDE_EINVAL, "forward: null pointer");
+    if (h->desc.solver == B200UDE_VERN7) {
+        // saved states only; the interpolating adjoint runs over a Tsit5 re-solve with the same step / tolerances (as in fp32)
+        Fwd64Host p{u0, out, nullptr, nullptr, status, (int)N, h->desc.n_steps, h->desc.save_every, h->desc.dt};
+        const Adapt64Host a = adapt64(h);
+        CUDA_TRY(h, launch_fwd_f64(h->sh64, p, 1, h->adaptive ? &a : nullptr, st));
+        if (!h->q_u0_keep && dalloc(h, &h->q_u0_keep, (size_t)h->D * h->cap) != cudaSuccess)
+            return fail(h, B200UDE_ENOMEM, "forward: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        CUDA_TRY(h, cudaMemcpyAsync(h->q_u0_keep, u0, sizeof(double) * (size_t)h->D * N, cudaMemcpyDeviceToDevice, st));
+        h->N = N;
+        h->have_forward = false;
+        h->vern7_pending = true;
+        return B200UDE_OK;
+    }
+    int32_t rc = tsit5_forward64(h, u0, N, out, status, st);
+    if (rc) return rc;
+    h->N = N;
+    h->have_forward = true;
+    return B200UDE_OK;
+}
+
+int32_t do_adjoint64(b200ude_handle *h, bool l2, const double *cot, double *loss, double *grad_theta, double *grad_u0, cudaStream_t st)
+{
+    CUDA_TRY(h, cudaSetDevice(h->desc.device));
+    if (h->desc.solver == B200UDE_VERN7 && h->vern7_pending) {
+        if (!h->q_aux_out && dalloc(h, &h->q_aux_out, (size_t)h->n_save * (size_t)h->D * h->cap) != cudaSuccess)
+            return fail(h, B200UDE_ENOMEM, "adjoint: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        int32_t rc = tsit5_forward64(h, h->q_u0_keep, h->N, h->q_aux_out, nullptr, st);
+        if (rc) return rc;
+        h->vern7_pending = false;
+        h->have_forward = true;
+    }
+    if (!h->have_forward) return fail(h, B200UDE_ESTATE, "adjoint: no stored forward solution (call b200ude_forward first)");
+    if (!cot || !grad_theta) return fail(h, B200UDE_EINVAL, "adjoint: null pointer");
+    Adj64Host p{h->q_ustep, h->q_dense, cot, grad_u0, h->q_partial, (int)h->N, h->desc.n_steps, h->desc.save_every, l2 ? 1 : 0, h->desc.dt};
+    int rows = 0;
+    if (h->adaptive) {
+        const Adapt64Host a = adapt64(h);
+        double *loss_l2 = nullptr;
+        if (l2) {   // cotangent 2 w (out - data) from the interpolated saved states of the last Tsit5 forward; the loss goes straight to `loss`
+            CUDA_TRY(h, launch_l2_cot_f64(h->sh64, h->q_last_out, cot, h->q_cot, loss, h->N, h->n_save, st));
+            p.cot = h->q_cot;
+            p.fused_l2 = 0;
+            loss_l2 = loss;
+        }
+        CUDA_TRY(h, launch_adj_f64(h->sh64, p, &a, st, &rows));
+        CUDA_TRY(h, launch_reduce_f64(h->q_partial, rows, h->P + 1, grad_theta, loss_l2 ? nullptr : loss, st));
+        return B200UDE_OK;
+    }
+    CUDA_TRY(h, launch_adj_f64(h->sh64, p, nullptr, st, &rows));
+    CUDA_TRY(h, launch_reduce_f64(h->q_partial, rows, h->P + 1, grad_theta, loss, st));
+    return B200UDE_OK;
+}
+
+int32_t f64_unsupported(b200ude_handle *h, const char *what)
+{
+    return fail(h, B200UDE_EUNSUPPORTED, "%s: not available for B200UDE_F64 handles (device-pointer forward / adjoint entry points only)", what);
+}
+
 }  // namespace
 
 // ---- exported entry points ------------------------------------------------------------------------
@@ -444,7 +529,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     *out = nullptr;
     if (d->struct_size != sizeof(b200ude_desc))
         return fail(nullptr, B200UDE_EINVAL, "create: struct_size %u != %zu (ABI mismatch)", d->struct_size, sizeof(b200ude_desc));
-    if (d->dtype != B200UDE_F32) return fail(nullptr, B200UDE_EUNSUPPORTED, "create: only B200UDE_F32 kernels exist in this build");
+    if (d->dtype != B200UDE_F32 && d->dtype != B200UDE_F64) return fail(nullptr, B200UDE_EINVAL, "create: unknown dtype %d", d->dtype);
     if (d->n_layers < 1 || d->n_layers > B200UDE_MAX_LAYERS) return fail(nullptr, B200UDE_EINVAL, "create: n_layers=%d out of range", d->n_layers);
     if (d->solver != B200UDE_TSIT5 && d->solver != B200UDE_VERN7 && d->solver != B200UDE_RKC2)
         return fail(nullptr, B200UDE_EINVAL, "create: unknown solver %d", d->solver);
@@ -455,14 +540,25 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     if (d->max_trajectories == 0 || d->max_trajectories > (1ull << 26)) return fail(nullptr, B200UDE_EINVAL, "create: max_trajectories out of range");
     if (d->n_loss_weights != 0 && d->n_loss_weights != d->state_dim) return fail(nullptr, B200UDE_EINVAL, "create: n_loss_weights must be 0 or state_dim");
     KernelId kid = pick_kernel(*d);
-    if (d->solver == B200UDE_VERN7) {
+    const bool want64 = d->dtype == B200UDE_F64;
+    if (want64) {
+        // fp64: the runtime-shape one-trajectory-per-thread kernels (ude_f64.cuh): LV / SEIR / NODE forms, Tsit5 and Vern7,
+        // fixed step and adaptive, interpolating adjoint
+        if (!generic_ok(*d) || d->model == B200UDE_MODEL_FKPP || d->solver == B200UDE_RKC2 || d->sensealg != B200UDE_INTERPOLATING_ADJOINT)
+            return fail(nullptr, B200UDE_EUNSUPPORTED,
+                        "create: B200UDE_F64 kernels exist for the LV / SEIR / NODE forms (chain widths <= 64), Tsit5 / Vern7, interpolating adjoint");
+        if (d->adaptive && (!(d->abstol > 0) || !(d->reltol > 0) || d->max_steps < 1))
+            return fail(nullptr, B200UDE_EINVAL, "create: adaptive stepping needs abstol > 0, reltol > 0, max_steps >= 1");
+        kid = K_F64;
+    }
+    if (!want64 && d->solver == B200UDE_VERN7) {
         if (!generic_ok(*d) || d->model == B200UDE_MODEL_FKPP)
             return fail(nullptr, B200UDE_EUNSUPPORTED, "create: Vern7 kernels exist for the LV / SEIR / NODE forms only");
         // fixed-step Vern7 of the SEIR 3-64-64-1 chain runs on the tensor-core kernels (and so does the Tsit5 re-solve its
         // adjoint uses); every other Vern7 configuration on the runtime-shape kernels
         if (!(kid == K_SEIR64 && !d->adaptive && env_int("B200UDE_SEIR_VERN7_TC", 1))) kid = K_GENERIC;
     }
-    if (d->adaptive) {
+    if (!want64 && d->adaptive) {
         if (!(d->abstol > 0) || !(d->reltol > 0) || d->max_steps < 1)
             return fail(nullptr, B200UDE_EINVAL, "create: adaptive stepping needs abstol > 0, reltol > 0, max_steps >= 1");
         if (!generic_ok(*d) || d->model == B200UDE_MODEL_FKPP)
@@ -506,7 +602,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->sm_count = prop.multiProcessorCount;
     h->adaptive = d->adaptive != 0;
     h->P = kernel_num_params(kid);
-    if (kid == K_GENERIC || kid == K_FKPP) {
+    if (kid == K_GENERIC || kid == K_FKPP || kid == K_F64) {
         int P = d->n_prefix + d->n_suffix;
         for (int l = 0; l < d->n_layers; ++l) P += d->widths[l] * d->widths[l + 1] + d->widths[l + 1];
         h->P = P;
@@ -514,7 +610,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
         h->gen.model = d->model; h->gen.D = d->state_dim; h->gen.din = d->widths[0]; h->gen.dout = d->widths[d->n_layers];
         h->gen.n_layers = d->n_layers; h->gen.n_prefix = d->n_prefix; h->gen.P = P;
         for (int l = 0; l < 8; ++l) { h->gen.widths[l] = l <= d->n_layers ? d->widths[l] : 0; h->gen.acts[l] = l < d->n_layers ? d->acts[l] : 0; }
-        if (P > 12288) { delete h; return fail(nullptr, B200UDE_EUNSUPPORTED, "create: %d parameters exceed the constant-bank budget", P); }
+        if (kid != K_F64 && P > 12288) { delete h; return fail(nullptr, B200UDE_EUNSUPPORTED, "create: %d parameters exceed the constant-bank budget", P); }
     }
     h->var.approx_tanh = (d->flags & B200UDE_FLAG_APPROX_TANH) ? 1 : 0;
     h->var.discrete = d->sensealg == B200UDE_DISCRETE_ADJOINT ? 1 : 0;
@@ -535,6 +631,38 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     h->wm_fwd_max = (size_t)env_int("B200UDE_WM_FWD_MAX", 1 << 26);
     h->wm_adj_max = (size_t)env_int("B200UDE_WM_ADJ_MAX", 1 << 26);
 
+    if (kid == K_F64) {
+        const size_t N64 = h->cap, D64 = (size_t)h->D;
+        const size_t rec = h->adaptive ? (size_t)d->max_steps : (size_t)d->n_steps;
+        h->partial_blocks = (size_t)adj_rows_f64((int)N64);
+        bool ok64 = dalloc(h, &h->q_theta, (size_t)h->P + 1) == cudaSuccess && dalloc(h, &h->q_ustep, (rec + 1) * D64 * N64) == cudaSuccess &&
+                    dalloc(h, &h->q_dense, (rec * 6 + 1) * D64 * N64) == cudaSuccess &&
+                    dalloc(h, &h->q_partial, h->partial_blocks * (size_t)(h->P + 1)) == cudaSuccess;
+        if (h->adaptive)
+            ok64 = ok64 && dalloc(h, &h->q_tgrid, (rec + 1) * N64) == cudaSuccess && dalloc(h, &h->d_nacc, N64) == cudaSuccess &&
+                   dalloc(h, &h->q_cot, (size_t)h->n_save * D64 * N64) == cudaSuccess;
+        if (!ok64) {
+            g_create_error = std::string("create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+            b200ude_destroy(h);
+            return B200UDE_ENOMEM;
+        }
+        cudaMemset(h->q_theta, 0, sizeof(double) * ((size_t)h->P + 1));
+        Shape64Host &sh = h->sh64;
+        sh.serial = serial; sh.model = d->model; sh.D = d->state_dim; sh.din = d->widths[0]; sh.dout = d->widths[d->n_layers];
+        sh.n_layers = d->n_layers; sh.n_prefix = d->n_prefix; sh.P = h->P; sh.theta = h->q_theta;
+        for (int l = 0; l < 8; ++l) { sh.widths[l] = l <= d->n_layers ? d->widths[l] : 0; sh.acts[l] = l < d->n_layers ? d->acts[l] : 0; }
+        for (int i = 0; i < 16; ++i) {
+            sh.consts[i] = i < d->n_consts ? d->consts[i] : 0.0;
+            sh.lossw[i] = d->n_loss_weights > 0 ? (i < d->n_loss_weights ? d->loss_weights[i] : 0.0) : 1.0;
+        }
+        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            g_create_error = "create: stream allocation failed";
+            b200ude_destroy(h);
+            return B200UDE_ENOMEM;
+        }
+        *out = h;
+        return B200UDE_OK;
+    }
     const size_t N = h->cap, D = (size_t)h->D;
     h->partial_blocks = (size_t)(kid == K_LV32 ? std::max(adj_grid_lv32((int)N), adj_rows_lv32_wm((int)N)) : kid == K_GENERIC ? adj_rows_generic((int)N) : kid == K_FKPP ? adj_rows_fkpp((int)N, d->state_dim) : kid == K_SEIR64 ? adj_rows_seir((int)N) : kid == K_FKPP16 ? adj_rows_fkpp16((int)N, d->state_dim) : adj_grid_lv5((int)N));
     bool ok = true;
@@ -591,6 +719,8 @@ void b200ude_destroy(b200ude_handle *h)
     cudaFree(h->d_u0_keep); cudaFree(h->d_aux_out);
     cudaFree(h->d_adam_m); cudaFree(h->d_adam_v); cudaFree(h->d_adam_t); cudaFree(h->d_train_out);
     cudaFree(h->d_tgrid); cudaFree(h->d_nacc); cudaFree(h->d_cot); cudaFree(h->d_block_loss);
+    cudaFree(h->q_theta); cudaFree(h->q_ustep); cudaFree(h->q_dense); cudaFree(h->q_partial); cudaFree(h->q_tgrid); cudaFree(h->q_cot);
+    cudaFree(h->q_u0_keep); cudaFree(h->q_aux_out);
     if (h->h_loss) cudaFreeHost(h->h_loss);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -607,6 +737,9 @@ int32_t b200ude_set_params(b200ude_handle *h, const void *theta, size_t P, int32
     if (!h) return B200UDE_EINVAL;
     if (!theta || P != (size_t)h->P) return fail(h, B200UDE_EINVAL, "set_params: P=%zu, expected %d", P, h->P);
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->kid == K_F64)
+        CUDA_TRY(h, cudaMemcpyAsync(h->q_theta, theta, sizeof(double) * P, mem == B200UDE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    else
     CUDA_TRY(h, cudaMemcpyAsync(h->d_theta, theta, sizeof(float) * P,
                                 mem == B200UDE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     h->have_theta = true;
@@ -616,12 +749,14 @@ int32_t b200ude_set_params(b200ude_handle *h, const void *theta, size_t P, int32
 int32_t b200ude_forward(b200ude_handle *h, const void *u0, size_t N, void *out, int32_t *status, void *stream)
 {
     if (!h) return B200UDE_EINVAL;
+    if (h->kid == K_F64) return do_forward64(h, (const double *)u0, N, (double *)out, status, (cudaStream_t)stream);
     return do_forward(h, (const float *)u0, N, (float *)out, status, (cudaStream_t)stream);
 }
 
 int32_t b200ude_adjoint(b200ude_handle *h, const void *dL_dout, void *grad_theta, void *grad_u0, void *stream)
 {
     if (!h) return B200UDE_EINVAL;
+    if (h->kid == K_F64) return do_adjoint64(h, false, (const double *)dL_dout, nullptr, (double *)grad_theta, (double *)grad_u0, (cudaStream_t)stream);
     return do_adjoint(h, false, (const float *)dL_dout, nullptr, (float *)grad_theta, (float *)grad_u0,
                       (cudaStream_t)stream);
 }
@@ -629,6 +764,7 @@ int32_t b200ude_adjoint(b200ude_handle *h, const void *dL_dout, void *grad_theta
 int32_t b200ude_adjoint_l2(b200ude_handle *h, const void *data, void *loss, void *grad_theta, void *grad_u0, void *stream)
 {
     if (!h) return B200UDE_EINVAL;
+    if (h->kid == K_F64) return do_adjoint64(h, true, (const double *)data, (double *)loss, (double *)grad_theta, (double *)grad_u0, (cudaStream_t)stream);
     return do_adjoint(h, true, (const float *)data, (float *)loss, (float *)grad_theta, (float *)grad_u0,
                       (cudaStream_t)stream);
 }
@@ -651,6 +787,7 @@ static int32_t ensure_host_path(b200ude_handle *h)
 int32_t b200ude_solve_host(b200ude_handle *h, const void *theta, const void *u0, size_t N, void *out, int32_t *status)
 {
     if (!h) return B200UDE_EINVAL;
+    if (h->kid == K_F64) return f64_unsupported(h, "solve_host");
     if (!theta || !u0 || !out) return fail(h, B200UDE_EINVAL, "solve_host: null pointer");
     if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "solve_host: N=%zu outside (0, %zu]", N, h->cap);
     int32_t rc = ensure_host_path(h);
@@ -672,6 +809,7 @@ int32_t b200ude_loss_gradient_host(b200ude_handle *h, const void *theta, const v
                                    double *loss, void *grad_theta, void *grad_u0)
 {
     if (!h) return B200UDE_EINVAL;
+    if (h->kid == K_F64) return f64_unsupported(h, "loss_gradient_host");
     if (!theta || !u0 || !data || !grad_theta) return fail(h, B200UDE_EINVAL, "loss_gradient_host: null pointer");
     if (N == 0 || N > h->cap) return fail(h, B200UDE_EINVAL, "loss_gradient_host: N=%zu outside (0, %zu]", N, h->cap);
     int32_t rc = ensure_host_path(h);
@@ -703,6 +841,10 @@ int32_t b200ude_get_params(b200ude_handle *h, void *theta, size_t P, int32_t mem
 {
     if (!h) return B200UDE_EINVAL;
     if (!theta || P != (size_t)h->P) return fail(h, B200UDE_EINVAL, "get_params: P=%zu, expected %d", P, h->P);
+    if (h->kid == K_F64)
+        CUDA_TRY(h, cudaMemcpyAsync(theta, h->q_theta, sizeof(double) * P, mem == B200UDE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream));
+    else
     CUDA_TRY(h, cudaMemcpyAsync(theta, h->d_theta, sizeof(float) * P,
                                 mem == B200UDE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     if (mem != B200UDE_DEVICE) CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
@@ -797,6 +939,7 @@ static size_t peer_buf_bytes(const b200ude_handle *h)
 int32_t b200ude_peer_export(b200ude_handle *h, void *handle_out)
 {
     if (!h) return B200UDE_EINVAL;
+    if (h->kid == K_F64) return fail(h, B200UDE_EUNSUPPORTED, "peer_export: not available for B200UDE_F64 handles (all-reduce the result of b200ude_adjoint_l2)");
     if (!handle_out) return fail(h, B200UDE_EINVAL, "peer_export: null pointer");
     static_assert(sizeof(cudaIpcMemHandle_t) == B200UDE_PEER_HANDLE_BYTES, "CUDA IPC handle size");
     if (!h->d_peer_buf) {

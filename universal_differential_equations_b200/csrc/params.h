@@ -153,4 +153,37 @@ struct PeerLinks {
 cudaError_t launch_reduce_exchange(const float *partial, int nblocks, int P1, const PeerLinks &, float *grad, float *loss, cudaStream_t);
 cudaError_t launch_reduce(const float *partial, int nblocks, int P1, float *grad, float *loss, cudaStream_t);
 
+// ---- double-precision path (dtype = B200UDE_F64; k_f64.cu / ude_f64.cuh) ----
+struct Shape64Host {
+    uint64_t serial;
+    int model, D, din, dout, n_layers, n_prefix, P;
+    int widths[8], acts[8];
+    const double *theta;
+    double consts[16], lossw[16];
+};
+struct Fwd64Host {
+    const double *u0;
+    double *out, *ustep, *dense;
+    int32_t *status;
+    int N, n_steps, save_every;
+    double dt;
+};
+struct Adj64Host {
+    const double *ustep, *dense, *cot;
+    double *grad_u0, *partial;
+    int N, n_steps, save_every, fused_l2;
+    double dt;
+};
+struct Adapt64Host {
+    double t0, save_dt, abstol, reltol;
+    int n_save, max_steps;
+    double *tgrid;
+    int *nacc;
+};
+int adj_rows_f64(int N);
+cudaError_t launch_fwd_f64(const Shape64Host &, const Fwd64Host &, int solver, const Adapt64Host *adaptive_or_null, cudaStream_t);
+cudaError_t launch_adj_f64(const Shape64Host &, const Adj64Host &, const Adapt64Host *adaptive_or_null, cudaStream_t, int *rows_out);
+cudaError_t launch_reduce_f64(const double *partial, int nrows, int P1, double *grad, double *loss, cudaStream_t);
+cudaError_t launch_l2_cot_f64(const Shape64Host &, const double *out, const double *data, double *cot, double *loss, size_t N, int n_save, cudaStream_t);
+
 }  // namespace b200ude

@@ -74,8 +74,14 @@ __device__ __forceinline__ void model_inputs(const float *u, float *x)
     }
 }
 
-__device__ __forceinline__ void model_rhs(const float *u, float *du)
+__device__ __forceinline__ void model_rhs(const float *u_in, float *du)
 {
+    // private register copy of the state: the chain's scratch arrays (x, y, and chain_fwd's own) live in local memory, and the
+    // state is read again after the chain -- with the caller's array that read came back clobbered by x in the Vern7 adaptive
+    // kernel (stack-slot sharing after inlining; found with a device printf), which sent every SEIR solve to max_steps
+    float u[MAXD];
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) u[c] = c < c_gen.D ? u_in[c] : 0.0f;
     float x[MAXD], y[MAXD];
     model_inputs(u, x);
     chain_fwd<false>(x, y, nullptr, nullptr);
@@ -240,8 +246,11 @@ __device__ __noinline__ void chain_vjp(const float *x, const float *dy, float w,
 }
 
 // kl = (df/du)^T g ; this warp's gradient vector += sc * (df/dtheta)^T g   (all lanes of the warp participate)
-__device__ __forceinline__ void model_vjp(const float *u, const float *g, float sc, float lv, float *kl, float *gw, int lane)
+__device__ __forceinline__ void model_vjp(const float *u_in, const float *g_in, float sc, float lv, float *kl, float *gw, int lane)
 {
+    float u[MAXD], g[MAXD];   // private register copies, read again after the chain (see model_rhs)
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) { u[c] = c < c_gen.D ? u_in[c] : 0.0f; g[c] = c < c_gen.D ? g_in[c] : 0.0f; }
     float x[MAXD], dy[MAXD], dx[MAXD];
     model_inputs(u, x);
     const float w = sc * lv;   // quadrature weight, zero for padding lanes

@@ -306,7 +306,7 @@ class UDESolver:
 
     def __init__(self, f, t0, dt, n_steps, save_every=1, max_trajectories=1, device=None,
                  loss_weights=None, alg=None, sensealg=None, approx_tanh=False, adaptive=False, abstol=1e-6, reltol=1e-3,
-                 max_steps=512):
+                 max_steps=512, dtype=torch.float32):
         alg = alg or Tsit5()
         sensealg = sensealg or InterpolatingAdjoint()
         if not isinstance(sensealg, (InterpolatingAdjoint, ForwardDiffSensitivity)):
@@ -319,7 +319,10 @@ class UDESolver:
         d = _lib.Desc()
         d.struct_size = C.sizeof(_lib.Desc)
         d.device = self.device.index
-        d.dtype = _lib.F32
+        if dtype not in (torch.float32, torch.float64):
+            raise TypeError("dtype must be torch.float32 or torch.float64")
+        self.dtype = dtype
+        d.dtype = _lib.F64 if dtype == torch.float64 else _lib.F32
         d.model = f.model
         d.state_dim = f.state_dim
         chain = f.chain
@@ -374,8 +377,8 @@ class UDESolver:
     # -- device-pointer API (inputs already resident in HBM) -------------------------------
     def set_params(self, theta: torch.Tensor):
         theta = theta.detach()
-        if theta.dtype != torch.float32 or theta.numel() != self.P:
-            raise ValueError(f"theta must be float32[{self.P}]")
+        if theta.dtype != self.dtype or theta.numel() != self.P:
+            raise ValueError(f"theta must be {self.dtype}[{self.P}]")
         if theta.is_cuda:
             theta = theta.contiguous()
             _lib.check(self._h, self._L.b200ude_set_params(self._h, theta.data_ptr(), self.P, _lib.DEVICE, _stream_ptr(self.device)))
@@ -386,12 +389,12 @@ class UDESolver:
         self.generation += 1
 
     def forward(self, u0: torch.Tensor, out: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None):
-        """u0[d, N] (cuda float32) -> out[n_save, d, N]."""
-        assert u0.is_cuda and u0.dtype == torch.float32 and u0.dim() == 2 and u0.shape[0] == self.d
+        """u0[d, N] (cuda, the solver's dtype) -> out[n_save, d, N]."""
+        assert u0.is_cuda and u0.dtype == self.dtype and u0.dim() == 2 and u0.shape[0] == self.d
         u0 = u0.contiguous()
         N = u0.shape[1]
         if out is None:
-            out = torch.empty((self.n_save, self.d, N), device=u0.device, dtype=torch.float32)
+            out = torch.empty((self.n_save, self.d, N), device=u0.device, dtype=self.dtype)
         sp = status.data_ptr() if status is not None else None
         _lib.check(self._h, self._L.b200ude_forward(self._h, u0.data_ptr(), N, out.data_ptr(), sp, _stream_ptr(self.device)))
         self.generation += 1
@@ -401,8 +404,9 @@ class UDESolver:
         """dL_dout[n_save, d, N] -> (grad_theta[P] summed over the ensemble, grad_u0[d, N])."""
         dL_dout = dL_dout.contiguous()
         N = dL_dout.shape[2]
-        gth = torch.empty(self.P, device=dL_dout.device, dtype=torch.float32)
-        gu0 = torch.empty((self.d, N), device=dL_dout.device, dtype=torch.float32) if want_grad_u0 else None
+        assert dL_dout.dtype == self.dtype
+        gth = torch.empty(self.P, device=dL_dout.device, dtype=self.dtype)
+        gu0 = torch.empty((self.d, N), device=dL_dout.device, dtype=self.dtype) if want_grad_u0 else None
         _lib.check(self._h, self._L.b200ude_adjoint(self._h, dL_dout.data_ptr(), gth.data_ptr(),
                                                   gu0.data_ptr() if gu0 is not None else None, _stream_ptr(self.device)))
         return gth, gu0
@@ -411,11 +415,12 @@ class UDESolver:
         """Fused L2 loss + adjoint: data[n_save, d, N] -> (loss[1], grad_theta[P], grad_u0)."""
         data = data.contiguous()
         N = data.shape[2]
+        assert data.dtype == self.dtype
         if grad_theta is None:
-            grad_theta = torch.empty(self.P, device=data.device, dtype=torch.float32)
+            grad_theta = torch.empty(self.P, device=data.device, dtype=self.dtype)
         if loss is None:
-            loss = torch.empty(1, device=data.device, dtype=torch.float32)
-        gu0 = torch.empty((self.d, N), device=data.device, dtype=torch.float32) if want_grad_u0 else None
+            loss = torch.empty(1, device=data.device, dtype=self.dtype)
+        gu0 = torch.empty((self.d, N), device=data.device, dtype=self.dtype) if want_grad_u0 else None
         _lib.check(self._h, self._L.b200ude_adjoint_l2(self._h, data.data_ptr(), loss.data_ptr(), grad_theta.data_ptr(),
                                                      gu0.data_ptr() if gu0 is not None else None, _stream_ptr(self.device)))
         return loss, grad_theta, gu0
@@ -481,7 +486,7 @@ class UDESolver:
         return a
 
     def get_params(self) -> torch.Tensor:
-        th = torch.empty(self.P, device=self.device, dtype=torch.float32)
+        th = torch.empty(self.P, device=self.device, dtype=self.dtype)
         _lib.check(self._h, self._L.b200ude_get_params(self._h, th.data_ptr(), self.P, _lib.DEVICE, _stream_ptr(self.device)))
         return th
 
@@ -571,7 +576,7 @@ def _grid_from(tspan, saveat, dt):
 
 
 def concrete_solve(prob, alg, u0=None, p=None, *, saveat=None, dt=None, adaptive=None, abstol=None, reltol=None,
-                   sensealg=None, loss_weights=None, max_steps=512):
+                   sensealg=None, loss_weights=None, max_steps=512, dtype=torch.float32):
     """Array(concrete_solve(prob, Tsit5(), u0, p; saveat, sensealg=InterpolatingAdjoint(...))).
 
     `prob` may be an ODEProblem (u0[d] -> d x n_save, like Julia's Array(sol)) or an
@@ -584,12 +589,12 @@ def concrete_solve(prob, alg, u0=None, p=None, *, saveat=None, dt=None, adaptive
     u0 = (prob.u0s if ens else base.u0) if u0 is None else u0
     p = base.p if p is None else p
     dev = torch.device("cuda", torch.cuda.current_device())
-    u0t = torch.as_tensor(u0, dtype=torch.float32, device=dev) if not isinstance(u0, torch.Tensor) else u0.to(dev, torch.float32)
+    u0t = torch.as_tensor(u0, dtype=dtype, device=dev) if not isinstance(u0, torch.Tensor) else u0.to(dev, dtype)
     if u0t.dim() == 1:
         u0t = u0t[:, None]
-    pt = torch.as_tensor(p, dtype=torch.float32, device=dev) if not isinstance(p, torch.Tensor) else p
-    if pt.dtype != torch.float32 or not pt.is_cuda:
-        pt = pt.to(dev, torch.float32)
+    pt = torch.as_tensor(p, dtype=dtype, device=dev) if not isinstance(p, torch.Tensor) else p
+    if pt.dtype != dtype or not pt.is_cuda:
+        pt = pt.to(dev, dtype)
     t0, dtv, n_steps, save_every = _grid_from(base.tspan, saveat, dt)
     N = u0t.shape[1]
     if adaptive is None:
@@ -598,13 +603,13 @@ def concrete_solve(prob, alg, u0=None, p=None, *, saveat=None, dt=None, adaptive
     reltol = 1e-3 if reltol is None else reltol
     key = (id(base.f), t0, dtv, n_steps, save_every, type(alg).__name__, getattr(alg, "stages", None), getattr(alg, "eigen_est", None),
            type(sensealg).__name__ if sensealg is not None else None, dev.index, tuple(loss_weights) if loss_weights else None,
-           bool(adaptive), abstol, reltol, max_steps)
+           bool(adaptive), abstol, reltol, max_steps, str(dtype))
     solver = _SOLVERS.get(key)
     if solver is None or solver.capacity < N:
         # a smaller cached solver is only dropped from the cache (not closed): autograd graphs that are still alive
         # may hold it for their backward pass; its handle is destroyed when the last reference goes
         solver = UDESolver(base.f, t0, dtv, n_steps, save_every, max_trajectories=max(N, 1), device=dev, alg=alg,
-                           sensealg=sensealg, loss_weights=loss_weights, adaptive=adaptive, abstol=abstol, reltol=reltol, max_steps=max_steps)
+                           sensealg=sensealg, loss_weights=loss_weights, adaptive=adaptive, abstol=abstol, reltol=reltol, max_steps=max_steps, dtype=dtype)
         _SOLVERS[key] = solver
     out = _SolveFn.apply(pt, u0t, solver)
     return out if ens else out[:, :, 0].transpose(0, 1)
