@@ -5,7 +5,7 @@ One "step" = one pass of the hot path over one batch of synthetic input: forward
 InterpolatingAdjoint gradient of the L2 trajectory-matching loss, summed over the ensemble (+ the sum over ranks of
 [grad_theta; loss] when N_gpus > 1, fused into the final reduction kernel over NVLink peer memory).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config lv|seir|fkpp]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config lv|seir|fkpp|hjb]
 
 --config lv (default, BASELINE config 2): 2->32->32->2 tanh chain, Glorot theta (seed 1), u0 ~ U(0.2,1) x U(2,5), 30 fixed
   Tsit5 steps of 0.1, states saved at every step, fp32.  The headline `value` is WEAK scaling (65 536 trajectories per GPU);
@@ -273,24 +273,187 @@ def kernel_names(run_step, torch):
         return None, f"profiler unavailable: {ex}"
 
 
+def hjb_flops(d, hls, n_steps):
+    """GEMM flops per path and iteration: forward + recomputed forward (2x), data gradients (layers 2..4) and weight gradients (4 layers)."""
+    mac_f = (d + 1) * hls + 2 * hls * hls + hls * d
+    mac_d = 2 * hls * hls + hls * d
+    return 2.0 * n_steps * (2 * mac_f + mac_d + mac_f)
+
+
+def main_hjb(a):
+    """--config hjb (BASELINE config 5): highdim_pde/lambaem.jl's NNPDENS solve -- d = 100, hls = 110, 20 Euler-Maruyama steps, 10 000
+    paths per GPU and iteration, fp64.  A step = one NNPDENS iteration (forward paths, loss, backward sweep, ADAM); metric = paths / s."""
+    import math
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    d, hls, n_steps = 100, 110, 20
+    m = a.n_per_gpu or 10000
+    unit, metric = "paths/s", "NNPDENS paths per second (forward SDE + reverse sweep + ADAM), HJB d=100"
+    workload = f"highdim_pde/lambaem.jl HJB d={d}, hls={hls}, {n_steps} EM steps, {m} paths per GPU and iteration, fp64"
+    sys.path.insert(0, ROOT)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import bsde_oracle as bo
+        theta = bo.init_params(d, hls, 0)
+        ms = min(m, 2000)
+        bo.loss_and_grad(theta, d, hls, np.zeros(d), 1.0, n_steps, 200, 1)
+        times = []
+        for i in range(max(3, min(a.steps, 5))):
+            t0 = time.perf_counter(); bo.loss_and_grad(theta, d, hls, np.zeros(d), 1.0, n_steps, ms, 1 + i); times.append(time.perf_counter() - t0)
+        v = ms / float(np.median(times))
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": len(times), "warmup": 1,
+                          "ms_per_step": 1e3 * float(np.median(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": workload, "paths_per_step": ms},
+                          "cpu_baseline": {"value": v, "unit": unit, "cores": HOST[0], "kind": "port",
+                                           "sample": f"{ms} paths per iteration (no ADAM update), oracle/bsde_oracle.py numpy fp64 (BLAS threads as the box gives)"},
+                          "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    import universal_differential_equations_b200 as ude
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    prob = ude.TerminalPDEProblem(ude.HJBTerminal(0.5, 0.5), ude.HJBNonlinearity(1.0), ude.ZeroDrift(), ude.ConstantDiffusion(math.sqrt(2.0)), np.zeros(d), (0.0, 1.0))
+    u0 = ude.Chain(ude.Dense(d, hls, ude.relu), ude.Dense(hls, hls, ude.relu), ude.Dense(hls, 1))
+    sg = ude.Chain(ude.Dense(d + 1, hls, ude.relu), ude.Dense(hls, hls, ude.relu), ude.Dense(hls, hls, ude.relu), ude.Dense(hls, d))
+    alg = ude.NNPDENS(u0, sg, opt=ude.ADAM(0.03))
+    s = ude.BSDESolver(prob, alg, n_steps, m, device=local, dtype=torch.float64)
+    theta = ude.initial_params_pde(alg)
+    s.set_params(theta)
+    opt = ude.ADAM(0.03)
+    clk = ClockSampler(local); clk.__enter__()
+    g_all = torch.empty(s.P + 1, device=dev, dtype=torch.float64)
+
+    def dist_step(i):
+        # path shards: disjoint Philox path counters, mean over ALL paths; one all-reduce of [grad; loss]; identical ADAM update everywhere
+        out = torch.empty(2, device=dev, dtype=torch.float64)
+        ude._lib.check_bsde(s._h, s._L.b200ude_bsde_loss_gradient(s._h, m, 1 + i, rank * m, world * m, out.data_ptr(), g_all.data_ptr(), None))
+        g_all[s.P] = out[0]
+        dist.all_reduce(g_all)
+        s.adam_step(opt, g_all[:s.P])
+
+    if world == 1:
+        s.train_adam(opt, m, max(a.warmup, 3), seed0=1)
+        torch.cuda.synchronize()
+        s.train_adam(opt, m, a.steps, seed0=100)
+        total_ms = s.last_train_ms()
+        timing = "CUDA events on the handle's stream around the K iterations (1 direct launch + K-1 replays of one CUDA graph)"
+    else:
+        for i in range(max(a.warmup, 3)):
+            dist_step(i)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            dist_step(100 + i)
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t)
+        timing = "host clock around K synchronous iterations (each ends in a stream synchronize), max over ranks"
+    value = world * m * a.steps / (total_ms * 1e-3)
+
+    # end to end through the host-buffer call a script makes per optimiser iteration: theta in from host, loss + gradient back to host
+    th_h = np.ascontiguousarray(s.get_params())
+    g_h, l_h, u_h = np.empty(s.P), np.empty(1), np.empty(1)
+    e2e_steps = max(5, a.steps)
+    for _ in range(2):
+        s.set_params(th_h)
+        ude._lib.check_bsde(s._h, s._L.b200ude_bsde_loss_gradient(s._h, m, 7, rank * m, world * m, l_h.ctypes.data, g_h.ctypes.data, u_h.ctypes.data))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        s.set_params(th_h)
+        ude._lib.check_bsde(s._h, s._L.b200ude_bsde_loss_gradient(s._h, m, 7 + i, rank * m, world * m, l_h.ctypes.data, g_h.ctypes.data, u_h.ctypes.data))
+        if world > 1:
+            g_all[:s.P].copy_(torch.from_numpy(g_h)); dist.all_reduce(g_all); torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t)
+    names, names_src = (None, None)
+    if rank == 0:
+        names, names_src = kernel_names(lambda: s.loss_gradient(m, 3), torch)
+    # roofline denominator: the library's own fp64 GEMM rate on this GPU, measured now (MEASURED_PEAKS.json has no fp64 entry)
+    peak = None
+    if rank == 0:
+        A = torch.randn(4096, 4096, device=dev, dtype=torch.float64); B = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
+        for _ in range(2):
+            A @ B
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); A @ B; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+    t_probe = time.perf_counter()
+    while rank == 0 and len(clk.rows) < 6 and time.perf_counter() - t_probe < 4.0:
+        s.loss_gradient(m, 5)
+    if world > 1:
+        dist.barrier()
+    clk.__exit__()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    fl = hjb_flops(d, hls, n_steps) * m
+    ms_iter = total_ms / a.steps
+    ach = fl / (ms_iter * 1e-3) / 1e12
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        from oracle import bsde_oracle as bo
+        ms_ = min(m, a.cpu_sample or 1000)
+        bo.loss_and_grad(theta, d, hls, np.zeros(d), 1.0, n_steps, 100, 1)
+        tt = []
+        for i in range(3):
+            t0 = time.perf_counter(); bo.loss_and_grad(theta, d, hls, np.zeros(d), 1.0, n_steps, ms_, 1 + i); tt.append(time.perf_counter() - t0)
+        cpu = {"value": ms_ / float(np.median(tt)), "unit": unit, "cores": HOST[0], "kind": "port",
+               "sample": f"{ms_} of the {m} paths, median of 3 iterations, oracle/bsde_oracle.py (numpy fp64, BLAS threads)", "pass_seconds": [round(x, 4) for x in tt]}
+    print(json.dumps({
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_iter,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (Brownian paths generated on the device, Philox4x32-10)",
+        "config": {"workload": workload, "paths_per_gpu": m, "global_paths": world * m, "parallelism": f"path-sharded x{world}", "timing": timing,
+                   "l2": "per-iteration working set (activations 2 x 3 x 110 x paths x 8 B + paths) exceeds L2 only above ~20 000 paths; no flush (state-carrying loop)",
+                   "allreduce": "none (1 GPU)" if world == 1 else "NCCL all-reduce of [grad; loss] per iteration"},
+        "e2e": {"value": world * m * e2e_steps / e2e_s, "unit": unit, "h2d_bytes_per_step": 8 * s.P, "d2h_bytes_per_step": 8 * (s.P + 2), "steps": e2e_steps,
+                "note": "b200ude_bsde_set_params(host theta) + b200ude_bsde_loss_gradient(host loss / grad / u0), wall clock"},
+        "gpu_launches": (len(names) if names else 0) * a.steps, "kernels_per_step": sorted(set(names)) if names else None, "kernels_source": names_src,
+        "clocks": clk.summary(),
+        "roofline": {"kernel": "the cuBLAS fp64 GEMMs of the sigmaT_grad_u network (library) -- the custom kernels between them are HBM-trivial", "bound": "tensor",
+                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
+                     "peak_source": "torch.matmul fp64 4096^3, best of 5, measured in this run (no fp64 entry in MEASURED_PEAKS.json)",
+                     "flop_per_path_iteration": hjb_flops(d, hls, n_steps),
+                     "note": "whole-iteration time against GEMM flops: the fraction also carries the element-wise kernels and launch gaps between the 110-wide GEMMs"},
+        "cpu_baseline": cpu,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="lv", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="lv", choices=sorted(CONFIGS) + ["hjb"])
     ap.add_argument("--n-per-gpu", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories in the in-line CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     a = ap.parse_args()
+    global HOST
+    if a.config == "hjb":
+        HOST = host_cores()
+        return main_hjb(a)
     cfg = CONFIGS[a.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
-    global HOST
     HOST = host_cores()   # before NCCL / CUDA initialisation can narrow the calling thread's affinity
     if a.impl == "reference":
         if rank == 0:

@@ -240,6 +240,56 @@ int32_t b200ude_adjoint_l2_allreduce(b200ude_handle *h, const void *data, void *
  * with tanh in fp64.  device = CUDA ordinal. */
 int32_t b200ude_selftest_tanh(int32_t device, const void *x, void *y, size_t n, void *stream);
 
+/* TERMINAL-PDE / SDE PATH (BASELINE config 5) -- replaces, for highdim_pde/lambaem.jl:18-34,
+ *     solve(TerminalPDEProblem(g, f, mu, sigma, x0, tspan), NNPDENS(u0, sigmaT_grad_u, opt = ADAM(eta));
+ *           maxiters, trajectories = m, alg = LambaEM(), ...)                                   [EXT NeuralNetDiffEq 1.1.0]
+ * i.e. the deep-BSDE method: dX = mu dt + sigma dW, du = -f dt + z . dW with z = sigmaT_grad_u([X; t]) and u(0) = u0(x0), all
+ * `trajectories` paths advanced together, loss = mean (g(X_T) - u_T)^2, reverse-mode gradient through the discretised solve,
+ * Flux.ADAM on both networks; the solution is u0(x0).  Problem family of the script (Hamilton-Jacobi-Bellman):
+ *     mu = 0, sigma = sigma I, f(X, u, z, p, t) = -lambda |z|^2, g(X) = log(g_a + g_b |X|^2)
+ * Networks as in the script: u0 = Dense(d, hidden, relu), Dense(hidden, hidden, relu), Dense(hidden, 1);
+ * sigmaT_grad_u = Dense(d + 1, hidden, relu) x3 -> Dense(hidden, d); theta = [u0 net; sigmaT_grad_u net], each layer vec(W)
+ * (out x in, column-major) then b -- Flux.params order.  relu'(0) = 1 (Flux 0.9 / Tracker differentiating max(zero(x), x)).
+ * Time stepping: Euler-Maruyama with the fixed step T / n_steps (LambaEM is EM with step-size control).  Brownian increments:
+ * sqrt(dt) * Box-Muller(Philox4x32-10) with counter (path, component / 4, step, 0) and key = seed; iteration i of
+ * b200ude_bsde_train_adam uses seed0 + i.  dtype selects float or double for every buffer of the calls. */
+typedef struct b200ude_bsde_handle b200ude_bsde_handle;
+typedef struct b200ude_bsde_desc {
+    uint32_t struct_size; /* = sizeof(b200ude_bsde_desc) */
+    int32_t device;
+    int32_t dtype;        /* B200UDE_F32 | B200UDE_F64 */
+    int32_t dim;          /* d */
+    int32_t hidden;       /* hls (the script: 10 + d) */
+    int32_t n_steps;
+    double T;             /* tspan = (0, T) */
+    double lambda, sigma; /* f = -lambda |z|^2; sigma = sqrt(2) in the script */
+    double g_a, g_b;      /* g(X) = log(g_a + g_b |X|^2); 0.5, 0.5 in the script */
+    const double *x0;     /* HOST double[dim]; copied by create */
+    uint64_t max_paths;   /* capacity (trajectories) */
+} b200ude_bsde_desc;
+int32_t b200ude_bsde_create(const b200ude_bsde_desc *desc, b200ude_bsde_handle **out);
+void b200ude_bsde_destroy(b200ude_bsde_handle *h);
+const char *b200ude_bsde_last_error(const b200ude_bsde_handle *h);
+size_t b200ude_bsde_num_params(const b200ude_bsde_handle *h);
+/* mem = B200UDE_HOST | B200UDE_DEVICE; set_params also zeroes the ADAM state */
+int32_t b200ude_bsde_set_params(b200ude_bsde_handle *h, const void *theta, size_t P, int32_t mem);
+int32_t b200ude_bsde_get_params(b200ude_bsde_handle *h, void *theta, size_t P, int32_t mem);
+/* one evaluation at the handle's theta: loss[1], grad[P], u0[1] = u0(x0) (host or device pointers of the handle's dtype; NULL =
+ * not wanted).  path_offset shifts the Philox path counter and total_paths (0 = n_paths) is the denominator of the mean, so
+ * that ranks of a multi-GPU job evaluate disjoint paths and their losses / gradients simply add. */
+int32_t b200ude_bsde_loss_gradient(b200ude_bsde_handle *h, size_t n_paths, uint64_t seed, uint64_t path_offset, size_t total_paths,
+                                   void *loss, void *grad, void *u0);
+/* `iters` NNPDENS iterations on the device (forward paths, loss, backward sweep, ADAM), the first launched directly, the rest
+ * as replays of one CUDA graph.  loss_history / u0_history: DEVICE arrays [iters] of the handle's dtype or NULL; slot i = the
+ * loss / u0(x0) at the pre-update theta of iteration i (what the script's `verbose` callback prints). */
+int32_t b200ude_bsde_train_adam(b200ude_bsde_handle *h, const b200ude_adam *opt, size_t n_paths, int32_t iters, uint64_t seed0,
+                                void *loss_history, void *u0_history);
+/* device time of the last b200ude_bsde_train_adam call in ms (CUDA events on the handle's stream around all its iterations) */
+double b200ude_bsde_last_train_ms(const b200ude_bsde_handle *h);
+/* one ADAM update with a caller-supplied DEVICE gradient [P] of the handle's dtype (multi-GPU: b200ude_bsde_loss_gradient on
+ * every rank's path shard, all-reduce of the gradient, then this call on every rank) */
+int32_t b200ude_bsde_adam_step(b200ude_bsde_handle *h, const b200ude_adam *opt, const void *grad);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,64 @@
+"""CPU checks of oracle/bsde_oracle.py (the deep-BSDE restatement of highdim_pde/lambaem.jl): generator known answers, the hand-written
+reverse sweep against finite differences, and the reference's own acceptance test (lambaem.jl:36-48) at a CPU-sized dimension."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from oracle import bsde_oracle as bo  # noqa: E402
+
+
+def test_philox4x32_10_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = bo.philox4x32(*[np.array([c]) for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+
+
+def test_normals_are_standard_and_independent_of_batch_size():
+    z = bo.normals(seed=7, step=3, n_paths=4000, d=10)
+    assert z.shape == (10, 4000)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    assert abs(np.corrcoef(z[0], z[1])[0, 1]) < 0.05 and abs(np.corrcoef(z[2], z[3])[0, 1]) < 0.05
+    np.testing.assert_array_equal(z[:, :100], bo.normals(7, 3, 100, 10))          # counter-based: a path's draws do not depend on M
+    assert not np.array_equal(z, bo.normals(7, 4, 4000, 10)) and not np.array_equal(z, bo.normals(8, 3, 4000, 10))
+
+
+def test_gradient_matches_central_differences():
+    d, hls, M, N = 6, 9, 16, 4
+    rng = np.random.default_rng(0)
+    pu, pz = bo.num_params(d, hls)
+    theta = 0.4 * rng.standard_normal(pu + pz)          # generic biases: no relu ties
+    x0 = rng.standard_normal(d)
+    l0, g, _ = bo.loss_and_grad(theta, d, hls, x0, 1.0, N, M, seed=5)
+    idx = rng.choice(theta.size, 40, replace=False)
+    for i in idx:
+        e = np.zeros_like(theta); e[i] = 1e-6
+        fd = (bo.loss_and_grad(theta + e, d, hls, x0, 1.0, N, M, 5)[0] - bo.loss_and_grad(theta - e, d, hls, x0, 1.0, N, M, 5)[0]) / 2e-6
+        assert abs(fd - g[i]) <= 1e-6 * max(1.0, abs(g[i])), (i, fd, g[i])
+
+
+def test_relu_tie_takes_derivative_one():
+    # zero input and zero biases: every hidden pre-activation of the u0 net is exactly 0 (lambaem.jl:9 x0 = fill(0, d), Flux zero-bias init);
+    # Flux 0.9 / Tracker give relu'(0) = 1 there, so the bias gradients of the u0 net are non-zero from the first iteration
+    d, hls = 4, 5
+    theta = bo.init_params(d, hls, seed=1)
+    pu, _ = bo.num_params(d, hls)
+    _, g, _ = bo.loss_and_grad(theta, d, hls, np.zeros(d), 1.0, 4, 8, seed=2)
+    b1 = g[d * hls:d * hls + hls]
+    assert np.all(b1 != 0.0)
+
+
+def test_reference_acceptance_criterion_small_dimension():
+    # lambaem.jl:36-48: error_l2 = |ans - analytic| / |ans| < 0.2, here at d = 10 so that the CPU suite stays short
+    d, hls, M, N = 10, 20, 64, 20
+    x0 = np.zeros(d)
+    theta, losses, u0s = bo.train(bo.init_params(d, hls, 0), d, hls, x0, 1.0, N, M, iters=250, eta=0.03, seed0=1)
+    ans = bo.loss_and_grad(theta, d, hls, x0, 1.0, N, M, seed=999)[2]
+    ref = bo.analytic_hjb(x0, 1.0, n_mc=200000)
+    assert abs(ans - ref) / abs(ans) < 0.2, (ans, ref)
+    assert losses[-20:].mean() < 0.2 * losses[:5].mean()

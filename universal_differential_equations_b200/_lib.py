@@ -30,6 +30,8 @@ EXPORTS = [
     "b200ude_forward", "b200ude_adjoint", "b200ude_adjoint_l2", "b200ude_solve_host",
     "b200ude_loss_gradient_host", "b200ude_get_params", "b200ude_adam_reset", "b200ude_adam_step", "b200ude_train_adam",
     "b200ude_peer_export", "b200ude_peer_attach", "b200ude_peer_detach", "b200ude_adjoint_l2_allreduce", "b200ude_selftest_tanh",
+    "b200ude_bsde_create", "b200ude_bsde_destroy", "b200ude_bsde_last_error", "b200ude_bsde_num_params", "b200ude_bsde_set_params",
+    "b200ude_bsde_get_params", "b200ude_bsde_loss_gradient", "b200ude_bsde_train_adam", "b200ude_bsde_adam_step", "b200ude_bsde_last_train_ms",
 ]
 PEER_HANDLE_BYTES = 64
 
@@ -57,6 +59,15 @@ class Adam(C.Structure):
         ("struct_size", C.c_uint32), ("reserved", C.c_uint32),
         ("eta", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
         ("loss_scale", C.c_double), ("l2_reg", C.c_double),
+    ]
+
+
+class BsdeDesc(C.Structure):
+    """struct b200ude_bsde_desc"""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("dtype", C.c_int32), ("dim", C.c_int32), ("hidden", C.c_int32),
+        ("n_steps", C.c_int32), ("T", C.c_double), ("lam", C.c_double), ("sigma", C.c_double), ("g_a", C.c_double), ("g_b", C.c_double),
+        ("x0", C.POINTER(C.c_double)), ("max_paths", C.c_uint64),
     ]
 
 
@@ -127,10 +138,37 @@ def lib():
     L.b200ude_adjoint_l2_allreduce.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b200ude_selftest_tanh.restype = i32
     L.b200ude_selftest_tanh.argtypes = [i32, vp, vp, sz, vp]
+    u64 = C.c_uint64
+    L.b200ude_bsde_create.restype = i32
+    L.b200ude_bsde_create.argtypes = [C.POINTER(BsdeDesc), C.POINTER(vp)]
+    L.b200ude_bsde_destroy.restype = None
+    L.b200ude_bsde_destroy.argtypes = [vp]
+    L.b200ude_bsde_last_error.restype = C.c_char_p
+    L.b200ude_bsde_last_error.argtypes = [vp]
+    L.b200ude_bsde_num_params.restype = sz
+    L.b200ude_bsde_num_params.argtypes = [vp]
+    L.b200ude_bsde_set_params.restype = i32
+    L.b200ude_bsde_set_params.argtypes = [vp, vp, sz, i32]
+    L.b200ude_bsde_get_params.restype = i32
+    L.b200ude_bsde_get_params.argtypes = [vp, vp, sz, i32]
+    L.b200ude_bsde_loss_gradient.restype = i32
+    L.b200ude_bsde_loss_gradient.argtypes = [vp, sz, u64, u64, sz, vp, vp, vp]
+    L.b200ude_bsde_train_adam.restype = i32
+    L.b200ude_bsde_train_adam.argtypes = [vp, C.POINTER(Adam), sz, i32, u64, vp, vp]
+    L.b200ude_bsde_last_train_ms.restype = C.c_double
+    L.b200ude_bsde_last_train_ms.argtypes = [vp]
+    L.b200ude_bsde_adam_step.restype = i32
+    L.b200ude_bsde_adam_step.argtypes = [vp, C.POINTER(Adam), vp]
     if L.b200ude_version() != ABI_VERSION:
         raise RuntimeError("libb200ude.so ABI version mismatch")
     _lib = L
     return L
+
+
+def check_bsde(handle, rc):
+    if rc != 0:
+        msg = lib().b200ude_bsde_last_error(handle)
+        raise B200UDEError(rc, msg.decode() if msg else "")
 
 
 def check(handle, rc):
