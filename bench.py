@@ -12,6 +12,8 @@ InterpolatingAdjoint gradient of the L2 trajectory-matching loss, summed over th
   the `strong` object of the same line is the metric's literal batch: 65 536 trajectories IN TOTAL over the N GPUs.
 --config seir (config 3): 7-state SEIR exposure UDE, 3->64->64->1 chain, 84 steps of 0.25, saved daily, loss on E, I, R.
 --config fkpp (config 4): Fisher-KPP UPDE on a 256-point grid, 1->16->16->1 reaction chain + 3-tap stencil, 200 steps.
+--config hjb (config 5): highdim_pde/lambaem.jl's NNPDENS solve (d = 100, hls = 110, 20 Euler-Maruyama steps), 10 000 paths per GPU
+  and iteration, fp64; a step = one iteration (forward paths + reverse sweep + ADAM); metric = paths/s.
 Under torchrun one rank per GPU.  Rank 0 prints ONE JSON line.
 """
 import argparse
@@ -274,10 +276,10 @@ def kernel_names(run_step, torch):
 
 
 def hjb_flops(d, hls, n_steps):
-    """GEMM flops per path and iteration: forward + recomputed forward (2x), data gradients (layers 2..4) and weight gradients (4 layers)."""
-    mac_f = (d + 1) * hls + 2 * hls * hls + hls * d
+    """GEMM flops per path and iteration: forward (bias column included), data gradients (layers 2..4), weight + bias gradients (4 layers)."""
+    mac_f = (d + 2) * hls + 2 * (hls + 1) * hls + (hls + 1) * d
     mac_d = 2 * hls * hls + hls * d
-    return 2.0 * n_steps * (2 * mac_f + mac_d + mac_f)
+    return 2.0 * n_steps * (mac_f + mac_d + mac_f)
 
 
 def main_hjb(a):

@@ -226,4 +226,50 @@ function train_adam!(h::Handle, θ::Vector{Float32}, u0, data, opt::Adam, iters:
     θ
 end
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# Terminal-PDE path: highdim_pde/lambaem.jl:18-34   solve(TerminalPDEProblem(...), NNPDENS(u0, σᵀ∇u, opt = ADAM(η)); ...)
+# (include/b200ude.h, b200ude_bsde_*).  g, f, μ, σ are closures in the script; the device path knows the script's family
+#   μ = 0, σ = s I, f = -λ |σᵀ∇u|², g(X) = log(a + b |X|²)
+# so the shim takes them as a tagged struct.  Source only (no `julia` in the build image).
+struct HJB; λ::Float64; s::Float64; a::Float64; b::Float64; end
+HJB(; λ = 1.0, s = sqrt(2.0), a = 0.5, b = 0.5) = HJB(λ, s, a, b)
+
+mutable struct BsdeDesc
+    struct_size::UInt32; device::Int32; dtype::Int32; dim::Int32; hidden::Int32; n_steps::Int32
+    T::Float64; lambda::Float64; sigma::Float64; g_a::Float64; g_b::Float64
+    x0::Ptr{Float64}; max_paths::UInt64
+end
+
+"""`solve_nnpdens(HJB(), x0, tspan, u0, σᵀ∇u; opt = Adam(0.03), maxiters = 500, trajectories = 100, dt = T/20, seed = 1, T = Float32)`:
+`u0`, `σᵀ∇u` are the script's Flux chains (`Dense(d, hls, relu)` ... ); their parameters are read with `Flux.destructure`
+(per layer vec(W), then b: the ABI's order), trained on the device and written back.  Returns u0(x0) (the script's `ans`)."""
+function solve_nnpdens(fam::HJB, x0::AbstractVector, tspan, u0, σᵀ∇u; opt::Adam, maxiters = 500, trajectories = 100,
+                       dt = (tspan[2] - tspan[1]) / 20, seed = 1, device = 0, T::Type = Float32, destructure)
+    d = length(x0); θu, reu = destructure(u0); θz, rez = destructure(σᵀ∇u)
+    # length(θu) = d h + h + h² + h + h + 1 = h² + (d + 3) h + 1  ->  h
+    hls = Int(round((-(d + 3) + sqrt((d + 3)^2 - 4 * (1 - length(θu)))) / 2))
+    x0d = Float64.(x0)
+    desc = BsdeDesc(0, device, T === Float64 ? 1 : 0, d, hls, round(Int, (tspan[2] - tspan[1]) / dt), Float64(tspan[2]), fam.λ, fam.s, fam.a, fam.b,
+                    pointer(x0d), trajectories)
+    desc.struct_size = sizeof(BsdeDesc)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve x0d begin
+        rc = ccall((:b200ude_bsde_create, lib), Int32, (Ref{BsdeDesc}, Ref{Ptr{Cvoid}}), desc, h)
+    end
+    rc == 0 || error(unsafe_string(ccall((:b200ude_bsde_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+    bcheck(rc) = rc == 0 || error(unsafe_string(ccall((:b200ude_bsde_last_error, lib), Cstring, (Ptr{Cvoid},), h[])))
+    try
+        θ = T.(vcat(θu, θz)); P = length(θ)
+        bcheck(ccall((:b200ude_bsde_set_params, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Int32), h[], θ, P, HOST))
+        opt.struct_size = sizeof(Adam)
+        bcheck(ccall((:b200ude_bsde_train_adam, lib), Int32, (Ptr{Cvoid}, Ref{Adam}, Csize_t, Int32, UInt64, Ptr{Cvoid}, Ptr{Cvoid}),
+                     h[], opt, trajectories, maxiters, seed, C_NULL, C_NULL))
+        bcheck(ccall((:b200ude_bsde_get_params, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Int32), h[], θ, P, HOST))
+        u0t = reu(θ[1:length(θu)])                       # the trained networks, as Flux chains again
+        return first(u0t(T.(x0))), u0t, rez(θ[length(θu)+1:end])
+    finally
+        ccall((:b200ude_bsde_destroy, lib), Cvoid, (Ptr{Cvoid},), h[])
+    end
+end
+
 end # module
