@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -222,6 +223,352 @@ __global__ void k_adam(R *theta, R *m, R *v, const R *grad, int P, int *t_dev, u
     }
 }
 
+// ---- fused fp64 sweeps (DMMA) ---------------------------------------------------------------------------------------------
+// One warp owns 8 paths and carries them through the whole network in the fragment layout of mma.sync.m8n8k4.f64: M = the 8 paths,
+// N = the units of a layer (<= FT tiles of 8), K = the layer's inputs + the bias row.  The D fragment of a layer (path lane >> 2, unit
+// pair 2 (lane & 3)) is written as one 16-byte word into the warp's own shared-memory rows and read back as the A fragment of the next
+// layer -- no other warp ever touches those rows.  The weights (0.4 MB in fp64: more than an SM's shared memory) stream through a
+// two-slab ring in shared memory that all warps of the CTA share: a zero-padded operand copy of theta is cut into slabs of FSR
+// contraction rows x FLD (unit-contiguous, already in the padded shared-memory layout), and ONE elected thread moves a whole slab
+// with one TMA bulk copy (cp.async.bulk + mbarrier transaction count) two slabs ahead of the math; a slab is released by a CTA barrier.
+// (Reading the B fragments straight from L2 instead made every warp stream all weights: 10 TFLOP/s, L2-bound.)  relu (with the side
+// of a zero in its sign bit), the bias (K includes the ones row), the Euler-Maruyama update, the Brownian increments, the terminal
+// residual (forward) and the cotangent of z, the relu' masks (backward) are applied to the fragments in registers; the tape
+// (activations, cotangents) is written from the fragments for the batched weight-gradient GEMMs.
+constexpr int FT = 14;        // unit tiles per layer: widths up to 112
+constexpr int FW = 8 * FT;    // padded unit count
+constexpr int FLD = 116;      // row stride in doubles of activations and slabs (= 4 mod 16: conflict-free 8-byte fragment reads per half warp)
+constexpr int FSR = 16;       // contraction rows per slab
+constexpr int FSLAB = FSR * FLD;                          // doubles per slab
+constexpr uint32_t FSLAB_BYTES = FSLAB * sizeof(double);   // 14 848
+constexpr int FWPC = 4;       // warps per CTA; three CTAs per SM run out of step with one another, so one's barrier / tape-latency /
+                              // Euler-Maruyama phases are covered by the others' DMMA phases
+constexpr int FMAXSLABS = 32;
+
+struct FusedArgs {
+    const double *slabs;   // forward slabs, then backward slabs
+    int n_f, n_b;          // slab counts
+    // per slab: layer, first contraction row, k-steps of 4 valid rows, last slab of its layer?
+    unsigned char f_layer[FMAXSLABS], f_k0[FMAXSLABS], f_ks[FMAXSLABS], f_last[FMAXSLABS];
+    unsigned char b_layer[FMAXSLABS], b_k0[FMAXSLABS], b_ks[FMAXSLABS], b_last[FMAXSLABS];
+    double *IN, *H[3], *Z, *Zb, *C[3], *u, *r2, *ubar;   // Z holds G = 2 lambda z dt + dW here (zbar = ubar G)
+    uint32_t *mask;        // relu' bits of the hidden layers: word ((n * 3 + l) * M + path) * 4 + (lane & 3), bit 2 nt + e
+    const double *x0, *u0;
+    const uint64_t *seed;
+    uint32_t path0;
+    int M, N, d, hl;
+    double dt, lam, s, ga, gb, inv_total;
+};
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+// the two standard normals this lane needs for components (m, m + 1), m even: the first or second Box-Muller pair of block m / 4
+__device__ __forceinline__ void normals2(uint64_t seed, uint32_t path, int m, uint32_t step, double &n0, double &n1)
+{
+    uint32_t c0 = path, c1 = (uint32_t)(m >> 2), c2 = step, c3 = 0u;
+    philox4x32(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double s32 = 2.3283064365386963e-10;
+    const bool second = (m & 2) != 0;
+    const double ua = ((double)(second ? c2 : c0) + 0.5) * s32, ub = ((double)(second ? c3 : c1) + 0.5) * s32;
+    const double ra = sqrt(-2.0 * log(ua));
+    double sn, cs;
+    sincos(6.283185307179586 * ub, &sn, &cs);
+    n0 = ra * cs; n1 = ra * sn;
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+}
+// the slab ring: FRING buffers with one "full" mbarrier each; the stream of slabs (n_slabs per round, round after round) is
+// consumed in order; (cb, cph) = buffer and barrier phase of the slab being consumed
+constexpr int FRING = 3;
+struct SlabProducer {     // thread 0's bookkeeping, kept in shared memory (registers are the scarce resource of these kernels)
+    const double *src;
+    long issued, total;
+    int n_slabs, ib;      // slabs per round; buffer of the next slab to issue
+};
+struct SlabRing {
+    double *base;         // FRING slabs
+    uint32_t bar0;        // FRING mbarriers, 8 bytes apart
+    SlabProducer *prod;
+    int cb, cph;          // consumer cursor
+    __device__ __forceinline__ void issue()   // one thread
+    {
+        SlabProducer &q = *prod;
+        if (q.issued >= q.total) return;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(base + (size_t)q.ib * FSLAB), br = bar0 + 8u * q.ib;
+        const double *g = q.src + (size_t)(q.issued % q.n_slabs) * FSLAB;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(br), "r"(FSLAB_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g), "r"(FSLAB_BYTES),
+                     "r"(br)
+                     : "memory");
+        ++q.issued;
+        q.ib = q.ib == FRING - 1 ? 0 : q.ib + 1;
+    }
+    __device__ __forceinline__ const double *cur() const { return base + (size_t)cb * FSLAB; }
+    __device__ __forceinline__ int nb() const { return cb == FRING - 1 ? 0 : cb + 1; }
+    __device__ __forceinline__ void wait_cur() const { mbar_wait(bar0 + 8u * cb, (uint32_t)cph); }
+    __device__ __forceinline__ const double *wait_next() const   // the slab after the current one (must exist)
+    {
+        const int n = nb();
+        mbar_wait(bar0 + 8u * n, (uint32_t)(n == 0 ? cph ^ 1 : cph));
+        return base + (size_t)n * FSLAB;
+    }
+    __device__ __forceinline__ void advance() { cb = nb(); if (cb == 0) cph ^= 1; }
+};
+// One slab of a layer: acc[nt] += sum over its FSR rows of in[r][k0 + k] * slab[k][8 nt + r'].  The B fragments of a k-step are loaded
+// one k-step ahead of the DMMAs that use them -- bv holds those of the slab's first k-step on entry and, with `more`, those of the
+// NEXT slab's first k-step on return (its arrival is awaited just before, three k-steps into this slab).  Rows beyond a layer's inputs
+// are zero in the slab and finite in `in`, so every slab runs all its k-steps.
+__device__ __forceinline__ void slab_mma(const double *in, const SlabRing &ring, bool more, int k0, int r, int c, double (&acc)[FT][2], double (&bv)[FT])
+{
+    const double *wp = ring.cur() + c * FLD + r;
+    const double *ap = in + r * FLD + k0 + c;
+#pragma unroll
+    for (int ks = 0; ks < FSR / 4; ++ks) {
+        double nx[FT];
+        if (ks < FSR / 4 - 1) {
+#pragma unroll
+            for (int nt = 0; nt < FT; ++nt) nx[nt] = wp[(ks + 1) * 4 * FLD + 8 * nt];
+        } else if (more) {
+            const double *np = ring.wait_next() + c * FLD + r;
+#pragma unroll
+            for (int nt = 0; nt < FT; ++nt) nx[nt] = np[8 * nt];
+        }
+        const double av = ap[4 * ks];
+#pragma unroll
+        for (int nt = 0; nt < FT; ++nt) dmma(acc[nt], av, bv[nt]);
+#pragma unroll
+        for (int nt = 0; nt < FT; ++nt) bv[nt] = nx[nt];
+    }
+}
+__device__ __forceinline__ void slab_first(const SlabRing &ring, int r, int c, double (&bv)[FT])   // start (or restart) of the B pipeline
+{
+    ring.wait_cur();
+    const double *wp = ring.cur() + c * FLD + r;
+#pragma unroll
+    for (int nt = 0; nt < FT; ++nt) bv[nt] = wp[8 * nt];
+}
+// shared-memory carve-up: [FRING slabs][per warp: one activation buffer of 8 rows, updated in place][FRING mbarriers]
+__device__ __forceinline__ void fused_setup(double *fsm, int nwarps, SlabRing &ring, const double *src, int n_slabs, long total)
+{
+    ring.base = fsm;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + FRING * FSLAB + (size_t)nwarps * 8 * FLD);
+    ring.bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    ring.prod = reinterpret_cast<SlabProducer *>(bars + FRING);
+    ring.cb = 0; ring.cph = 0;
+    if (threadIdx.x == 0) { ring.prod->src = src; ring.prod->n_slabs = n_slabs; ring.prod->issued = 0; ring.prod->total = total; ring.prod->ib = 0; }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < FRING; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring.bar0 + 8u * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < FRING; ++i) ring.issue();
+    }
+}
+
+__global__ void __launch_bounds__(32 * FWPC, 3) k_fused_forward(const FusedArgs a)
+{
+    extern __shared__ __align__(16) double fsm[];
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+    SlabRing ring;
+    fused_setup(fsm, nwarps, ring, a.slabs, a.n_f, (long)a.n_f * a.N);
+    double *buf = fsm + FRING * FSLAB + (size_t)warp * 8 * FLD;
+    const int path = (blockIdx.x * nwarps + warp) * 8 + r;
+    const bool live = path < a.M;
+    const size_t pc = (size_t)(live ? path : a.M - 1);
+    const int d = a.d, hl = a.hl;
+    const double sq = sqrt(a.dt);
+    const uint64_t seed = *a.seed;
+    double u = *a.u0, nn = 0.0;
+    const size_t s_in = (size_t)(d + 2) * a.M, s_h = (size_t)(hl + 1) * a.M, s_z = (size_t)d * a.M;
+    {   // X_0 -> the tape and the warp's input rows (X lives on the tape between steps, not in registers)
+        double *inx = a.IN + pc * (d + 2);
+#pragma unroll
+        for (int nt = 0; nt < FT; ++nt) {
+            const int m = 8 * nt + 2 * c;
+            const double x0 = m < d ? a.x0[m] : 0.0, x1 = m + 1 < d ? a.x0[m + 1] : 0.0;
+            if (live && m < d) inx[m] = x0;
+            if (live && m + 1 < d) inx[m + 1] = x1;
+            *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(x0, x1);
+        }
+    }
+    for (int n = 0; n < a.N; ++n) {
+        // the warp's input rows hold [X_n; 0...]: add t_n and the ones row (rows d, d + 1 of the tape hold them already)
+        __syncwarp();
+        if (c == 0) { buf[r * FLD + d] = n * a.dt; buf[r * FLD + d + 1] = 1.0; }
+        __syncwarp();
+        double acc[FT][2], bv[FT];
+        slab_first(ring, r, c, bv);
+#pragma unroll 1
+        for (int i = 0; i < a.n_f; ++i) {
+            const int l = a.f_layer[i];
+            if (a.f_k0[i] == 0) {
+#pragma unroll
+                for (int nt = 0; nt < FT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+            }
+            slab_mma(buf, ring, i + 1 < a.n_f, a.f_k0[i], r, c, acc, bv);   // the B pipeline restarts at every step (registers for the update)
+            ring.advance();
+            __syncthreads();                       // every warp is done with this slab: its buffer may be refilled
+            if (threadIdx.x == 0) ring.issue();
+            if (!a.f_last[i]) continue;
+            if (l < 3) {   // the layer's output replaces its input in the warp's rows (all of the warp's reads are behind the barrier)
+                double *hp = a.H[l] + n * s_h + pc * (hl + 1);
+                uint32_t bits = 0u;
+#pragma unroll
+                for (int nt = 0; nt < FT; ++nt) {
+                    const int m = 8 * nt + 2 * c;
+                    const bool neg0 = !(acc[nt][0] >= 0.0), neg1 = !(acc[nt][1] >= 0.0);
+                    const double h0 = neg0 ? -0.0 : acc[nt][0], h1 = neg1 ? -0.0 : acc[nt][1];
+                    bits |= (neg0 ? 1u : 0u) << (2 * nt) | (neg1 ? 1u : 0u) << (2 * nt + 1);
+                    *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(h0, h1);
+                    if (live && m < hl) hp[m] = h0;
+                    if (live && m + 1 < hl) hp[m + 1] = h1;
+                }
+                if (live) a.mask[((size_t)(n * 3 + l) * a.M + pc) * 4 + c] = bits;
+                __syncwarp();
+                if (c == 0) buf[r * FLD + hl] = 1.0;   // the ones row (the padded weights are zero beyond it)
+                __syncwarp();
+            }
+        }
+        // acc = z_n for the warp's paths: Euler-Maruyama update in the fragment layout; X_{n+1} goes to the tape and to the input rows
+        double zz = 0.0, zw = 0.0;
+        double *zp = a.Z + n * s_z + pc * d;
+        const double *xo = a.IN + n * s_in + pc * (d + 2);
+        double *xn = a.IN + (n + 1) * s_in + pc * (d + 2);
+#pragma unroll
+        for (int nt = 0; nt < FT; ++nt) {
+            const int m = 8 * nt + 2 * c;
+            double x0 = 0.0, x1 = 0.0;
+            if (m < d) {
+                double n0, n1;
+                normals2(seed, a.path0 + (uint32_t)path, m, (uint32_t)n, n0, n1);
+                const double dw0 = sq * n0, dw1 = sq * n1, z0 = acc[nt][0], z1 = m + 1 < d ? acc[nt][1] : 0.0;
+                zz = fma(z0, z0, zz); zw = fma(z0, dw0, zw);
+                x0 = xo[m] + a.s * dw0;
+                if (live) { zp[m] = 2.0 * a.lam * z0 * a.dt + dw0; xn[m] = x0; }   // zp: d(u_T)/d(z_n) up to the factor ubar
+                if (m + 1 < d) {
+                    zz = fma(z1, z1, zz); zw = fma(z1, dw1, zw);
+                    x1 = xo[m + 1] + a.s * dw1;
+                    if (live) { zp[m + 1] = 2.0 * a.lam * z1 * a.dt + dw1; xn[m + 1] = x1; }
+                }
+            }
+            *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(x0, x1);
+            if (n == a.N - 1) nn = fma(x0, x0, fma(x1, x1, nn));
+        }
+        zz += __shfl_xor_sync(0xffffffffu, zz, 1); zw += __shfl_xor_sync(0xffffffffu, zw, 1);
+        zz += __shfl_xor_sync(0xffffffffu, zz, 2); zw += __shfl_xor_sync(0xffffffffu, zw, 2);
+        u += a.lam * zz * a.dt + zw;
+    }
+    nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+    nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+    if (live && c == 0) {
+        const double res = log(a.ga + a.gb * nn) - u;
+        a.u[path] = u;
+        a.r2[path] = res * res;
+        a.ubar[path] = -2.0 * res * a.inv_total;
+    }
+}
+
+// cotangents: a warp takes one (step, 8-path tile) at a time: zbar = ubar G -> hidden 3 -> hidden 2 -> hidden 1; persistent CTAs walk
+// the task groups (the slab stream just keeps repeating)
+__global__ void __launch_bounds__(32 * FWPC, 3) k_fused_backward(const FusedArgs a)
+{
+    extern __shared__ __align__(16) double fsm[];
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+    const int tiles = (a.M + 7) / 8;
+    const long tasks = (long)tiles * a.N, groups = (tasks + nwarps - 1) / nwarps;
+    const long my_groups = groups > blockIdx.x ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    SlabRing ring;
+    fused_setup(fsm, nwarps, ring, a.slabs + (size_t)a.n_f * FSLAB, a.n_b, (long)a.n_b * my_groups);
+    double *buf = fsm + FRING * FSLAB + (size_t)warp * 8 * FLD;
+    const int d = a.d, hl = a.hl;
+    const size_t s_z = (size_t)d * a.M, s_c = (size_t)hl * a.M;
+    for (long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const long task = g * nwarps + warp;
+        const bool task_live = task < tasks;
+        const int n = (int)((task_live ? task : tasks - 1) / tiles), p0 = (int)((task_live ? task : tasks - 1) % tiles) * 8;
+        const int path = p0 + r;
+        const bool live = task_live && path < a.M;
+        const size_t pc = (size_t)(path < a.M ? path : a.M - 1);
+        const double ub = a.ubar[pc];
+        const double *gp = a.Z + n * s_z + pc * d;
+        double *zb = a.Zb + n * s_z + pc * d;
+        uint32_t bits[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) bits[l] = a.mask[((size_t)(n * 3 + l) * a.M + pc) * 4 + c];
+#pragma unroll
+        for (int nt = 0; nt < FT; ++nt) {
+            const int m = 8 * nt + 2 * c;
+            double b0 = 0.0, b1 = 0.0;
+            if (m < d) {
+                b0 = ub * gp[m];
+                if (live) zb[m] = b0;
+                if (m + 1 < d) {
+                    b1 = ub * gp[m + 1];
+                    if (live) zb[m + 1] = b1;
+                }
+            }
+            *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(b0, b1);
+        }
+        __syncwarp();
+        double acc[FT][2], bv[FT];
+        slab_first(ring, r, c, bv);
+#pragma unroll 1
+        for (int i = 0; i < a.n_b; ++i) {
+            const int l = a.b_layer[i];
+            if (a.b_k0[i] == 0) {
+#pragma unroll
+                for (int nt = 0; nt < FT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+            }
+            slab_mma(buf, ring, i + 1 < a.n_b, a.b_k0[i], r, c, acc, bv);
+            ring.advance();
+            __syncthreads();
+            if (threadIdx.x == 0) ring.issue();
+            if (!a.b_last[i]) continue;
+            const uint32_t mb = l == 3 ? bits[2] : (l == 2 ? bits[1] : bits[0]);
+            double *cp = a.C[l - 1] + n * s_c + pc * hl;
+#pragma unroll
+            for (int nt = 0; nt < FT; ++nt) {
+                const int m = 8 * nt + 2 * c;
+                const double c0 = (m < hl && !((mb >> (2 * nt)) & 1u)) ? acc[nt][0] : 0.0;
+                const double c1 = (m + 1 < hl && !((mb >> (2 * nt + 1)) & 1u)) ? acc[nt][1] : 0.0;
+                if (live && m < hl) cp[m] = c0;
+                if (live && m + 1 < hl) cp[m + 1] = c1;
+                *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(c0, c1);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// zero-padded operand slabs of the sigmaT_grad_u network (blockIdx.y = slab, one thread per element).  Forward operand of layer l: row k
+// holds [W_l | b_l][m][k] (k < in + 1, m < out); backward operand: row i holds W_l[i][j] (i < out, j < in).
+struct PackArgs {
+    size_t w_off[4];
+    int nin[4], nout[4];
+};
+__global__ void k_pack_slabs(const double *__restrict__ theta, double *dst, const FusedArgs a, const PackArgs q)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, sl = blockIdx.y;
+    if (i >= FSLAB) return;
+    const bool backward = sl >= a.n_f;
+    const int l = backward ? a.b_layer[sl - a.n_f] : a.f_layer[sl], k0 = backward ? a.b_k0[sl - a.n_f] : a.f_k0[sl];
+    const int k = k0 + i / FLD, m = i % FLD, nin = q.nin[l], nout = q.nout[l];
+    double v = 0.0;
+    if (!backward) { if (k < nin + 1 && m < nout) v = theta[q.w_off[l] + (size_t)k * nout + m]; }
+    else           { if (k < nout && m < nin) v = theta[q.w_off[l] + (size_t)m * nout + k]; }
+    dst[(size_t)sl * FSLAB + i] = v;
+}
+
 inline cublasStatus_t gemm(cublasHandle_t h, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k, const float *al, const float *A, int lda,
                            const float *B, int ldb, const float *be, float *C, int ldc)
 {
@@ -279,6 +626,11 @@ struct b200ude_bsde_handle {
     //   C[k] [n_steps][hls][cap] = cotangents of hidden k
     void *IN = nullptr, *u = nullptr, *H[3] = {}, *Z = nullptr, *Zb = nullptr, *C[3] = {}, *r2 = nullptr, *ubar = nullptr, *ones = nullptr;
     int init_M = 0;   // the constant rows are laid out for this many paths
+    bool fused = false;       // fp64, widths <= 112: the fused DMMA sweeps instead of per-layer library GEMMs
+    void *packed = nullptr;   // zero-padded operand copies of the z network for the fused sweeps
+    void *mask = nullptr;     // relu' bits of the hidden layers (fused sweeps)
+    FusedArgs fa;             // slab tables (the pointers are filled per call)
+    int sm_count = 148;
     void *hu[3] = {}, *cu_[3] = {};   // u0 net (single column): activations / cotangents
     void *scal = nullptr;             // [0] loss, [1] sum ubar, [2] u0(x0)
     int *t_dev = nullptr;
@@ -350,6 +702,35 @@ int32_t net_backward(b200ude_bsde_handle *h, const Net &n, const R *in, R *const
     return B200UDE_OK;
 }
 
+inline size_t fused_smem(int warps) { return ((size_t)FRING * FSLAB + (size_t)warps * 8 * FLD) * sizeof(double) + 8 * FRING + sizeof(SlabProducer); }
+
+// the fused fp64 path of one iteration: operand slabs, forward sweep (+ residual), loss sums, cotangent sweep
+int32_t fused_sweeps(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_total, cudaStream_t st)
+{
+    const Net &nz = h->nz;
+    double *pk = (double *)h->packed;
+    FusedArgs a = h->fa;
+    PackArgs q;
+    for (int l = 0; l < 4; ++l) { q.w_off[l] = nz.w_off[l]; q.nin[l] = nz.widths[l]; q.nout[l] = nz.widths[l + 1]; }
+    k_pack_slabs<<<dim3(blocks((size_t)FSLAB), a.n_f + a.n_b), 256, 0, st>>>((const double *)h->theta, pk, a, q);
+    a.slabs = pk;
+    a.IN = (double *)h->IN; a.Z = (double *)h->Z; a.Zb = (double *)h->Zb; a.u = (double *)h->u; a.r2 = (double *)h->r2; a.ubar = (double *)h->ubar;
+    for (int k = 0; k < 3; ++k) { a.H[k] = (double *)h->H[k]; a.C[k] = (double *)h->C[k]; }
+    a.x0 = (const double *)h->x0; a.u0 = (const double *)h->scal + 2; a.seed = h->seed_dev; a.path0 = path0;
+    a.M = M; a.N = h->desc.n_steps; a.d = h->d; a.hl = h->hls;
+    a.dt = h->desc.T / h->desc.n_steps; a.lam = h->desc.lambda; a.s = h->desc.sigma; a.ga = h->desc.g_a; a.gb = h->desc.g_b; a.inv_total = inv_total;
+    a.mask = (uint32_t *)h->mask;
+    const int tiles = (M + 7) / 8;
+    const size_t smem = fused_smem(FWPC);
+    k_fused_forward<<<(tiles + FWPC - 1) / FWPC, 32 * FWPC, smem, st>>>(a);
+    k_sum2<double><<<1, 256, 0, st>>>((const double *)h->r2, (const double *)h->ubar, M, inv_total, (double *)h->scal, (double *)h->scal + 1);
+    const long groups = ((long)tiles * a.N + FWPC - 1) / FWPC;
+    const long slots = 3L * h->sm_count;
+    k_fused_backward<<<(unsigned)(groups < slots ? groups : slots), 32 * FWPC, smem, st>>>(a);
+    BS_CUDA(h, cudaGetLastError());
+    return B200UDE_OK;
+}
+
 // one NNPDENS iteration: loss -> scal[0], u0(x0) -> scal[2], gradient -> grad
 template <class R>
 int32_t loss_gradient(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_total, cudaStream_t st)
@@ -367,32 +748,39 @@ int32_t loss_gradient(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_
     BS_CUDA(h, cudaMemsetAsync(h->grad, 0, sizeof(R) * h->nu.P, st));   // the u0 net's gradients accumulate; the z net's are written
     int32_t rc = net_forward<R>(h, h->nu, (const R *)h->x0, outs_u, 1, st);   // u0(x0)
     if (rc) return rc;
-    k_init_paths<R><<<blocks((size_t)d * M), 256, 0, st>>>(IN, u, (const R *)h->x0, scal + 2, d, M);
-    for (int n = 0; n < N; ++n) {
-        // layer l: [W | b] (out x (in + 1), theta's own layout) times the ones-augmented activations
-        const R *a = IN + n * s_in;
-        int ka = d + 2;
-        for (int l = 0; l < 3; ++l) {
-            R *o = H[l] + n * s_h;
-            BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, hl, M, ka, &one, th + nz.w_off[l], hl, a, ka, &zero, o, hl + 1));
-            k_relu<R><<<blocks((size_t)hl * M), 256, 0, st>>>(o, hl, hl + 1, M);
-            a = o; ka = hl + 1;
+    bool fused = false;
+    if constexpr (sizeof(R) == 8) fused = h->fused;
+    if (fused) {
+        rc = fused_sweeps(h, M, path0, inv_total, st);
+        if (rc) return rc;
+    } else {
+        k_init_paths<R><<<blocks((size_t)d * M), 256, 0, st>>>(IN, u, (const R *)h->x0, scal + 2, d, M);
+        for (int n = 0; n < N; ++n) {
+            // layer l: [W | b] (out x (in + 1), theta's own layout) times the ones-augmented activations
+            const R *a = IN + n * s_in;
+            int ka = d + 2;
+            for (int l = 0; l < 3; ++l) {
+                R *o = H[l] + n * s_h;
+                BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, hl, M, ka, &one, th + nz.w_off[l], hl, a, ka, &zero, o, hl + 1));
+                k_relu<R><<<blocks((size_t)hl * M), 256, 0, st>>>(o, hl, hl + 1, M);
+                a = o; ka = hl + 1;
+            }
+            BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, d, M, ka, &one, th + nz.w_off[3], d, a, ka, &zero, Z + n * s_z, d));
+            k_em_step<R><<<blocks((size_t)M * 32, 256), 256, 0, st>>>(IN + n * s_in, IN + (n + 1) * s_in, u, Z + n * s_z, h->seed_dev, path0, n, d, M, dt, lam, s);
         }
-        BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, d, M, ka, &one, th + nz.w_off[3], d, a, ka, &zero, Z + n * s_z, d));
-        k_em_step<R><<<blocks((size_t)M * 32, 256), 256, 0, st>>>(IN + n * s_in, IN + (n + 1) * s_in, u, Z + n * s_z, h->seed_dev, path0, n, d, M, dt, lam, s);
-    }
-    k_residual<R><<<blocks((size_t)M * 32, 256), 256, 0, st>>>(IN + N * s_in, u, (R *)h->r2, (R *)h->ubar, d, M, h->desc.g_a, h->desc.g_b, inv_total);
-    k_sum2<R><<<1, 256, 0, st>>>((const R *)h->r2, (const R *)h->ubar, M, inv_total, scal, scal + 1);
-    // cotangents, step by step (the steps only couple through ubar, which is the same for all of them: any order works)
-    for (int n = 0; n < N; ++n) {
-        k_zbar<R><<<blocks((size_t)((d + 3) / 4) * M), 256, 0, st>>>(Zb + n * s_z, Z + n * s_z, (const R *)h->ubar, h->seed_dev, path0, n, d, M, dt, lam);
-        const R *c = Zb + n * s_z;
-        int nc = d;
-        for (int l = 3; l >= 1; --l) {   // cot of hidden l = W_{l+1}^T cot_{l+1}, masked by relu'
-            R *o = C[l - 1] + n * s_c;
-            BS_BLAS(h, gemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, hl, M, nc, &one, th + nz.w_off[l], nc, c, nc, &zero, o, hl));
-            k_relu_mask<R><<<blocks((size_t)hl * M), 256, 0, st>>>(o, H[l - 1] + n * s_h, hl, hl + 1, M);
-            c = o; nc = hl;
+        k_residual<R><<<blocks((size_t)M * 32, 256), 256, 0, st>>>(IN + N * s_in, u, (R *)h->r2, (R *)h->ubar, d, M, h->desc.g_a, h->desc.g_b, inv_total);
+        k_sum2<R><<<1, 256, 0, st>>>((const R *)h->r2, (const R *)h->ubar, M, inv_total, scal, scal + 1);
+        // cotangents, step by step (the steps only couple through ubar, which is the same for all of them: any order works)
+        for (int n = 0; n < N; ++n) {
+            k_zbar<R><<<blocks((size_t)((d + 3) / 4) * M), 256, 0, st>>>(Zb + n * s_z, Z + n * s_z, (const R *)h->ubar, h->seed_dev, path0, n, d, M, dt, lam);
+            const R *c = Zb + n * s_z;
+            int nc = d;
+            for (int l = 3; l >= 1; --l) {   // cot of hidden l = W_{l+1}^T cot_{l+1}, masked by relu'
+                R *o = C[l - 1] + n * s_c;
+                BS_BLAS(h, gemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, hl, M, nc, &one, th + nz.w_off[l], nc, c, nc, &zero, o, hl));
+                k_relu_mask<R><<<blocks((size_t)hl * M), 256, 0, st>>>(o, H[l - 1] + n * s_h, hl, hl + 1, M);
+                c = o; nc = hl;
+            }
         }
     }
     // [dW | db] of every layer in one GEMM over all steps: cot [out x (N M)] times augmented activation^T [(N M) x (in + 1)]
@@ -527,6 +915,34 @@ int32_t b200ude_bsde_create(const b200ude_bsde_desc *d, b200ude_bsde_handle **ou
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess && cublasCreate(&h->blas) == CUBLAS_STATUS_SUCCESS &&
               cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
     int32_t rc = ok ? (h->f64 ? alloc_all<double>(h) : alloc_all<float>(h)) : B200UDE_ENOMEM;
+    const char *fenv = getenv("B200UDE_BSDE_FUSED");
+    if (rc == B200UDE_OK && h->f64 && d->dim <= FW - 2 && d->hidden <= FW - 1 && !(fenv && fenv[0] == '0')) {
+        FusedArgs &fa = h->fa;
+        memset(&fa, 0, sizeof(fa));
+        for (int l = 0; l < 4; ++l)   // forward: contraction over in_l + 1 rows
+            for (int k0 = 0; k0 < h->nz.widths[l] + 1; k0 += FSR) {
+                const int rows = h->nz.widths[l] + 1 - k0 < FSR ? h->nz.widths[l] + 1 - k0 : FSR;
+                const int i = fa.n_f++;
+                fa.f_layer[i] = (unsigned char)l; fa.f_k0[i] = (unsigned char)k0; fa.f_ks[i] = (unsigned char)((rows + 3) / 4);
+                fa.f_last[i] = (unsigned char)(k0 + FSR >= h->nz.widths[l] + 1);
+            }
+        for (int l = 3; l >= 1; --l)  // backward: contraction over out_l rows
+            for (int k0 = 0; k0 < h->nz.widths[l + 1]; k0 += FSR) {
+                const int rows = h->nz.widths[l + 1] - k0 < FSR ? h->nz.widths[l + 1] - k0 : FSR;
+                const int i = fa.n_b++;
+                fa.b_layer[i] = (unsigned char)l; fa.b_k0[i] = (unsigned char)k0; fa.b_ks[i] = (unsigned char)((rows + 3) / 4);
+                fa.b_last[i] = (unsigned char)(k0 + FSR >= h->nz.widths[l + 1]);
+            }
+        h->sm_count = prop.multiProcessorCount;
+        const int smem = (int)fused_smem(FWPC);
+        if (cudaMalloc(&h->packed, (size_t)(fa.n_f + fa.n_b) * FSLAB * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->mask, (size_t)d->n_steps * 3 * d->max_paths * 4 * sizeof(uint32_t)) == cudaSuccess &&
+            cudaFuncSetAttribute(k_fused_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+            cudaFuncSetAttribute(k_fused_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess)
+            h->fused = true;
+        else
+            rc = B200UDE_ENOMEM;
+    }
     if (rc == B200UDE_OK) {
         ok = cublasSetStream(h->blas, h->stream) == CUBLAS_STATUS_SUCCESS && cublasSetWorkspace(h->blas, h->workspace, 32u << 20) == CUBLAS_STATUS_SUCCESS &&
              cublasSetPointerMode(h->blas, CUBLAS_POINTER_MODE_HOST) == CUBLAS_STATUS_SUCCESS &&
@@ -550,7 +966,7 @@ void b200ude_bsde_destroy(b200ude_bsde_handle *h)
 {
     if (!h) return;
     void *bufs[] = {h->theta, h->grad, h->adam_m, h->adam_v, h->x0, h->IN, h->u, h->H[0], h->H[1], h->H[2], h->Z, h->Zb, h->C[0], h->C[1], h->C[2],
-                    h->r2, h->ubar, h->ones, h->hu[0], h->hu[1], h->cu_[0], h->cu_[1], h->scal, h->t_dev, h->seed_dev, h->workspace};
+                    h->r2, h->ubar, h->ones, h->hu[0], h->hu[1], h->cu_[0], h->cu_[1], h->scal, h->t_dev, h->seed_dev, h->workspace, h->packed, h->mask};
     for (void *b : bufs) cudaFree(b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
