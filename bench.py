@@ -403,7 +403,17 @@ def main_hjb(a):
         return
     fl = hjb_flops(d, hls, n_steps) * m
     ms_iter = total_ms / a.steps
-    ach = fl / (ms_iter * 1e-3) / 1e12
+    # dominant kernel: the fused forward sweep (csrc/bsde.cu::k_fused_forward); its time from CUDA events on the handle's stream,
+    # averaged over eager (non-graph) iterations of the same workload
+    sweeps = []
+    for i in range(5):
+        s.loss_gradient(m, 50 + i)
+        sweeps.append(s.last_sweep_ms())
+    fwd_ms, bwd_ms, wg_ms = (float(np.mean([x[k] for x in sweeps])) for k in range(3))
+    mac_f = (d + 2) * hls + 2 * (hls + 1) * hls + (hls + 1) * d          # [W | b] times the ones-augmented activations
+    fwd_flops = 2.0 * n_steps * mac_f * m
+    ach = fwd_flops / (fwd_ms * 1e-3) / 1e12
+    dmma_peak = 36.5   # TFLOP/s, mma.sync.m8n8k4.f64 issue-rate microbenchmark on this GPU model (profiles/r02_dmma_microbench.txt)
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         from oracle import bsde_oracle as bo
@@ -422,13 +432,18 @@ def main_hjb(a):
                    "allreduce": "none (1 GPU)" if world == 1 else "NCCL all-reduce of [grad; loss] per iteration"},
         "e2e": {"value": world * m * e2e_steps / e2e_s, "unit": unit, "h2d_bytes_per_step": 8 * s.P, "d2h_bytes_per_step": 8 * (s.P + 2), "steps": e2e_steps,
                 "note": "b200ude_bsde_set_params(host theta) + b200ude_bsde_loss_gradient(host loss / grad / u0), wall clock"},
-        "gpu_launches": (len(names) if names else 0) * a.steps, "kernels_per_step": sorted(set(names)) if names else None, "kernels_source": names_src,
+        "gpu_launches": (sum(1 for k in names if "::k_" in k) if names else 0) * a.steps,
+        "library_launches": (sum(1 for k in names if "::k_" not in k) if names else 0) * a.steps,
+        "kernels_per_step": sorted(set(names)) if names else None, "kernels_source": names_src,
         "clocks": clk.summary(),
-        "roofline": {"kernel": "the cuBLAS fp64 GEMMs of the sigmaT_grad_u network (library) -- the custom kernels between them are HBM-trivial", "bound": "tensor",
-                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
-                     "peak_source": "torch.matmul fp64 4096^3, best of 5, measured in this run (no fp64 entry in MEASURED_PEAKS.json)",
-                     "flop_per_path_iteration": hjb_flops(d, hls, n_steps),
-                     "note": "whole-iteration time against GEMM flops: the fraction also carries the element-wise kernels and launch gaps between the 110-wide GEMMs"},
+        "roofline": {"kernel": "k_fused_forward (fused DMMA forward sweep: 4 layers x 20 steps + Euler-Maruyama, csrc/bsde.cu)", "bound": "tensor",
+                     "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak, "traffic": None,
+                     "peak_source": "fp64 tensor pipe: DMMA.8x8x4 issue-rate microbenchmark (tools/microbench/dmma.cu, profiles/r02_dmma_microbench.txt); "
+                                    f"torch.matmul fp64 4096^3 in this run: {peak:.1f} TFLOP/s",
+                     "algorithmic_flop_per_path_step": 2.0 * mac_f, "kernel_ms": fwd_ms,
+                     "note": "share of the iteration: forward sweep / cotangent sweep / batched weight-gradient GEMMs (cuBLAS) in kernel_ms"},
+        "kernel_ms": {"forward_sweep": fwd_ms, "cotangent_sweep": bwd_ms, "weight_gradient_gemms": wg_ms, "iteration": ms_iter},
+        "iteration_gemm_tflops": fl / (ms_iter * 1e-3) / 1e12,
         "cpu_baseline": cpu,
     }))
     if world > 1:

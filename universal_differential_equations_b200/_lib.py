@@ -31,7 +31,7 @@ EXPORTS = [
     "b200ude_loss_gradient_host", "b200ude_get_params", "b200ude_adam_reset", "b200ude_adam_step", "b200ude_train_adam",
     "b200ude_peer_export", "b200ude_peer_attach", "b200ude_peer_detach", "b200ude_adjoint_l2_allreduce", "b200ude_selftest_tanh",
     "b200ude_bsde_create", "b200ude_bsde_destroy", "b200ude_bsde_last_error", "b200ude_bsde_num_params", "b200ude_bsde_set_params",
-    "b200ude_bsde_get_params", "b200ude_bsde_loss_gradient", "b200ude_bsde_train_adam", "b200ude_bsde_adam_step", "b200ude_bsde_last_train_ms",
+    "b200ude_bsde_get_params", "b200ude_bsde_loss_gradient", "b200ude_bsde_train_adam", "b200ude_bsde_adam_step", "b200ude_bsde_last_train_ms", "b200ude_bsde_last_sweep_ms",
 ]
 PEER_HANDLE_BYTES = 64
 
@@ -157,6 +157,8 @@ def lib():
     L.b200ude_bsde_train_adam.argtypes = [vp, C.POINTER(Adam), sz, i32, u64, vp, vp]
     L.b200ude_bsde_last_train_ms.restype = C.c_double
     L.b200ude_bsde_last_train_ms.argtypes = [vp]
+    L.b200ude_bsde_last_sweep_ms.restype = i32
+    L.b200ude_bsde_last_sweep_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.b200ude_bsde_adam_step.restype = i32
     L.b200ude_bsde_adam_step.argtypes = [vp, C.POINTER(Adam), vp]
     if L.b200ude_version() != ABI_VERSION:

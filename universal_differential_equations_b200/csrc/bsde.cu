@@ -639,6 +639,8 @@ struct b200ude_bsde_handle {
     bool have_theta = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.0f;
+    cudaEvent_t kev[5] = {};   // around the sweeps of an eager b200ude_bsde_loss_gradient call: start, forward, loss sums, backward, weight gradients
+    bool time_kernels = false;
     std::vector<double> x0_host;
     std::string err;
 };
@@ -722,11 +724,15 @@ int32_t fused_sweeps(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_t
     a.mask = (uint32_t *)h->mask;
     const int tiles = (M + 7) / 8;
     const size_t smem = fused_smem(FWPC);
+    if (h->time_kernels) cudaEventRecord(h->kev[0], st);
     k_fused_forward<<<(tiles + FWPC - 1) / FWPC, 32 * FWPC, smem, st>>>(a);
+    if (h->time_kernels) cudaEventRecord(h->kev[1], st);
     k_sum2<double><<<1, 256, 0, st>>>((const double *)h->r2, (const double *)h->ubar, M, inv_total, (double *)h->scal, (double *)h->scal + 1);
+    if (h->time_kernels) cudaEventRecord(h->kev[2], st);
     const long groups = ((long)tiles * a.N + FWPC - 1) / FWPC;
     const long slots = 3L * h->sm_count;
     k_fused_backward<<<(unsigned)(groups < slots ? groups : slots), 32 * FWPC, smem, st>>>(a);
+    if (h->time_kernels) cudaEventRecord(h->kev[3], st);
     BS_CUDA(h, cudaGetLastError());
     return B200UDE_OK;
 }
@@ -790,6 +796,7 @@ int32_t loss_gradient(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_
     BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[1], hl, H[0], hl + 1, &zero, g + nz.w_off[1], hl));
     BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[2], hl, H[1], hl + 1, &zero, g + nz.w_off[2], hl));
     BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, d, hl + 1, K, &one, Zb, d, H[2], hl + 1, &zero, g + nz.w_off[3], d));
+    if (h->time_kernels) cudaEventRecord(h->kev[4], st);
     rc = net_backward<R>(h, h->nu, (const R *)h->x0, outs_u, cots_u, 1, st);   // cotangent of u0(x0) = sum of ubar (already in scal[1])
     if (rc) return rc;
     BS_CUDA(h, cudaGetLastError());
@@ -914,6 +921,7 @@ int32_t b200ude_bsde_create(const b200ude_bsde_desc *d, b200ude_bsde_handle **ou
     h->desc.x0 = nullptr;   // the caller's array is not kept
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess && cublasCreate(&h->blas) == CUBLAS_STATUS_SUCCESS &&
               cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
+    for (int i = 0; ok && i < 5; ++i) ok = cudaEventCreate(&h->kev[i]) == cudaSuccess;
     int32_t rc = ok ? (h->f64 ? alloc_all<double>(h) : alloc_all<float>(h)) : B200UDE_ENOMEM;
     const char *fenv = getenv("B200UDE_BSDE_FUSED");
     if (rc == B200UDE_OK && h->f64 && d->dim <= FW - 2 && d->hidden <= FW - 1 && !(fenv && fenv[0] == '0')) {
@@ -968,6 +976,8 @@ void b200ude_bsde_destroy(b200ude_bsde_handle *h)
     void *bufs[] = {h->theta, h->grad, h->adam_m, h->adam_v, h->x0, h->IN, h->u, h->H[0], h->H[1], h->H[2], h->Z, h->Zb, h->C[0], h->C[1], h->C[2],
                     h->r2, h->ubar, h->ones, h->hu[0], h->hu[1], h->cu_[0], h->cu_[1], h->scal, h->t_dev, h->seed_dev, h->workspace, h->packed, h->mask};
     for (void *b : bufs) cudaFree(b);
+    for (cudaEvent_t e : h->kev)
+        if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->blas) cublasDestroy(h->blas);
@@ -977,6 +987,21 @@ void b200ude_bsde_destroy(b200ude_bsde_handle *h)
 
 size_t b200ude_bsde_num_params(const b200ude_bsde_handle *h) { return h ? (size_t)h->P : 0; }
 double b200ude_bsde_last_train_ms(const b200ude_bsde_handle *h) { return h ? (double)h->last_ms : 0.0; }
+int32_t b200ude_bsde_last_sweep_ms(b200ude_bsde_handle *h, double *ms)
+{
+    if (!h || !ms) return B200UDE_EINVAL;
+    if (!h->fused) return bfail(h, B200UDE_EUNSUPPORTED, "bsde_last_sweep_ms: the handle runs on library GEMMs (fp32, or widths above 112)");
+    const int pairs[3][2] = {{0, 1}, {2, 3}, {3, 4}};
+    for (int i = 0; i < 3; ++i) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, h->kev[pairs[i][0]], h->kev[pairs[i][1]]) != cudaSuccess) {
+            cudaGetLastError();
+            return bfail(h, B200UDE_ESTATE, "bsde_last_sweep_ms: no completed b200ude_bsde_loss_gradient call yet");
+        }
+        ms[i] = t;
+    }
+    return B200UDE_OK;
+}
 
 int32_t b200ude_bsde_set_params(b200ude_bsde_handle *h, const void *theta, size_t P, int32_t mem)
 {
@@ -1013,10 +1038,12 @@ int32_t b200ude_bsde_loss_gradient(b200ude_bsde_handle *h, size_t n_paths, uint6
     const double inv_total = 1.0 / (double)(total_paths ? total_paths : n_paths);
     int32_t rc = h->f64 ? prepare<double>(h, (int)n_paths) : prepare<float>(h, (int)n_paths);
     if (rc) return rc;
+    h->time_kernels = h->fused;
     rc = h->f64 ? loss_gradient<double>(h, (int)n_paths, (uint32_t)path_offset, inv_total, h->stream)
                         : loss_gradient<float>(h, (int)n_paths, (uint32_t)path_offset, inv_total, h->stream);
     if (rc) return rc;
     const size_t es = h->f64 ? 8 : 4;
+    h->time_kernels = false;
     if (loss) BS_CUDA(h, cudaMemcpyAsync(loss, h->scal, es, cudaMemcpyDefault, h->stream));
     if (u0) BS_CUDA(h, cudaMemcpyAsync(u0, (char *)h->scal + 2 * es, es, cudaMemcpyDefault, h->stream));
     if (grad) BS_CUDA(h, cudaMemcpyAsync(grad, h->grad, es * (size_t)h->P, cudaMemcpyDefault, h->stream));

@@ -147,6 +147,12 @@ class BSDESolver:
     def last_train_ms(self) -> float:
         return float(self._L.b200ude_bsde_last_train_ms(self._h))
 
+    def last_sweep_ms(self):
+        """(forward sweep, cotangent sweep, weight-gradient GEMMs) device ms of the last loss_gradient call (fused fp64 handles)."""
+        ms = (C.c_double * 3)()
+        _lib.check_bsde(self._h, self._L.b200ude_bsde_last_sweep_ms(self._h, ms))
+        return tuple(ms)
+
     def _adam(self, opt):
         return _lib.Adam(struct_size=C.sizeof(_lib.Adam), eta=opt.eta, beta1=opt.beta[0], beta2=opt.beta[1], eps=opt.eps, loss_scale=1.0, l2_reg=0.0)
 
