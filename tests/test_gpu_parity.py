@@ -205,6 +205,21 @@ def test_lv32_host_buffer_entry_points(O):
     solver.close()
 
 
+def test_lv32_host_path_split_adjoint_is_bitwise_the_device_path():
+    """Host-buffer call on a large ensemble: the data upload and the adjoint run in two halves of the trajectories (sub-range
+    launches of the warp-collective adjoint); the partial rows, hence the sums, are those of the single launch."""
+    ude = _ude()
+    N = 20011
+    theta = glorot_theta((2, 32, 32, 2), seed=5)
+    u0, y = synthetic_ensemble(N)
+    solver = ude.UDESolver(_lv32(ude), 0.0, 0.1, 30, 1, max_trajectories=N)
+    _, loss, g, gu, _ = _run(solver, theta, u0, y)
+    gu_h = np.empty_like(u0)
+    l_h, g_h, _ = solver.loss_gradient_host(theta, u0, y, grad_u0=gu_h)
+    assert np.array_equal(g_h, g) and np.array_equal(gu_h, gu) and abs(l_h - loss) <= 1e-6 * abs(loss)
+    solver.close()
+
+
 def test_autograd_concrete_solve_matches_adjoint(O):
     """loss.backward() through concrete_solve(EnsembleProblem) == fused adjoint == oracle."""
     ude = _ude()

@@ -83,7 +83,7 @@ struct b200ude_handle {
     float *h_loss = nullptr;  // pinned
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-buffer path: the data upload overlaps the forward kernel
-    cudaEvent_t data_ready = nullptr;
+    cudaEvent_t data_ready = nullptr, data_ready2 = nullptr;
     RkcHost rkc;                    // solver = B200UDE_RKC2: recurrence tables for desc.n_stages
     // fused reduce + all-reduce over NVLink peer memory (b200ude_peer_*)
     void *d_peer_buf = nullptr;     // this rank's exchange buffer (cudaMalloc, exported with CUDA IPC)
@@ -288,8 +288,10 @@ int32_t do_forward(b200ude_handle *h, const float *u0, size_t N, float *out, int
     return B200UDE_OK;
 }
 
+// split: two events (data of the first / second half of the trajectories resident) for the host-buffer path: the warp-collective LV
+// adjoint then runs as two sub-range launches, the first one under the second half's upload
 int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, float *grad_theta,
-                   float *grad_u0, cudaStream_t st, bool peer = false)
+                   float *grad_u0, cudaStream_t st, bool peer = false, const cudaEvent_t *split = nullptr, size_t split_at = 0)
 {
     CUDA_TRY(h, cudaSetDevice(h->desc.device));
     if (peer && !h->peer_attached) return fail(h, B200UDE_ESTATE, "adjoint_l2_allreduce: b200ude_peer_attach has not been called");
@@ -304,6 +306,12 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     }
     if (!h->have_forward) return fail(h, B200UDE_ESTATE, "adjoint: no stored forward solution (call b200ude_forward first)");
     if (!cot || !grad_theta) return fail(h, B200UDE_EINVAL, "adjoint: null pointer");
+    const bool split_ok = split && h->kid == K_LV32 && !h->adaptive && h->desc.solver != B200UDE_RKC2 && !h->var.discrete &&
+                          use_wm(h->var.adj_wm, h->N, h->wm_adj_max) && split_at > 0 && split_at < h->N;
+    if (split && !split_ok) {   // every other kernel family reads the whole data array
+        CUDA_TRY(h, cudaStreamWaitEvent(st, split[0], 0));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, split[1], 0));
+    }
     AdjParams p;
     p.ustep = h->d_ustep; p.dense = h->d_dense; p.cot = cot; p.grad_u0 = grad_u0; p.partial = h->d_partial;
     p.theta = h->d_theta; p.N = (int)h->N; p.n_steps = h->desc.n_steps; p.save_every = h->desc.save_every; p.P = h->P;
@@ -332,8 +340,22 @@ int32_t do_adjoint(b200ude_handle *h, bool l2, const float *cot, float *loss, fl
     }
     switch (h->kid) {
     case K_LV32:
-        e = (!h->var.discrete && use_wm(h->var.adj_wm, h->N, h->wm_adj_max)) ? launch_adj_lv32_wm(h->var, h->tab, p, st, &grid)
-                                                                              : launch_adj_lv32(h->var, h->tab, p, st, &grid);
+        if (split_ok) {
+            int g0 = 0, g1 = 0;
+            AdjParams q = p;
+            q.n0 = 0; q.n_cnt = (int)split_at; q.row0 = 0;
+            CUDA_TRY(h, cudaStreamWaitEvent(st, split[0], 0));
+            e = launch_adj_lv32_wm(h->var, h->tab, q, st, &g0);
+            if (e == cudaSuccess) {
+                q.n0 = (int)split_at; q.n_cnt = (int)(h->N - split_at); q.row0 = g0;
+                CUDA_TRY(h, cudaStreamWaitEvent(st, split[1], 0));
+                e = launch_adj_lv32_wm(h->var, h->tab, q, st, &g1);
+            }
+            grid = g0 + g1;
+        } else {
+            e = (!h->var.discrete && use_wm(h->var.adj_wm, h->N, h->wm_adj_max)) ? launch_adj_lv32_wm(h->var, h->tab, p, st, &grid)
+                                                                                  : launch_adj_lv32(h->var, h->tab, p, st, &grid);
+        }
         break;
     case K_LV5P0: e = launch_adj_lv5(0, h->var, h->tab, p, st, &grid); break;
     case K_LV5P1: e = launch_adj_lv5(1, h->var, h->tab, p, st, &grid); break;
@@ -689,6 +711,7 @@ int32_t b200ude_create(const b200ude_desc *d, b200ude_handle **out)
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->data_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->data_ready2, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void **)&h->h_loss, sizeof(float)) != cudaSuccess) {
         g_create_error = "create: stream / pinned allocation failed";
         b200ude_destroy(h);
@@ -725,6 +748,7 @@ void b200ude_destroy(b200ude_handle *h)
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->data_ready) cudaEventDestroy(h->data_ready);
+    if (h->data_ready2) cudaEventDestroy(h->data_ready2);
     delete h;
 }
 
@@ -821,12 +845,20 @@ int32_t b200ude_loss_gradient_host(b200ude_handle *h, const void *theta, const v
     CUDA_TRY(h, cudaMemcpyAsync(h->d_u0, u0, sizeof(float) * D * N, cudaMemcpyHostToDevice, st));
     // the data (n_save x larger than u0) is only needed by the adjoint: upload it on a second stream while
     // the forward kernel runs (pinned host memory makes the two overlap)
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_data, data, sizeof(float) * (size_t)h->n_save * D * N, cudaMemcpyHostToDevice, h->copy_stream));
+    // ... in two halves of the trajectories (strided copies: the layout is trajectory-fastest), so that the adjoint of the first half
+    // can start under the second half's upload when the link is slower than the forward kernel
+    const size_t half = N >= 8192 ? ((N / 2 + 15) / 16) * 16 : N;
+    const size_t rows = (size_t)h->n_save * D;
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->d_data, sizeof(float) * N, data, sizeof(float) * N, sizeof(float) * half, rows, cudaMemcpyHostToDevice, h->copy_stream));
     CUDA_TRY(h, cudaEventRecord(h->data_ready, h->copy_stream));
+    if (half < N)
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->d_data + half, sizeof(float) * N, (const float *)data + half, sizeof(float) * N, sizeof(float) * (N - half), rows,
+                                      cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(h, cudaEventRecord(h->data_ready2, h->copy_stream));
     rc = do_forward(h, h->d_u0, N, h->d_out, nullptr, st);
     if (rc) return rc;
-    CUDA_TRY(h, cudaStreamWaitEvent(st, h->data_ready, 0));
-    rc = do_adjoint(h, true, h->d_data, h->d_loss, h->d_grad, grad_u0 ? h->d_gu0 : nullptr, st);
+    const cudaEvent_t ev[2] = {h->data_ready, h->data_ready2};
+    rc = do_adjoint(h, true, h->d_data, h->d_loss, h->d_grad, grad_u0 ? h->d_gu0 : nullptr, st, false, ev, half);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(grad_theta, h->d_grad, sizeof(float) * (size_t)h->P, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -53,7 +53,7 @@ static cudaError_t launch_adj(const ConstTables &t, const AdjParams &p, int *row
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int warps = (p.N + 8 * R - 1) / (8 * R);
+    const int warps = ((p.n_cnt ? p.n_cnt : p.N) + 8 * R - 1) / (8 * R);
     *rows_out = warps;
     kern<<<(warps + WPC - 1) / WPC, 32 * WPC, smem, st>>>(p, make_consts(t));
     return cudaGetLastError();
@@ -61,7 +61,7 @@ static cudaError_t launch_adj(const ConstTables &t, const AdjParams &p, int *row
 
 cudaError_t launch_adj_lv32_wm(const Variant &v, const ConstTables &t, const AdjParams &p, cudaStream_t st, int *rows_out)
 {
-    const int R = pick_rows(v, p.N);
+    const int R = pick_rows(v, p.N);   // by the whole ensemble, also for a sub-range launch (both halves use the same rows per warp)
     if (v.approx_tanh) return R == 1 ? launch_adj<1, 1>(t, p, rows_out, st) : launch_adj<1, 2>(t, p, rows_out, st);
     return R == 1 ? launch_adj<0, 1>(t, p, rows_out, st) : launch_adj<0, 2>(t, p, rows_out, st);
 }

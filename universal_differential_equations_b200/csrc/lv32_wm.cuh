@@ -411,8 +411,9 @@ __global__ void __launch_bounds__(32 * WPC, MINB) adjoint_kernel(AdjParams p, Co
 
     const size_t N = (size_t)p.N;
     const int wg = blockIdx.x * WPC + warp;
-    const long n = (long)wg * (8 * R) + L.fg + (R == 2 ? 8 * L.rsel : 0);
-    const bool live = n < (long)N && (R == 2 || L.rsel == 0);   // R = 1: lanes tig >= 2 shadow tig - 2 (weight 0, stores masked)
+    const long n_end = p.n_cnt ? (long)p.n0 + p.n_cnt : (long)N;
+    const long n = (long)p.n0 + (long)wg * (8 * R) + L.fg + (R == 2 ? 8 * L.rsel : 0);
+    const bool live = n < n_end && (R == 2 || L.rsel == 0);   // R = 1: lanes tig >= 2 shadow tig - 2 (weight 0, stores masked)
     const size_t idx = (size_t)L.comp * N + (size_t)(n < (long)N ? n : (long)N - 1);
     const float lv = live ? 1.0f : 0.0f;
     const float pc = L.comp ? -cs.p4 : cs.p1;
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) adjoint_kernel(AdjParams p, Co
     };
 #pragma unroll
     for (int q = 0; q < 4; ++q) { red_fg(gW3a[q]); red_fg(gW3b[q]); red_fg(gB2[q]); red_fg(gB1[q]); red_fg(gW1a[q]); red_fg(gW1b[q]); }
-    float *dst = p.partial + (size_t)wg * (P + 1);
+    float *dst = p.partial + (size_t)(p.row0 + wg) * (P + 1);
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll

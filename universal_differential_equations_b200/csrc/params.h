@@ -28,6 +28,9 @@ struct AdjParams {
     int N, n_steps, save_every, P;
     int fused_l2;         // 1: cot is the data, form 2 w (u - data) and the loss in-kernel
     float dt;
+    // sub-range launches (warp-collective LV kernels only): trajectories [n0, n0 + n_cnt) of the N, partial rows from row0
+    // (n_cnt = 0: all N).  Lets the host-buffer path start the adjoint of the first half while the second half's data still uploads.
+    int n0 = 0, n_cnt = 0, row0 = 0;
 };
 
 // per-handle tables every launch pushes into the launching translation unit's constant bank
