@@ -38,11 +38,11 @@ def philox4x32(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def normals(seed, step, n_paths, d):
-    """dW / sqrt(dt): standard normals [d, n_paths]; component block q = 4 consecutive components from one Philox call with
-    counter (path, q, step, 0) and key (seed low, seed high); Box-Muller on (x + 0.5) 2^-32."""
+def normals(seed, step, n_paths, d, path0=0):
+    """dW / sqrt(dt): standard normals [d, n_paths] of paths path0 .. path0 + n_paths - 1; component block q = 4 consecutive
+    components from one Philox call with counter (path, q, step, 0) and key (seed low, seed high); Box-Muller on (x + 0.5) 2^-32."""
     nq = (d + 3) // 4
-    path = np.arange(n_paths, dtype=np.uint64)[None, :].repeat(nq, 0)
+    path = (np.arange(n_paths, dtype=np.uint64) + np.uint64(path0))[None, :].repeat(nq, 0)
     q = np.arange(nq, dtype=np.uint64)[:, None].repeat(n_paths, 1)
     r = philox4x32(path, q, np.full_like(path, step), np.zeros_like(path), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     u = [(x.astype(np.float64) + 0.5) * 2.0 ** -32 for x in r]
@@ -96,8 +96,11 @@ def mlp_bwd(layers, acts, cot):
     return np.concatenate(grads), cot
 
 
-def loss_and_grad(theta, d, hls, x0, T, n_steps, n_paths, seed, lam=1.0, s=np.sqrt(2.0), a=0.5, b=0.5):
-    """One NNPDENS iteration: loss = mean (g(X_T) - u_T)^2 and its gradient w.r.t. theta = [theta_u0; theta_z]."""
+def loss_and_grad(theta, d, hls, x0, T, n_steps, n_paths, seed, lam=1.0, s=np.sqrt(2.0), a=0.5, b=0.5, path0=0, n_total=None):
+    """One NNPDENS iteration: loss = mean (g(X_T) - u_T)^2 and its gradient w.r.t. theta = [theta_u0; theta_z].
+    path0 / n_total: this call evaluates the shard path0 .. path0 + n_paths - 1 of n_total paths (the mean's denominator), so that the
+    shards of a multi-GPU job add up to the whole batch."""
+    n_total = n_total or n_paths
     pu, pz = num_params(d, hls)
     Lu = unpack(theta[:pu], (d, hls, hls, 1))
     Lz = unpack(theta[pu:], (d + 1, hls, hls, hls, d))
@@ -109,14 +112,14 @@ def loss_and_grad(theta, d, hls, x0, T, n_steps, n_paths, seed, lam=1.0, s=np.sq
     for n in range(n_steps):
         acts = mlp_fwd(Lz, np.vstack([X, np.full((1, n_paths), n * dt)]))
         z = acts[-1]
-        dW = np.sqrt(dt) * normals(seed, n, n_paths, d)
+        dW = np.sqrt(dt) * normals(seed, n, n_paths, d, path0)
         steps.append((acts, dW))
         u = u + lam * (z * z).sum(0) * dt + (z * dW).sum(0)
         X = X + s * dW
     nrm = a + b * (X * X).sum(0)
     r = np.log(nrm) - u
-    loss = (r * r).mean()
-    ubar = -2.0 * r / n_paths
+    loss = (r * r).sum() / n_total
+    ubar = -2.0 * r / n_total
     gz = np.zeros(pz)
     for n in range(n_steps - 1, -1, -1):
         acts, dW = steps[n]

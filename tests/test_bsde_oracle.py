@@ -62,3 +62,52 @@ def test_reference_acceptance_criterion_small_dimension():
     ref = bo.analytic_hjb(x0, 1.0, n_mc=200000)
     assert abs(ans - ref) / abs(ans) < 0.2, (ans, ref)
     assert losses[-20:].mean() < 0.2 * losses[:5].mean()
+
+
+def _golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "hjb_small.npz"))
+
+
+def test_oracle_reproduces_its_frozen_vectors():
+    g = _golden()
+    d, hls, M, N = int(g["d"]), int(g["hls"]), int(g["M"]), int(g["N"])
+    np.testing.assert_allclose(bo.normals(int(g["seed"]), 3, 8, d), g["normals_step3"], rtol=0, atol=1e-15)
+    l, gr, u0 = bo.loss_and_grad(g["theta"], d, hls, g["x0"], 1.0, N, M, int(g["seed"]))
+    assert abs(l - float(g["loss"])) <= 1e-13 * abs(l) and abs(u0 - float(g["u0"])) <= 1e-13
+    np.testing.assert_allclose(gr, g["grad"], rtol=1e-11, atol=1e-14)
+    l, gr, _ = bo.loss_and_grad(g["theta_tie"], d, hls, np.zeros(d), 1.0, N, M, int(g["seed_tie"]))
+    assert abs(l - float(g["loss_tie"])) <= 1e-13 * abs(l)
+    np.testing.assert_allclose(gr, g["grad_tie"], rtol=1e-11, atol=1e-14)
+
+
+def _shard_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = _golden()
+    d, hls, M, N = int(g["d"]), int(g["hls"]), int(g["M"]), int(g["N"])
+    lo, hi = rank * M // world, (rank + 1) * M // world
+    l, gr, _ = bo.loss_and_grad(g["theta"], d, hls, g["x0"], 1.0, N, hi - lo, int(g["seed"]), path0=lo, n_total=M)
+    buf = torch.from_numpy(np.concatenate([gr, [l]]))
+    dist.all_reduce(buf)                                  # the job's one collective: [grad; loss] summed over the path shards
+    q.put((rank, buf.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_path_shards_over_two_ranks_add_up_gloo():
+    """Multi-GPU rule of the SDE path (path_offset / total_paths of b200ude_bsde_loss_gradient): disjoint Philox path counters, the mean
+    over ALL paths; the all-reduced [grad; loss] equals the single-process evaluation."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    ps = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    g = _golden()
+    want = np.concatenate([g["grad"], [float(g["loss"])]])
+    for r in range(2):
+        np.testing.assert_allclose(res[r], want, rtol=1e-11, atol=1e-14)

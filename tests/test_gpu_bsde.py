@@ -49,6 +49,23 @@ def test_f64_loss_gradient_vs_oracle(d, hls, M, N):
     s.close()
 
 
+def test_f64_frozen_vectors():
+    """tests/golden/hjb_small.npz (tools/make_golden_bsde.py): the comparison does not run the oracle."""
+    import os
+    ude = _ude()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hjb_small.npz"))
+    d, hls, M, N = int(g["d"]), int(g["hls"]), int(g["M"]), int(g["N"])
+    for th, x0, seed, l_w, g_w, u_w in ((g["theta"], g["x0"], int(g["seed"]), float(g["loss"]), g["grad"], float(g["u0"])),
+                                        (g["theta_tie"], np.zeros(d), int(g["seed_tie"]), float(g["loss_tie"]), g["grad_tie"], float(g["u0_tie"]))):
+        prob, alg = _problem(ude, d, hls, x0)
+        s = ude.BSDESolver(prob, alg, N, M, dtype=torch.float64)
+        s.set_params(th)
+        loss, gr, u0 = s.loss_gradient(M, seed=seed)
+        assert abs(loss - l_w) <= 1e-10 * abs(l_w) and abs(u0 - u_w) <= 1e-10 * max(1.0, abs(u_w))
+        assert np.linalg.norm(gr.cpu().numpy() - g_w) <= 1e-9 * np.linalg.norm(g_w)
+        s.close()
+
+
 def test_f64_relu_ties_follow_the_reference_convention():
     """x0 = 0 with Flux's zero-bias init (lambaem.jl:9,24-31): every hidden pre-activation of the u0 net is exactly 0; relu'(0) = 1."""
     ude = _ude()
