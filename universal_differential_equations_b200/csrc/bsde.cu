@@ -68,6 +68,23 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint32_t path, uint32_t 
     z[0] = ra * ca; z[1] = ra * sa; z[2] = rb * cb; z[3] = rb * sb;
 }
 
+// Brownian increments of a whole iteration for the fused sweeps: dW[n][path][m] = sqrt(dt) * normal(path, m, n), one thread per
+// (step, path, block of 4 components).  A separate, fully parallel pass: inside the forward sweep the fp64 log / sincos chains of the
+// Box-Muller transform sat on every warp's critical path (a third of the sweep's time, measured with clock64()).
+__global__ void k_dw_tape(double *__restrict__ dW, const uint64_t *seed, uint32_t path0, int M, int N, int d, double sq)
+{
+    const int nq = (d + 3) / 4;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)N * M * nq) return;
+    const int q = (int)(i % nq), m = (int)((i / nq) % M), n = (int)(i / ((long)nq * M));
+    double nz[4];
+    normals4(*seed, path0 + (uint32_t)m, (uint32_t)q, (uint32_t)n, nz);
+    double *o = dW + ((size_t)n * M + m) * d + 4 * q;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (4 * q + e < d) o[e] = sq * nz[e];
+}
+
 // ---- element-wise kernels (R = float or double) ------------------------------------------------------------------------------
 // constant rows of the augmented activations for all steps: IN[n] = [X_n (d rows); t_n; 1], H_k[n] = [h (hls rows); 1]
 template <class R>
@@ -243,6 +260,8 @@ constexpr int FSLAB = FSR * FLD;                          // doubles per slab
 constexpr uint32_t FSLAB_BYTES = FSLAB * sizeof(double);   // 14 848
 constexpr int FWPC = 4;       // warps per CTA; three CTAs per SM run out of step with one another, so one's barrier / tape-latency /
                               // Euler-Maruyama phases are covered by the others' DMMA phases
+constexpr int FWF = 4;        // forward sweep: warps per CTA (one per scheduler: the warps of a CTA then share their schedulers with equally
+                              // many others and run at the same pace -- with 5 the ring made the faster ones wait for the slower)
 constexpr int FMAXSLABS = 32;
 
 struct FusedArgs {
@@ -252,6 +271,7 @@ struct FusedArgs {
     unsigned char f_layer[FMAXSLABS], f_k0[FMAXSLABS], f_ks[FMAXSLABS], f_last[FMAXSLABS];
     unsigned char b_layer[FMAXSLABS], b_k0[FMAXSLABS], b_ks[FMAXSLABS], b_last[FMAXSLABS];
     double *IN, *H[3], *Z, *Zb, *C[3], *u, *r2, *ubar;   // Z holds G = 2 lambda z dt + dW here (zbar = ubar G)
+    const double *dW;      // Brownian increments [n][path][d] of this iteration (k_dw_tape)
     uint32_t *mask;        // relu' bits of the hidden layers: word ((n * 3 + l) * M + path) * 4 + (lane & 3), bit 2 nt + e
     const double *x0, *u0;
     const uint64_t *seed;
@@ -264,20 +284,6 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
-// the two standard normals this lane needs for components (m, m + 1), m even: the first or second Box-Muller pair of block m / 4
-__device__ __forceinline__ void normals2(uint64_t seed, uint32_t path, int m, uint32_t step, double &n0, double &n1)
-{
-    uint32_t c0 = path, c1 = (uint32_t)(m >> 2), c2 = step, c3 = 0u;
-    philox4x32(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double s32 = 2.3283064365386963e-10;
-    const bool second = (m & 2) != 0;
-    const double ua = ((double)(second ? c2 : c0) + 0.5) * s32, ub = ((double)(second ? c3 : c1) + 0.5) * s32;
-    const double ra = sqrt(-2.0 * log(ua));
-    double sn, cs;
-    sincos(6.283185307179586 * ub, &sn, &cs);
-    n0 = ra * cs; n1 = ra * sn;
-}
-
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
 {
     uint32_t done = 0;
@@ -287,95 +293,91 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
 // the slab ring: FRING buffers with one "full" mbarrier each; the stream of slabs (n_slabs per round, round after round) is
 // consumed in order; (cb, cph) = buffer and barrier phase of the slab being consumed
 constexpr int FRING = 3;
-struct SlabProducer {     // thread 0's bookkeeping, kept in shared memory (registers are the scarce resource of these kernels)
-    const double *src;
-    long issued, total;
-    int n_slabs, ib;      // slabs per round; buffer of the next slab to issue
+struct SlabShared {       // per-CTA bookkeeping in shared memory
+    int done[FRING];      // warps that have finished with the slab in buffer b
 };
 struct SlabRing {
     double *base;         // FRING slabs
-    uint32_t bar0;        // FRING mbarriers, 8 bytes apart
-    SlabProducer *prod;
-    int cb, cph;          // consumer cursor
-    __device__ __forceinline__ void issue()   // one thread
+    uint32_t bar0;        // FRING "full" mbarriers, 8 bytes apart
+    SlabShared *sh;
+    const double *src;
+    long total, idx;      // slabs of this CTA's stream; index of the slab being consumed
+    int n_slabs, nwarps;  // slabs per round (the stream repeats round after round)
+    int cb, cph;          // buffer and barrier phase of the slab being consumed
+    __device__ __forceinline__ void issue(long i, int b) const   // one thread: slab i of the stream -> buffer b
     {
-        SlabProducer &q = *prod;
-        if (q.issued >= q.total) return;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(base + (size_t)q.ib * FSLAB), br = bar0 + 8u * q.ib;
-        const double *g = q.src + (size_t)(q.issued % q.n_slabs) * FSLAB;
+        if (i >= total) return;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(base + (size_t)b * FSLAB), br = bar0 + 8u * b;
+        const double *g = src + (size_t)(i % n_slabs) * FSLAB;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(br), "r"(FSLAB_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g), "r"(FSLAB_BYTES),
                      "r"(br)
                      : "memory");
-        ++q.issued;
-        q.ib = q.ib == FRING - 1 ? 0 : q.ib + 1;
     }
     __device__ __forceinline__ const double *cur() const { return base + (size_t)cb * FSLAB; }
-    __device__ __forceinline__ int nb() const { return cb == FRING - 1 ? 0 : cb + 1; }
     __device__ __forceinline__ void wait_cur() const { mbar_wait(bar0 + 8u * cb, (uint32_t)cph); }
-    __device__ __forceinline__ const double *wait_next() const   // the slab after the current one (must exist)
+    // This warp is done with the current slab.  No CTA barrier: the LAST warp to finish refills the buffer with the slab FRING ahead,
+    // so the warps of a CTA drift freely within the ring's depth (a barrier per slab cost the forward sweep a sixth of its time).
+    __device__ __forceinline__ void release(int lane)
     {
-        const int n = nb();
-        mbar_wait(bar0 + 8u * n, (uint32_t)(n == 0 ? cph ^ 1 : cph));
-        return base + (size_t)n * FSLAB;
-    }
-    __device__ __forceinline__ void advance() { cb = nb(); if (cb == 0) cph ^= 1; }
-};
-// One slab of a layer: acc[nt] += sum over its FSR rows of in[r][k0 + k] * slab[k][8 nt + r'].  The B fragments of a k-step are loaded
-// one k-step ahead of the DMMAs that use them -- bv holds those of the slab's first k-step on entry and, with `more`, those of the
-// NEXT slab's first k-step on return (its arrival is awaited just before, three k-steps into this slab).  Rows beyond a layer's inputs
-// are zero in the slab and finite in `in`, so every slab runs all its k-steps.
-__device__ __forceinline__ void slab_mma(const double *in, const SlabRing &ring, bool more, int k0, int r, int c, double (&acc)[FT][2], double (&bv)[FT])
-{
-    const double *wp = ring.cur() + c * FLD + r;
-    const double *ap = in + r * FLD + k0 + c;
-#pragma unroll
-    for (int ks = 0; ks < FSR / 4; ++ks) {
-        double nx[FT];
-        if (ks < FSR / 4 - 1) {
-#pragma unroll
-            for (int nt = 0; nt < FT; ++nt) nx[nt] = wp[(ks + 1) * 4 * FLD + 8 * nt];
-        } else if (more) {
-            const double *np = ring.wait_next() + c * FLD + r;
-#pragma unroll
-            for (int nt = 0; nt < FT; ++nt) nx[nt] = np[8 * nt];
+        __syncwarp();
+        if (lane == 0) {   // (__syncwarp above orders the other lanes' reads of the slab before this)
+            if (atomicAdd(&sh->done[cb], 1) == nwarps - 1) {
+                sh->done[cb] = 0;
+                issue(idx + FRING, cb);
+            }
         }
-        const double av = ap[4 * ks];
-#pragma unroll
-        for (int nt = 0; nt < FT; ++nt) dmma(acc[nt], av, bv[nt]);
-#pragma unroll
-        for (int nt = 0; nt < FT; ++nt) bv[nt] = nx[nt];
+        cb = cb == FRING - 1 ? 0 : cb + 1;
+        if (cb == 0) cph ^= 1;
+        ++idx;
     }
-}
-__device__ __forceinline__ void slab_first(const SlabRing &ring, int r, int c, double (&bv)[FT])   // start (or restart) of the B pipeline
+};
+// One slab of a layer: acc[nt] += sum over its FSR rows of in[r][k0 + k] * slab[k][8 nt + r'].  Each B fragment register is reloaded
+// for the next k-step right behind the DMMA that read it (the other warps of the scheduler cover the load latency); rows beyond a
+// layer's inputs are zero in the slab and finite in `in`, so every slab runs all its k-steps.
+__device__ __forceinline__ void slab_mma(const double *in, const SlabRing &ring, int k0, int r, int c, double (&acc)[FT][2])
 {
     ring.wait_cur();
     const double *wp = ring.cur() + c * FLD + r;
+    const double *ap = in + r * FLD + k0 + c;
+    double bv[FT];
 #pragma unroll
     for (int nt = 0; nt < FT; ++nt) bv[nt] = wp[8 * nt];
+#pragma unroll
+    for (int ks = 0; ks < FSR / 4; ++ks) {
+        const double av = ap[4 * ks];
+#pragma unroll
+        for (int nt = 0; nt < FT; ++nt) {
+            dmma(acc[nt], av, bv[nt]);
+            if (ks < FSR / 4 - 1) bv[nt] = wp[(ks + 1) * 4 * FLD + 8 * nt];
+        }
+    }
 }
-// shared-memory carve-up: [FRING slabs][per warp: one activation buffer of 8 rows, updated in place][FRING mbarriers]
+// shared-memory carve-up: [FRING slabs][per warp: one activation buffer of 8 rows, updated in place][FRING mbarriers][SlabShared]
 __device__ __forceinline__ void fused_setup(double *fsm, int nwarps, SlabRing &ring, const double *src, int n_slabs, long total)
 {
     ring.base = fsm;
     uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + FRING * FSLAB + (size_t)nwarps * 8 * FLD);
     ring.bar0 = (uint32_t)__cvta_generic_to_shared(bars);
-    ring.prod = reinterpret_cast<SlabProducer *>(bars + FRING);
+    ring.sh = reinterpret_cast<SlabShared *>(bars + FRING);
+    ring.src = src; ring.n_slabs = n_slabs; ring.total = total; ring.idx = 0; ring.nwarps = nwarps;
     ring.cb = 0; ring.cph = 0;
-    if (threadIdx.x == 0) { ring.prod->src = src; ring.prod->n_slabs = n_slabs; ring.prod->issued = 0; ring.prod->total = total; ring.prod->ib = 0; }
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < FRING; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring.bar0 + 8u * i));
+        for (int i = 0; i < FRING; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring.bar0 + 8u * i));
+            ring.sh->done[i] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < FRING; ++i) ring.issue();
+        for (int i = 0; i < FRING; ++i) ring.issue(i, i);
     }
 }
 
-__global__ void __launch_bounds__(32 * FWPC, 3) k_fused_forward(const FusedArgs a)
+__global__ void __launch_bounds__(32 * FWF, 3) k_fused_forward(const FusedArgs a)
 {
     extern __shared__ __align__(16) double fsm[];
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
@@ -386,28 +388,36 @@ __global__ void __launch_bounds__(32 * FWPC, 3) k_fused_forward(const FusedArgs 
     const bool live = path < a.M;
     const size_t pc = (size_t)(live ? path : a.M - 1);
     const int d = a.d, hl = a.hl;
-    const double sq = sqrt(a.dt);
-    const uint64_t seed = *a.seed;
-    double u = *a.u0, nn = 0.0;
+    double u = *a.u0;
     const size_t s_in = (size_t)(d + 2) * a.M, s_h = (size_t)(hl + 1) * a.M, s_z = (size_t)d * a.M;
-    {   // X_0 -> the tape and the warp's input rows (X lives on the tape between steps, not in registers)
-        double *inx = a.IN + pc * (d + 2);
+    double X[FT][2];   // the warp's paths in the fragment layout
+#pragma unroll
+    for (int nt = 0; nt < FT; ++nt) {
+        const int m = 8 * nt + 2 * c;
+        X[nt][0] = m < d ? a.x0[m] : 0.0;
+        X[nt][1] = m + 1 < d ? a.x0[m + 1] : 0.0;
+    }
+    for (int n = 0; n <= a.N; ++n) {
+        // X_n -> the tape (rows d, d + 1 of IN hold t_n and 1 already) and the warp's input rows [X; t; 1; 0...]
+        double *inx = a.IN + n * s_in + pc * (d + 2);
 #pragma unroll
         for (int nt = 0; nt < FT; ++nt) {
             const int m = 8 * nt + 2 * c;
-            const double x0 = m < d ? a.x0[m] : 0.0, x1 = m + 1 < d ? a.x0[m + 1] : 0.0;
-            if (live && m < d) inx[m] = x0;
-            if (live && m + 1 < d) inx[m + 1] = x1;
-            *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(x0, x1);
+            if (live && m < d) inx[m] = X[nt][0];
+            if (live && m + 1 < d) inx[m + 1] = X[nt][1];
+            *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(X[nt][0], X[nt][1]);
         }
-    }
-    for (int n = 0; n < a.N; ++n) {
-        // the warp's input rows hold [X_n; 0...]: add t_n and the ones row (rows d, d + 1 of the tape hold them already)
+        if (n == a.N) break;
+        {   // the step's Brownian increments towards L2 while the layers run (8 rows of d doubles: lane i asks for lines i, i + 32)
+            const int p0 = path - r, rows = p0 < a.M ? (a.M - p0 < 8 ? a.M - p0 : 8) : 0;
+            const char *w0 = reinterpret_cast<const char *>(a.dW + n * s_z + (size_t)(rows ? p0 : 0) * d);
+            const size_t bytes = (size_t)rows * d * sizeof(double);
+            for (size_t o = (size_t)lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + o));
+        }
         __syncwarp();
         if (c == 0) { buf[r * FLD + d] = n * a.dt; buf[r * FLD + d + 1] = 1.0; }
         __syncwarp();
-        double acc[FT][2], bv[FT];
-        slab_first(ring, r, c, bv);
+        double acc[FT][2];
 #pragma unroll 1
         for (int i = 0; i < a.n_f; ++i) {
             const int l = a.f_layer[i];
@@ -415,12 +425,10 @@ __global__ void __launch_bounds__(32 * FWPC, 3) k_fused_forward(const FusedArgs 
 #pragma unroll
                 for (int nt = 0; nt < FT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
             }
-            slab_mma(buf, ring, i + 1 < a.n_f, a.f_k0[i], r, c, acc, bv);   // the B pipeline restarts at every step (registers for the update)
-            ring.advance();
-            __syncthreads();                       // every warp is done with this slab: its buffer may be refilled
-            if (threadIdx.x == 0) ring.issue();
+            slab_mma(buf, ring, a.f_k0[i], r, c, acc);
+            ring.release(lane);
             if (!a.f_last[i]) continue;
-            if (l < 3) {   // the layer's output replaces its input in the warp's rows (all of the warp's reads are behind the barrier)
+            if (l < 3) {   // the layer's output replaces its input in the warp's own rows
                 double *hp = a.H[l] + n * s_h + pc * (hl + 1);
                 uint32_t bits = 0u;
 #pragma unroll
@@ -439,35 +447,34 @@ __global__ void __launch_bounds__(32 * FWPC, 3) k_fused_forward(const FusedArgs 
                 __syncwarp();
             }
         }
-        // acc = z_n for the warp's paths: Euler-Maruyama update in the fragment layout; X_{n+1} goes to the tape and to the input rows
+        // acc = z_n for the warp's paths: Euler-Maruyama update in the fragment layout
         double zz = 0.0, zw = 0.0;
         double *zp = a.Z + n * s_z + pc * d;
-        const double *xo = a.IN + n * s_in + pc * (d + 2);
-        double *xn = a.IN + (n + 1) * s_in + pc * (d + 2);
+        const double *wn = a.dW + n * s_z + pc * d;
 #pragma unroll
         for (int nt = 0; nt < FT; ++nt) {
             const int m = 8 * nt + 2 * c;
-            double x0 = 0.0, x1 = 0.0;
             if (m < d) {
-                double n0, n1;
-                normals2(seed, a.path0 + (uint32_t)path, m, (uint32_t)n, n0, n1);
-                const double dw0 = sq * n0, dw1 = sq * n1, z0 = acc[nt][0], z1 = m + 1 < d ? acc[nt][1] : 0.0;
+                const double dw0 = wn[m], z0 = acc[nt][0];
                 zz = fma(z0, z0, zz); zw = fma(z0, dw0, zw);
-                x0 = xo[m] + a.s * dw0;
-                if (live) { zp[m] = 2.0 * a.lam * z0 * a.dt + dw0; xn[m] = x0; }   // zp: d(u_T)/d(z_n) up to the factor ubar
+                X[nt][0] += a.s * dw0;
+                if (live) zp[m] = 2.0 * a.lam * z0 * a.dt + dw0;   // d(u_T)/d(z_n) up to the factor ubar
                 if (m + 1 < d) {
+                    const double dw1 = wn[m + 1], z1 = acc[nt][1];
                     zz = fma(z1, z1, zz); zw = fma(z1, dw1, zw);
-                    x1 = xo[m + 1] + a.s * dw1;
-                    if (live) { zp[m + 1] = 2.0 * a.lam * z1 * a.dt + dw1; xn[m + 1] = x1; }
+                    X[nt][1] += a.s * dw1;
+                    if (live) zp[m + 1] = 2.0 * a.lam * z1 * a.dt + dw1;
                 }
             }
-            *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(x0, x1);
-            if (n == a.N - 1) nn = fma(x0, x0, fma(x1, x1, nn));
         }
         zz += __shfl_xor_sync(0xffffffffu, zz, 1); zw += __shfl_xor_sync(0xffffffffu, zw, 1);
         zz += __shfl_xor_sync(0xffffffffu, zz, 2); zw += __shfl_xor_sync(0xffffffffu, zw, 2);
         u += a.lam * zz * a.dt + zw;
+        __syncwarp();
     }
+    double nn = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < FT; ++nt) nn = fma(X[nt][0], X[nt][0], fma(X[nt][1], X[nt][1], nn));
     nn += __shfl_xor_sync(0xffffffffu, nn, 1);
     nn += __shfl_xor_sync(0xffffffffu, nn, 2);
     if (live && c == 0) {
@@ -520,8 +527,7 @@ __global__ void __launch_bounds__(32 * FWPC, 3) k_fused_backward(const FusedArgs
             *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(b0, b1);
         }
         __syncwarp();
-        double acc[FT][2], bv[FT];
-        slab_first(ring, r, c, bv);
+        double acc[FT][2];
 #pragma unroll 1
         for (int i = 0; i < a.n_b; ++i) {
             const int l = a.b_layer[i];
@@ -529,10 +535,8 @@ __global__ void __launch_bounds__(32 * FWPC, 3) k_fused_backward(const FusedArgs
 #pragma unroll
                 for (int nt = 0; nt < FT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
             }
-            slab_mma(buf, ring, i + 1 < a.n_b, a.b_k0[i], r, c, acc, bv);
-            ring.advance();
-            __syncthreads();
-            if (threadIdx.x == 0) ring.issue();
+            slab_mma(buf, ring, a.b_k0[i], r, c, acc);
+            ring.release(lane);
             if (!a.b_last[i]) continue;
             const uint32_t mb = l == 3 ? bits[2] : (l == 2 ? bits[1] : bits[0]);
             double *cp = a.C[l - 1] + n * s_c + pc * hl;
@@ -629,6 +633,7 @@ struct b200ude_bsde_handle {
     bool fused = false;       // fp64, widths <= 112: the fused DMMA sweeps instead of per-layer library GEMMs
     void *packed = nullptr;   // zero-padded operand copies of the z network for the fused sweeps
     void *mask = nullptr;     // relu' bits of the hidden layers (fused sweeps)
+    void *dW = nullptr;       // Brownian increments of the iteration (fused sweeps)
     FusedArgs fa;             // slab tables (the pointers are filled per call)
     int sm_count = 148;
     void *hu[3] = {}, *cu_[3] = {};   // u0 net (single column): activations / cotangents
@@ -704,7 +709,7 @@ int32_t net_backward(b200ude_bsde_handle *h, const Net &n, const R *in, R *const
     return B200UDE_OK;
 }
 
-inline size_t fused_smem(int warps) { return ((size_t)FRING * FSLAB + (size_t)warps * 8 * FLD) * sizeof(double) + 8 * FRING + sizeof(SlabProducer); }
+inline size_t fused_smem(int warps) { return ((size_t)FRING * FSLAB + (size_t)warps * 8 * FLD) * sizeof(double) + 8 * FRING + sizeof(SlabShared); }
 
 // the fused fp64 path of one iteration: operand slabs, forward sweep (+ residual), loss sums, cotangent sweep
 int32_t fused_sweeps(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_total, cudaStream_t st)
@@ -722,10 +727,15 @@ int32_t fused_sweeps(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_t
     a.M = M; a.N = h->desc.n_steps; a.d = h->d; a.hl = h->hls;
     a.dt = h->desc.T / h->desc.n_steps; a.lam = h->desc.lambda; a.s = h->desc.sigma; a.ga = h->desc.g_a; a.gb = h->desc.g_b; a.inv_total = inv_total;
     a.mask = (uint32_t *)h->mask;
+    a.dW = (const double *)h->dW;
+    {
+        const long total = (long)a.N * M * ((a.d + 3) / 4);
+        k_dw_tape<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((double *)h->dW, h->seed_dev, path0, M, a.N, a.d, sqrt(a.dt));
+    }
     const int tiles = (M + 7) / 8;
     const size_t smem = fused_smem(FWPC);
     if (h->time_kernels) cudaEventRecord(h->kev[0], st);
-    k_fused_forward<<<(tiles + FWPC - 1) / FWPC, 32 * FWPC, smem, st>>>(a);
+    k_fused_forward<<<(tiles + FWF - 1) / FWF, 32 * FWF, fused_smem(FWF), st>>>(a);
     if (h->time_kernels) cudaEventRecord(h->kev[1], st);
     k_sum2<double><<<1, 256, 0, st>>>((const double *)h->r2, (const double *)h->ubar, M, inv_total, (double *)h->scal, (double *)h->scal + 1);
     if (h->time_kernels) cudaEventRecord(h->kev[2], st);
@@ -942,9 +952,10 @@ int32_t b200ude_bsde_create(const b200ude_bsde_desc *d, b200ude_bsde_handle **ou
                 fa.b_last[i] = (unsigned char)(k0 + FSR >= h->nz.widths[l + 1]);
             }
         h->sm_count = prop.multiProcessorCount;
-        const int smem = (int)fused_smem(FWPC);
+        const int smem = (int)fused_smem(FWF);
         if (cudaMalloc(&h->packed, (size_t)(fa.n_f + fa.n_b) * FSLAB * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->mask, (size_t)d->n_steps * 3 * d->max_paths * 4 * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMalloc(&h->dW, (size_t)d->n_steps * d->dim * d->max_paths * sizeof(double)) == cudaSuccess &&
             cudaFuncSetAttribute(k_fused_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
             cudaFuncSetAttribute(k_fused_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess)
             h->fused = true;
@@ -974,7 +985,7 @@ void b200ude_bsde_destroy(b200ude_bsde_handle *h)
 {
     if (!h) return;
     void *bufs[] = {h->theta, h->grad, h->adam_m, h->adam_v, h->x0, h->IN, h->u, h->H[0], h->H[1], h->H[2], h->Z, h->Zb, h->C[0], h->C[1], h->C[2],
-                    h->r2, h->ubar, h->ones, h->hu[0], h->hu[1], h->cu_[0], h->cu_[1], h->scal, h->t_dev, h->seed_dev, h->workspace, h->packed, h->mask};
+                    h->r2, h->ubar, h->ones, h->hu[0], h->hu[1], h->cu_[0], h->cu_[1], h->scal, h->t_dev, h->seed_dev, h->workspace, h->packed, h->mask, h->dW};
     for (void *b : bufs) cudaFree(b);
     for (cudaEvent_t e : h->kev)
         if (e) cudaEventDestroy(e);
