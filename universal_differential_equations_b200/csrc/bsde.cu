@@ -88,7 +88,7 @@ __global__ void k_dw_tape(double *__restrict__ dW, const uint64_t *seed, uint32_
 // ---- element-wise kernels (R = float or double) ------------------------------------------------------------------------------
 // constant rows of the augmented activations for all steps: IN[n] = [X_n (d rows); t_n; 1], H_k[n] = [h (hls rows); 1]
 template <class R>
-__global__ void k_init_aug(R *IN, R *H1, R *H2, R *H3, int d, int hls, int M, int n_steps, double dt)
+__global__ void k_init_aug(R *IN, R *H1, R *H2, R *H3, int d, int hls, int ldh, int M, int n_steps, double dt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (n_steps + 1) * M) return;
@@ -96,9 +96,10 @@ __global__ void k_init_aug(R *IN, R *H1, R *H2, R *H3, int d, int hls, int M, in
     IN[(size_t)i * (d + 2) + d] = (R)(n * dt);
     IN[(size_t)i * (d + 2) + d + 1] = (R)1;
     if (n < n_steps) {
-        H1[(size_t)i * (hls + 1) + hls] = (R)1;
-        H2[(size_t)i * (hls + 1) + hls] = (R)1;
-        H3[(size_t)i * (hls + 1) + hls] = (R)1;
+        for (int k = hls; k < ldh; ++k) {   // the ones row, then zero padding up to the (even) leading dimension
+            const R v = k == hls ? (R)1 : (R)0;
+            H1[(size_t)i * ldh + k] = v; H2[(size_t)i * ldh + k] = v; H3[(size_t)i * ldh + k] = v;
+        }
     }
 }
 template <class R>
@@ -276,7 +277,7 @@ struct FusedArgs {
     const double *x0, *u0;
     const uint64_t *seed;
     uint32_t path0;
-    int M, N, d, hl;
+    int M, N, d, hl, ldh;
     double dt, lam, s, ga, gb, inv_total;
 };
 
@@ -389,7 +390,8 @@ __global__ void __launch_bounds__(32 * FWF, 3) k_fused_forward(const FusedArgs a
     const size_t pc = (size_t)(live ? path : a.M - 1);
     const int d = a.d, hl = a.hl;
     double u = *a.u0;
-    const size_t s_in = (size_t)(d + 2) * a.M, s_h = (size_t)(hl + 1) * a.M, s_z = (size_t)d * a.M;
+    const size_t s_in = (size_t)(d + 2) * a.M, s_h = (size_t)a.ldh * a.M, s_z = (size_t)d * a.M;
+    const bool even_d = (d & 1) == 0;   // then (path * ld + m) is even for the lane's pairs: 16-byte tape accesses
     double X[FT][2];   // the warp's paths in the fragment layout
 #pragma unroll
     for (int nt = 0; nt < FT; ++nt) {
@@ -403,8 +405,11 @@ __global__ void __launch_bounds__(32 * FWF, 3) k_fused_forward(const FusedArgs a
 #pragma unroll
         for (int nt = 0; nt < FT; ++nt) {
             const int m = 8 * nt + 2 * c;
-            if (live && m < d) inx[m] = X[nt][0];
-            if (live && m + 1 < d) inx[m + 1] = X[nt][1];
+            if (live && even_d && m < d) *reinterpret_cast<double2 *>(inx + m) = make_double2(X[nt][0], X[nt][1]);
+            else {
+                if (live && m < d) inx[m] = X[nt][0];
+                if (live && m + 1 < d) inx[m + 1] = X[nt][1];
+            }
             *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(X[nt][0], X[nt][1]);
         }
         if (n == a.N) break;
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(32 * FWF, 3) k_fused_forward(const FusedArgs a
             ring.release(lane);
             if (!a.f_last[i]) continue;
             if (l < 3) {   // the layer's output replaces its input in the warp's own rows
-                double *hp = a.H[l] + n * s_h + pc * (hl + 1);
+                double *hp = a.H[l] + n * s_h + pc * a.ldh;
                 uint32_t bits = 0u;
 #pragma unroll
                 for (int nt = 0; nt < FT; ++nt) {
@@ -438,8 +443,8 @@ __global__ void __launch_bounds__(32 * FWF, 3) k_fused_forward(const FusedArgs a
                     const double h0 = neg0 ? -0.0 : acc[nt][0], h1 = neg1 ? -0.0 : acc[nt][1];
                     bits |= (neg0 ? 1u : 0u) << (2 * nt) | (neg1 ? 1u : 0u) << (2 * nt + 1);
                     *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(h0, h1);
-                    if (live && m < hl) hp[m] = h0;
-                    if (live && m + 1 < hl) hp[m + 1] = h1;
+                    if (live && m + 1 < hl) *reinterpret_cast<double2 *>(hp + m) = make_double2(h0, h1);   // ldh is even
+                    else if (live && m < hl) hp[m] = h0;
                 }
                 if (live) a.mask[((size_t)(n * 3 + l) * a.M + pc) * 4 + c] = bits;
                 __syncwarp();
@@ -454,11 +459,17 @@ __global__ void __launch_bounds__(32 * FWF, 3) k_fused_forward(const FusedArgs a
 #pragma unroll
         for (int nt = 0; nt < FT; ++nt) {
             const int m = 8 * nt + 2 * c;
-            if (m < d) {
+            if (even_d && m < d) {
+                const double2 dw = *reinterpret_cast<const double2 *>(wn + m);
+                const double z0 = acc[nt][0], z1 = acc[nt][1];
+                zz = fma(z0, z0, fma(z1, z1, zz)); zw = fma(z0, dw.x, fma(z1, dw.y, zw));
+                X[nt][0] += a.s * dw.x; X[nt][1] += a.s * dw.y;
+                if (live) *reinterpret_cast<double2 *>(zp + m) = make_double2(2.0 * a.lam * z0 * a.dt + dw.x, 2.0 * a.lam * z1 * a.dt + dw.y);   // d(u_T)/d(z_n) / ubar
+            } else if (m < d) {
                 const double dw0 = wn[m], z0 = acc[nt][0];
                 zz = fma(z0, z0, zz); zw = fma(z0, dw0, zw);
                 X[nt][0] += a.s * dw0;
-                if (live) zp[m] = 2.0 * a.lam * z0 * a.dt + dw0;   // d(u_T)/d(z_n) up to the factor ubar
+                if (live) zp[m] = 2.0 * a.lam * z0 * a.dt + dw0;
                 if (m + 1 < d) {
                     const double dw1 = wn[m + 1], z1 = acc[nt][1];
                     zz = fma(z1, z1, zz); zw = fma(z1, dw1, zw);
@@ -499,6 +510,7 @@ __global__ void __launch_bounds__(32 * FWPC, 3) k_fused_backward(const FusedArgs
     double *buf = fsm + FRING * FSLAB + (size_t)warp * 8 * FLD;
     const int d = a.d, hl = a.hl;
     const size_t s_z = (size_t)d * a.M, s_c = (size_t)hl * a.M;
+    const bool even_d = (d & 1) == 0, even_h = (hl & 1) == 0;
     for (long g = blockIdx.x; g < groups; g += gridDim.x) {
         const long task = g * nwarps + warp;
         const bool task_live = task < tasks;
@@ -516,7 +528,11 @@ __global__ void __launch_bounds__(32 * FWPC, 3) k_fused_backward(const FusedArgs
         for (int nt = 0; nt < FT; ++nt) {
             const int m = 8 * nt + 2 * c;
             double b0 = 0.0, b1 = 0.0;
-            if (m < d) {
+            if (even_d && m < d) {   // (path * d + m) is even: 16-byte tape accesses
+                const double2 gg = *reinterpret_cast<const double2 *>(gp + m);
+                b0 = ub * gg.x; b1 = ub * gg.y;
+                if (live) *reinterpret_cast<double2 *>(zb + m) = make_double2(b0, b1);
+            } else if (m < d) {
                 b0 = ub * gp[m];
                 if (live) zb[m] = b0;
                 if (m + 1 < d) {
@@ -545,8 +561,11 @@ __global__ void __launch_bounds__(32 * FWPC, 3) k_fused_backward(const FusedArgs
                 const int m = 8 * nt + 2 * c;
                 const double c0 = (m < hl && !((mb >> (2 * nt)) & 1u)) ? acc[nt][0] : 0.0;
                 const double c1 = (m + 1 < hl && !((mb >> (2 * nt + 1)) & 1u)) ? acc[nt][1] : 0.0;
-                if (live && m < hl) cp[m] = c0;
-                if (live && m + 1 < hl) cp[m + 1] = c1;
+                if (live && even_h && m + 1 < hl) *reinterpret_cast<double2 *>(cp + m) = make_double2(c0, c1);
+                else {
+                    if (live && m < hl) cp[m] = c0;
+                    if (live && m + 1 < hl) cp[m + 1] = c1;
+                }
                 *reinterpret_cast<double2 *>(buf + r * FLD + m) = make_double2(c0, c1);
             }
             __syncwarp();
@@ -617,6 +636,7 @@ Net make_net(const int *widths, int n_layers, size_t base)
 struct b200ude_bsde_handle {
     b200ude_bsde_desc desc;
     int d = 0, hls = 0, P = 0;
+    int ldh = 0;   // leading dimension of the hidden-activation tapes: hls + 1 (the ones row) rounded up to even (16-byte columns in fp64)
     bool f64 = true;
     size_t cap = 0;
     Net nu, nz;
@@ -626,7 +646,7 @@ struct b200ude_bsde_handle {
     // device buffers (element type = the handle's dtype)
     void *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr, *x0 = nullptr;
     // per-step storage, step n of an M-path evaluation at element offset n * ld * M:
-    //   IN [n_steps + 1][d + 2][cap]  = [X_n; t_n; 1]      H[k] [n_steps][hls + 1][cap] = [hidden k; 1]      Z, Zb [n_steps][d][cap]
+    //   IN [n_steps + 1][d + 2][cap]  = [X_n; t_n; 1]      H[k] [n_steps][ldh][cap] = [hidden k; 1; 0 pad]      Z, Zb [n_steps][d][cap]
     //   C[k] [n_steps][hls][cap] = cotangents of hidden k
     void *IN = nullptr, *u = nullptr, *H[3] = {}, *Z = nullptr, *Zb = nullptr, *C[3] = {}, *r2 = nullptr, *ubar = nullptr, *ones = nullptr;
     int init_M = 0;   // the constant rows are laid out for this many paths
@@ -724,7 +744,7 @@ int32_t fused_sweeps(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_t
     a.IN = (double *)h->IN; a.Z = (double *)h->Z; a.Zb = (double *)h->Zb; a.u = (double *)h->u; a.r2 = (double *)h->r2; a.ubar = (double *)h->ubar;
     for (int k = 0; k < 3; ++k) { a.H[k] = (double *)h->H[k]; a.C[k] = (double *)h->C[k]; }
     a.x0 = (const double *)h->x0; a.u0 = (const double *)h->scal + 2; a.seed = h->seed_dev; a.path0 = path0;
-    a.M = M; a.N = h->desc.n_steps; a.d = h->d; a.hl = h->hls;
+    a.M = M; a.N = h->desc.n_steps; a.d = h->d; a.hl = h->hls; a.ldh = h->ldh;
     a.dt = h->desc.T / h->desc.n_steps; a.lam = h->desc.lambda; a.s = h->desc.sigma; a.ga = h->desc.g_a; a.gb = h->desc.g_b; a.inv_total = inv_total;
     a.mask = (uint32_t *)h->mask;
     a.dW = (const double *)h->dW;
@@ -758,7 +778,8 @@ int32_t loss_gradient(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_
     const Net &nz = h->nz;
     R *u = (R *)h->u, *scal = (R *)h->scal, *IN = (R *)h->IN, *Z = (R *)h->Z, *Zb = (R *)h->Zb;
     R *H[3] = {(R *)h->H[0], (R *)h->H[1], (R *)h->H[2]}, *C[3] = {(R *)h->C[0], (R *)h->C[1], (R *)h->C[2]};
-    const size_t s_in = (size_t)(d + 2) * M, s_h = (size_t)(hl + 1) * M, s_c = (size_t)hl * M, s_z = (size_t)d * M;
+    const int ldh = h->ldh;
+    const size_t s_in = (size_t)(d + 2) * M, s_h = (size_t)ldh * M, s_c = (size_t)hl * M, s_z = (size_t)d * M;
     R *outs_u[3] = {(R *)h->hu[0], (R *)h->hu[1], scal + 2};
     R *cots_u[3] = {(R *)h->cu_[0], (R *)h->cu_[1], scal + 1};
     BS_CUDA(h, cudaMemsetAsync(h->grad, 0, sizeof(R) * h->nu.P, st));   // the u0 net's gradients accumulate; the z net's are written
@@ -774,14 +795,14 @@ int32_t loss_gradient(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_
         for (int n = 0; n < N; ++n) {
             // layer l: [W | b] (out x (in + 1), theta's own layout) times the ones-augmented activations
             const R *a = IN + n * s_in;
-            int ka = d + 2;
+            int ka = d + 2, lda = d + 2;   // contraction length (inputs + ones row) and leading dimension of the input block
             for (int l = 0; l < 3; ++l) {
                 R *o = H[l] + n * s_h;
-                BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, hl, M, ka, &one, th + nz.w_off[l], hl, a, ka, &zero, o, hl + 1));
-                k_relu<R><<<blocks((size_t)hl * M), 256, 0, st>>>(o, hl, hl + 1, M);
-                a = o; ka = hl + 1;
+                BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, hl, M, ka, &one, th + nz.w_off[l], hl, a, lda, &zero, o, ldh));
+                k_relu<R><<<blocks((size_t)hl * M), 256, 0, st>>>(o, hl, ldh, M);
+                a = o; ka = hl + 1; lda = ldh;
             }
-            BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, d, M, ka, &one, th + nz.w_off[3], d, a, ka, &zero, Z + n * s_z, d));
+            BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, d, M, ka, &one, th + nz.w_off[3], d, a, lda, &zero, Z + n * s_z, d));
             k_em_step<R><<<blocks((size_t)M * 32, 256), 256, 0, st>>>(IN + n * s_in, IN + (n + 1) * s_in, u, Z + n * s_z, h->seed_dev, path0, n, d, M, dt, lam, s);
         }
         k_residual<R><<<blocks((size_t)M * 32, 256), 256, 0, st>>>(IN + N * s_in, u, (R *)h->r2, (R *)h->ubar, d, M, h->desc.g_a, h->desc.g_b, inv_total);
@@ -794,7 +815,7 @@ int32_t loss_gradient(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_
             for (int l = 3; l >= 1; --l) {   // cot of hidden l = W_{l+1}^T cot_{l+1}, masked by relu'
                 R *o = C[l - 1] + n * s_c;
                 BS_BLAS(h, gemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, hl, M, nc, &one, th + nz.w_off[l], nc, c, nc, &zero, o, hl));
-                k_relu_mask<R><<<blocks((size_t)hl * M), 256, 0, st>>>(o, H[l - 1] + n * s_h, hl, hl + 1, M);
+                k_relu_mask<R><<<blocks((size_t)hl * M), 256, 0, st>>>(o, H[l - 1] + n * s_h, hl, ldh, M);
                 c = o; nc = hl;
             }
         }
@@ -803,9 +824,9 @@ int32_t loss_gradient(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_
     R *g = (R *)h->grad;
     const int K = N * M;
     BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, d + 2, K, &one, C[0], hl, IN, d + 2, &zero, g + nz.w_off[0], hl));
-    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[1], hl, H[0], hl + 1, &zero, g + nz.w_off[1], hl));
-    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[2], hl, H[1], hl + 1, &zero, g + nz.w_off[2], hl));
-    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, d, hl + 1, K, &one, Zb, d, H[2], hl + 1, &zero, g + nz.w_off[3], d));
+    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[1], hl, H[0], ldh, &zero, g + nz.w_off[1], hl));
+    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[2], hl, H[1], ldh, &zero, g + nz.w_off[2], hl));
+    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, d, hl + 1, K, &one, Zb, d, H[2], ldh, &zero, g + nz.w_off[3], d));
     if (h->time_kernels) cudaEventRecord(h->kev[4], st);
     rc = net_backward<R>(h, h->nu, (const R *)h->x0, outs_u, cots_u, 1, st);   // cotangent of u0(x0) = sum of ubar (already in scal[1])
     if (rc) return rc;
@@ -819,7 +840,7 @@ int32_t prepare(b200ude_bsde_handle *h, int M)
 {
     if (h->init_M == M) return B200UDE_OK;
     const int N = h->desc.n_steps;
-    k_init_aug<R><<<blocks((size_t)(N + 1) * M), 256, 0, h->stream>>>((R *)h->IN, (R *)h->H[0], (R *)h->H[1], (R *)h->H[2], h->d, h->hls, M, N, h->desc.T / N);
+    k_init_aug<R><<<blocks((size_t)(N + 1) * M), 256, 0, h->stream>>>((R *)h->IN, (R *)h->H[0], (R *)h->H[1], (R *)h->H[2], h->d, h->hls, h->ldh, M, N, h->desc.T / N);
     BS_CUDA(h, cudaGetLastError());
     h->init_M = M;
     return B200UDE_OK;
@@ -832,7 +853,7 @@ int32_t alloc_all(b200ude_bsde_handle *h)
     auto A = [&](void **p, size_t n) { return cudaMalloc(p, sizeof(R) * n) == cudaSuccess; };
     const size_t N = h->desc.n_steps;
     bool ok = A(&h->theta, h->P) && A(&h->grad, h->P) && A(&h->adam_m, h->P) && A(&h->adam_v, h->P) && A(&h->x0, d) && A(&h->u, M) &&
-              A(&h->IN, (N + 1) * (d + 2) * M) && A(&h->H[0], N * (hl + 1) * M) && A(&h->H[1], N * (hl + 1) * M) && A(&h->H[2], N * (hl + 1) * M) &&
+              A(&h->IN, (N + 1) * (d + 2) * M) && A(&h->H[0], N * (size_t)h->ldh * M) && A(&h->H[1], N * (size_t)h->ldh * M) && A(&h->H[2], N * (size_t)h->ldh * M) &&
               A(&h->Z, N * d * M) && A(&h->Zb, N * d * M) && A(&h->C[0], N * hl * M) && A(&h->C[1], N * hl * M) && A(&h->C[2], N * hl * M) && A(&h->r2, M) &&
               A(&h->ubar, M) && A(&h->ones, M) && A(&h->hu[0], hl) &&
               A(&h->hu[1], hl) && A(&h->cu_[0], hl) && A(&h->cu_[1], hl) && A(&h->scal, 4);
@@ -922,7 +943,7 @@ int32_t b200ude_bsde_create(const b200ude_bsde_desc *d, b200ude_bsde_handle **ou
     b200ude_bsde_handle *h = new (std::nothrow) b200ude_bsde_handle();
     if (!h) return bfail(nullptr, B200UDE_ENOMEM, "bsde_create: out of host memory");
     h->desc = *d;
-    h->d = d->dim; h->hls = d->hidden; h->f64 = d->dtype == B200UDE_F64; h->cap = d->max_paths;
+    h->d = d->dim; h->hls = d->hidden; h->ldh = (d->hidden + 2) & ~1; h->f64 = d->dtype == B200UDE_F64; h->cap = d->max_paths;
     const int wu[4] = {d->dim, d->hidden, d->hidden, 1}, wz[5] = {d->dim + 1, d->hidden, d->hidden, d->hidden, d->dim};
     h->nu = make_net(wu, 3, 0);
     h->nz = make_net(wz, 4, h->nu.P);
