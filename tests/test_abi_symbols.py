@@ -102,3 +102,24 @@ def test_ctypes_mirrors_have_the_sizes_the_c_compiler_gives_the_header(tmp_path)
     D, A = _lib.Desc, _lib.Adam
     want = [C.sizeof(D), D.consts.offset, D.loss_weights.offset, D.max_trajectories.offset, D.max_steps.offset, C.sizeof(A), A.l2_reg.offset]
     assert got == want, (got, want)
+
+
+def test_bsde_desc_layout_and_no_cpu_fallback(libpath):
+    """Terminal-PDE path: a wrong ctypes mirror of b200ude_bsde_desc is rejected (EINVAL), bad arguments are usage errors, and without a
+    CUDA device create fails with ENODEVICE after validating the descriptor -- there is no CPU path behind b200ude_bsde_*."""
+    import torch
+    from universal_differential_equations_b200 import _lib
+    L = _lib.lib()
+    x0 = (C.c_double * 4)(0.0, 0.0, 0.0, 0.0)
+    d = _lib.BsdeDesc(struct_size=C.sizeof(_lib.BsdeDesc) + 8, device=0, dtype=_lib.F64, dim=4, hidden=8, n_steps=5, T=1.0, lam=1.0, sigma=1.4,
+                      g_a=0.5, g_b=0.5, x0=x0, max_paths=16)
+    h = C.c_void_p()
+    assert L.b200ude_bsde_create(C.byref(d), C.byref(h)) == _lib.EINVAL and b"struct_size" in L.b200ude_bsde_last_error(None)
+    d.struct_size = C.sizeof(_lib.BsdeDesc)
+    d.n_steps = 0
+    assert L.b200ude_bsde_create(C.byref(d), C.byref(h)) == _lib.EINVAL
+    d.n_steps = 5
+    if not torch.cuda.is_available():
+        assert L.b200ude_bsde_create(C.byref(d), C.byref(h)) == _lib.ENODEVICE and not h.value
+    assert L.b200ude_bsde_num_params(None) == 0
+    assert L.b200ude_bsde_set_params(None, None, 0, _lib.HOST) == _lib.EINVAL
