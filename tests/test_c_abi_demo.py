@@ -22,6 +22,50 @@ def _build(tmp_path):
     return exe
 
 
+def _build_bsde(tmp_path):
+    from universal_differential_equations_b200 import _lib
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    obj, exe = str(tmp_path / "bsde_demo.o"), str(tmp_path / "bsde_demo")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           "-c", os.path.join(ROOT, "examples", "c_abi_bsde_demo.c"), "-o", obj])
+    subprocess.check_call(["gcc", "-o", exe, obj, "-L", CSRC, "-lb200ude", f"-Wl,-rpath,{CSRC}"])
+    return exe
+
+
+def _write_bsde_inputs(path):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hjb_small.npz"))
+    with open(path, "wb") as f:
+        f.write(struct.pack("iiiiQ", int(g["d"]), int(g["hls"]), int(g["N"]), int(g["M"]), int(g["seed"])))
+        f.write(np.asarray(g["x0"], np.float64).tobytes()); f.write(np.asarray(g["theta"], np.float64).tobytes())
+    return g
+
+
+def test_c_bsde_demo_compiles_links_and_fails_loudly_without_a_device(tmp_path):
+    import torch
+    exe = _build_bsde(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the gpu-marked test runs the demo")
+    _write_bsde_inputs(str(tmp_path / "in.bin"))
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "b200ude_bsde_create failed (-5)" in r.stderr and not os.path.exists(tmp_path / "out.bin")
+
+
+@pytest.mark.gpu
+def test_c_bsde_demo_matches_the_frozen_vectors_on_the_gpu(tmp_path):
+    """C99 -> libb200ude.so -> GPU against tests/golden/hjb_small.npz (no Python, torch or oracle in the loop)."""
+    exe = _build_bsde(tmp_path)
+    g = _write_bsde_inputs(str(tmp_path / "in.bin"))
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = np.frombuffer(open(tmp_path / "out.bin", "rb").read(), np.float64)
+    P = g["theta"].size
+    loss, u0, grad, after = raw[0], raw[1], raw[2:2 + P], raw[2 + P:]
+    assert abs(loss - float(g["loss"])) <= 1e-10 * abs(loss) and abs(u0 - float(g["u0"])) <= 1e-10
+    assert np.linalg.norm(grad - g["grad"]) <= 1e-9 * np.linalg.norm(g["grad"])
+    assert after[2] < after[0] < loss        # three ADAM(0.03) iterations lower the loss on the same paths
+
+
 def _write_inputs(path, N, n_steps=30, dt=0.1):
     from helpers import glorot_theta, synthetic_ensemble
     theta = glorot_theta((2, 32, 32, 2), seed=1)
