@@ -87,7 +87,7 @@ def test_f32_loss_gradient_vs_oracle():
     d, hls, M, N = 100, 110, 100, 20
     prob, alg = _problem(ude, d, hls)
     theta = bo.init_params(d, hls, seed=0).astype(np.float32)
-    s = ude.BSDESolver(prob, alg, N, M, dtype=torch.float32)
+    s = ude.BSDESolver(prob, alg, N, M, dtype=torch.float32, arithmetic=torch.float32)   # the fp32 library-GEMM path of the ABI
     s.set_params(theta)
     loss, g, u0 = s.loss_gradient(M, seed=1)
     lo, go, u0o = bo.loss_and_grad(theta.astype(np.float64), d, hls, np.zeros(d), 1.0, N, M, seed=1)
@@ -95,6 +95,45 @@ def test_f32_loss_gradient_vs_oracle():
     print(f"bsde fp32: loss {loss:.6f} vs {lo:.6f}, grad rel-L2 {rel:.2e}")
     assert abs(loss - lo) <= 2e-4 * abs(lo)
     assert rel <= 2e-3
+    s.close()
+
+
+def test_f32_caller_gets_double_arithmetic_by_default():
+    """dtype=float32 (the script's precision): parameters / results are float32, the device computes on the fused fp64 sweeps."""
+    ude = _ude()
+    d, hls, M, N = 100, 110, 64, 10
+    prob, alg = _problem(ude, d, hls)
+    theta = bo.init_params(d, hls, seed=0).astype(np.float32)
+    s = ude.BSDESolver(prob, alg, N, M, dtype=torch.float32)
+    assert s.dtype == torch.float64 and s.io_dtype == torch.float32
+    s.set_params(theta)
+    loss, g, _ = s.loss_gradient(M, seed=1)
+    lo, go, _ = bo.loss_and_grad(theta.astype(np.float64), d, hls, np.zeros(d), 1.0, N, M, seed=1)
+    assert g.dtype == torch.float32 and s.get_params().dtype == np.float32
+    assert abs(loss - lo) <= 1e-9 * abs(lo)
+    assert np.linalg.norm(g.cpu().numpy() - go) <= 2e-7 * np.linalg.norm(go)      # rounding of the result to float32 only
+    s.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_wide_network_runs_on_the_library_gemm_path(dtype):
+    """hidden > 111: no fused sweeps; cuBLAS GEMMs with the hand-written kernels between them, both precisions."""
+    ude = _ude()
+    d, hls, M, N = 6, 120, 40, 4
+    rng = np.random.default_rng(3)
+    x0 = 0.2 * rng.standard_normal(d)
+    prob, alg = _problem(ude, d, hls, x0)
+    theta = bo.init_params(d, hls, seed=5) + 0.02 * rng.standard_normal(sum(bo.num_params(d, hls)))
+    s = ude.BSDESolver(prob, alg, N, M, dtype=dtype)
+    assert s.dtype == dtype
+    s.set_params(theta)
+    loss, g, u0 = s.loss_gradient(M, seed=3)
+    lo, go, u0o = bo.loss_and_grad(theta if dtype == torch.float64 else theta.astype(np.float32).astype(np.float64), d, hls, x0, 1.0, N, M, seed=3)
+    tol_l, tol_g = (1e-10, 1e-9) if dtype == torch.float64 else (2e-4, 2e-3)
+    assert abs(loss - lo) <= tol_l * abs(lo) and np.linalg.norm(g.cpu().numpy().astype(np.float64) - go) <= tol_g * np.linalg.norm(go)
+    losses, _ = s.train_adam(ude.ADAM(0.03), M, 4, seed0=3)          # the on-device loop of this path; slot 0 = the loss just checked
+    lh = losses.cpu().numpy().astype(np.float64)
+    assert abs(lh[0] - lo) <= tol_l * abs(lo) and np.isfinite(lh).all()
     s.close()
 
 

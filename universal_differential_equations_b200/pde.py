@@ -89,7 +89,10 @@ def initial_params_pde(pdealg: NNPDENS, rng: Optional[np.random.Generator] = Non
 class BSDESolver:
     """Owns one b200ude_bsde handle."""
 
-    def __init__(self, prob: TerminalPDEProblem, pdealg: NNPDENS, n_steps: int, max_paths: int, device=0, dtype=torch.float32):
+    def __init__(self, prob: TerminalPDEProblem, pdealg: NNPDENS, n_steps: int, max_paths: int, device=0, dtype=torch.float32, arithmetic=None):
+        """dtype: element type of the parameters / results the caller sees.  arithmetic: element type the device computes in; by default
+        float64 whenever the fused fp64 sweeps apply (widths <= 110 / 111) -- they are faster than the fp32 library-GEMM path and the
+        float32 caller simply gets correctly rounded double results -- else dtype.  arithmetic=torch.float32 forces the fp32 path."""
         d = len(prob.x0)
         wu, wz = _widths(pdealg.u0), _widths(pdealg.sigmaT_grad_u)
         hls = wu[1]
@@ -101,6 +104,10 @@ class BSDESolver:
         if float(prob.tspan[0]) != 0.0:
             raise ValueError("tspan must start at 0")
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.io_dtype = dtype
+        if arithmetic is None:
+            arithmetic = torch.float64 if (d <= 110 and hls <= 111) else dtype
+        dtype = arithmetic
         self.dtype = dtype
         self.np_dtype = np.float64 if dtype == torch.float64 else np.float32
         self.d, self.hls, self.n_steps = d, hls, n_steps
@@ -133,7 +140,7 @@ class BSDESolver:
     def get_params(self) -> np.ndarray:
         a = np.empty(self.P, self.np_dtype)
         _lib.check_bsde(self._h, self._L.b200ude_bsde_get_params(self._h, a.ctypes.data, a.size, _lib.HOST))
-        return a
+        return a.astype(np.float64 if self.io_dtype == torch.float64 else np.float32, copy=False)
 
     def loss_gradient(self, n_paths, seed, path_offset=0, total_paths=0):
         """(loss, grad [P] device tensor, u0(x0)) at the handle's theta."""
@@ -142,7 +149,7 @@ class BSDESolver:
         _lib.check_bsde(self._h, self._L.b200ude_bsde_loss_gradient(self._h, n_paths, seed, path_offset, total_paths, out.data_ptr(), grad.data_ptr(),
                                                                     out.data_ptr() + out.element_size()))
         o = out.cpu()
-        return float(o[0]), grad, float(o[1])
+        return float(o[0]), grad.to(self.io_dtype), float(o[1])
 
     def last_train_ms(self) -> float:
         return float(self._L.b200ude_bsde_last_train_ms(self._h))
@@ -167,7 +174,7 @@ class BSDESolver:
         hist = torch.empty(2, iters, device=self.device, dtype=self.dtype)
         a = self._adam(opt)
         _lib.check_bsde(self._h, self._L.b200ude_bsde_train_adam(self._h, C.byref(a), n_paths, iters, seed0, hist[0].data_ptr(), hist[1].data_ptr()))
-        return hist[0], hist[1]
+        return hist[0].to(self.io_dtype), hist[1].to(self.io_dtype)
 
 
 def solve(prob: TerminalPDEProblem, pdealg: NNPDENS, *, verbose=False, maxiters=500, trajectories=100, alg=None, dt=None, theta0=None, seed=1,
