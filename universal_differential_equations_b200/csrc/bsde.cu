@@ -304,6 +304,7 @@ struct SlabRing {
     const double *src;
     long total, idx;      // slabs of this CTA's stream; index of the slab being consumed
     int n_slabs, nwarps;  // slabs per round (the stream repeats round after round)
+    int depth;            // buffers in use (<= FRING)
     int cb, cph;          // buffer and barrier phase of the slab being consumed
     __device__ __forceinline__ void issue(long i, int b) const   // one thread: slab i of the stream -> buffer b
     {
@@ -325,10 +326,10 @@ struct SlabRing {
         if (lane == 0) {   // (__syncwarp above orders the other lanes' reads of the slab before this)
             if (atomicAdd(&sh->done[cb], 1) == nwarps - 1) {
                 sh->done[cb] = 0;
-                issue(idx + FRING, cb);
+                issue(idx + depth, cb);
             }
         }
-        cb = cb == FRING - 1 ? 0 : cb + 1;
+        cb = cb == depth - 1 ? 0 : cb + 1;
         if (cb == 0) cph ^= 1;
         ++idx;
     }
@@ -355,10 +356,12 @@ __device__ __forceinline__ void slab_mma(const double *in, const SlabRing &ring,
     }
 }
 // shared-memory carve-up: [FRING slabs][per warp: one activation buffer of 8 rows, updated in place][FRING mbarriers][SlabShared]
-__device__ __forceinline__ void fused_setup(double *fsm, int nwarps, SlabRing &ring, const double *src, int n_slabs, long total)
+__device__ __forceinline__ void fused_setup(double *fsm, int nwarps, SlabRing &ring, const double *src, int n_slabs, long total, int depth = FRING,
+                                            int act_rows = 0)
 {
     ring.base = fsm;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + FRING * FSLAB + (size_t)nwarps * 8 * FLD);
+    ring.depth = depth;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + depth * FSLAB + (size_t)(act_rows ? act_rows : nwarps * 8) * FLD);
     ring.bar0 = (uint32_t)__cvta_generic_to_shared(bars);
     ring.sh = reinterpret_cast<SlabShared *>(bars + FRING);
     ring.src = src; ring.n_slabs = n_slabs; ring.total = total; ring.idx = 0; ring.nwarps = nwarps;
@@ -373,8 +376,7 @@ __device__ __forceinline__ void fused_setup(double *fsm, int nwarps, SlabRing &r
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < FRING; ++i) ring.issue(i, i);
+        for (int i = 0; i < depth; ++i) ring.issue(i, i);
     }
 }
 
@@ -490,6 +492,165 @@ __global__ void __launch_bounds__(32 * FWF, 3) k_fused_forward(const FusedArgs a
     nn += __shfl_xor_sync(0xffffffffu, nn, 2);
     if (live && c == 0) {
         const double res = log(a.ga + a.gb * nn) - u;
+        a.u[path] = u;
+        a.r2[path] = res * res;
+        a.ubar[path] = -2.0 * res * a.inv_total;
+    }
+}
+
+// The forward sweep with a path tile shared by TWO warps, each owning half of a layer's unit tiles: twice as many warps on the same
+// DMMA work (1 250 tiles of 8 paths are only 2.1 warps per scheduler, too few to cover each warp's own non-DMMA phases), finer balance.
+// The pair meets at a named barrier after every layer (activation rows, relu' bits) and after the Euler-Maruyama update (the two
+// halves of |z|^2 and z . dW); the activation rows are double-buffered because one warp's output units are the other's inputs.
+constexpr int FPW = 10;        // warps per CTA: five pairs, two CTAs per SM
+constexpr int FHT = FT / 2;    // unit tiles per warp
+constexpr int FP_DEPTH = 2;    // slab ring depth of this kernel (shared memory: 2 slabs + 5 pairs x 2 x 8 rows = 104 KB per CTA)
+struct PairExch {
+    double zz[2][8], zw[2][8], nn[2][8];
+    uint32_t bits[2][2][32];   // [layer parity][half][lane]
+};
+__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+__device__ __forceinline__ void slab_mma_half(const double *in, const SlabRing &ring, int k0, int r, int c, int uoff, double (&acc)[FHT][2])
+{
+    ring.wait_cur();
+    const double *wp = ring.cur() + c * FLD + r + uoff;
+    const double *ap = in + r * FLD + k0 + c;
+    double bv[FHT];
+#pragma unroll
+    for (int nt = 0; nt < FHT; ++nt) bv[nt] = wp[8 * nt];
+#pragma unroll
+    for (int ks = 0; ks < FSR / 4; ++ks) {
+        const double av = ap[4 * ks];
+#pragma unroll
+        for (int nt = 0; nt < FHT; ++nt) {
+            dmma(acc[nt], av, bv[nt]);
+            if (ks < FSR / 4 - 1) bv[nt] = wp[(ks + 1) * 4 * FLD + 8 * nt];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * FPW, 2) k_fused_forward2(const FusedArgs a)
+{
+    extern __shared__ __align__(16) double fsm[];
+    constexpr int NP = FPW / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+    const int pair = warp >> 1, half = warp & 1, uoff = 8 * FHT * half;
+    SlabRing ring;
+    fused_setup(fsm, FPW, ring, a.slabs, a.n_f, (long)a.n_f * a.N, FP_DEPTH, NP * 2 * 8);
+    double *in = fsm + FP_DEPTH * FSLAB + (size_t)pair * 2 * 8 * FLD, *out = in + 8 * FLD;
+    PairExch *ex = reinterpret_cast<PairExch *>(fsm + FP_DEPTH * FSLAB + (size_t)NP * 2 * 8 * FLD + FRING + (sizeof(SlabShared) + 7) / 8) + pair;
+    const int path = (blockIdx.x * NP + pair) * 8 + r;
+    const bool live = path < a.M;
+    const size_t pc = (size_t)(live ? path : a.M - 1);
+    const int d = a.d, hl = a.hl;
+    double u = *a.u0;
+    const size_t s_in = (size_t)(d + 2) * a.M, s_h = (size_t)a.ldh * a.M, s_z = (size_t)d * a.M;
+    const bool even_d = (d & 1) == 0;
+    const int ones_half = hl >= 8 * FHT ? 1 : 0;
+    double X[FHT][2];   // this warp's components of the pair's paths
+#pragma unroll
+    for (int nt = 0; nt < FHT; ++nt) {
+        const int m = uoff + 8 * nt + 2 * c;
+        X[nt][0] = m < d ? a.x0[m] : 0.0;
+        X[nt][1] = m + 1 < d ? a.x0[m + 1] : 0.0;
+    }
+    for (int n = 0; n <= a.N; ++n) {
+        double *inx = a.IN + n * s_in + pc * (d + 2);
+#pragma unroll
+        for (int nt = 0; nt < FHT; ++nt) {
+            const int m = uoff + 8 * nt + 2 * c;
+            if (live && even_d && m < d) *reinterpret_cast<double2 *>(inx + m) = make_double2(X[nt][0], X[nt][1]);
+            else {
+                if (live && m < d) inx[m] = X[nt][0];
+                if (live && m + 1 < d) inx[m + 1] = X[nt][1];
+            }
+            *reinterpret_cast<double2 *>(in + r * FLD + m) = make_double2(X[nt][0], X[nt][1]);
+        }
+        if (n == a.N) break;
+        if (half == 0) {   // the step's Brownian increments towards L2 while the layers run
+            const int p0 = path - r, rows = p0 < a.M ? (a.M - p0 < 8 ? a.M - p0 : 8) : 0;
+            const char *w0 = reinterpret_cast<const char *>(a.dW + n * s_z + (size_t)(rows ? p0 : 0) * d);
+            const size_t bytes = (size_t)rows * d * sizeof(double);
+            for (size_t o = (size_t)lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + o));
+        }
+        pair_sync(pair);
+        if (half == 0 && c == 0) { in[r * FLD + d] = n * a.dt; in[r * FLD + d + 1] = 1.0; }
+        pair_sync(pair);
+        double acc[FHT][2];
+#pragma unroll 1
+        for (int i = 0; i < a.n_f; ++i) {
+            const int l = a.f_layer[i];
+            if (a.f_k0[i] == 0) {
+#pragma unroll
+                for (int nt = 0; nt < FHT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+            }
+            slab_mma_half(in, ring, a.f_k0[i], r, c, uoff, acc);
+            ring.release(lane);
+            if (!a.f_last[i] || l == 3) continue;
+            double *hp = a.H[l] + n * s_h + pc * a.ldh;
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int nt = 0; nt < FHT; ++nt) {
+                const int m = uoff + 8 * nt + 2 * c;
+                const bool neg0 = !(acc[nt][0] >= 0.0), neg1 = !(acc[nt][1] >= 0.0);
+                const double h0 = neg0 ? -0.0 : acc[nt][0], h1 = neg1 ? -0.0 : acc[nt][1];
+                bits |= (neg0 ? 1u : 0u) << (2 * nt) | (neg1 ? 1u : 0u) << (2 * nt + 1);
+                *reinterpret_cast<double2 *>(out + r * FLD + m) = make_double2(h0, h1);
+                if (live && m + 1 < hl) *reinterpret_cast<double2 *>(hp + m) = make_double2(h0, h1);   // ldh is even
+                else if (live && m < hl) hp[m] = h0;
+            }
+            ex->bits[l & 1][half][lane] = bits;
+            if (half == ones_half) {
+                __syncwarp();
+                if (c == 0) out[r * FLD + hl] = 1.0;   // the ones row (the padded weights are zero beyond it)
+            }
+            pair_sync(pair);
+            if (half == 0 && live) a.mask[((size_t)(n * 3 + l) * a.M + pc) * 4 + c] = bits | (ex->bits[l & 1][1][lane] << (2 * FHT));
+            double *t = in; in = out; out = t;
+        }
+        // acc = this warp's components of z_n: Euler-Maruyama update; the pair adds its halves of |z|^2 and z . dW
+        double zz = 0.0, zw = 0.0;
+        double *zp = a.Z + n * s_z + pc * d;
+        const double *wn = a.dW + n * s_z + pc * d;
+#pragma unroll
+        for (int nt = 0; nt < FHT; ++nt) {
+            const int m = uoff + 8 * nt + 2 * c;
+            if (even_d && m < d) {
+                const double2 dw = *reinterpret_cast<const double2 *>(wn + m);
+                const double z0 = acc[nt][0], z1 = acc[nt][1];
+                zz = fma(z0, z0, fma(z1, z1, zz)); zw = fma(z0, dw.x, fma(z1, dw.y, zw));
+                X[nt][0] += a.s * dw.x; X[nt][1] += a.s * dw.y;
+                if (live) *reinterpret_cast<double2 *>(zp + m) = make_double2(2.0 * a.lam * z0 * a.dt + dw.x, 2.0 * a.lam * z1 * a.dt + dw.y);
+            } else if (m < d) {
+                const double dw0 = wn[m], z0 = acc[nt][0];
+                zz = fma(z0, z0, zz); zw = fma(z0, dw0, zw);
+                X[nt][0] += a.s * dw0;
+                if (live) zp[m] = 2.0 * a.lam * z0 * a.dt + dw0;
+                if (m + 1 < d) {
+                    const double dw1 = wn[m + 1], z1 = acc[nt][1];
+                    zz = fma(z1, z1, zz); zw = fma(z1, dw1, zw);
+                    X[nt][1] += a.s * dw1;
+                    if (live) zp[m + 1] = 2.0 * a.lam * z1 * a.dt + dw1;
+                }
+            }
+        }
+        zz += __shfl_xor_sync(0xffffffffu, zz, 1); zw += __shfl_xor_sync(0xffffffffu, zw, 1);
+        zz += __shfl_xor_sync(0xffffffffu, zz, 2); zw += __shfl_xor_sync(0xffffffffu, zw, 2);
+        if (c == 0) { ex->zz[half][r] = zz; ex->zw[half][r] = zw; }
+        pair_sync(pair);
+        u += a.lam * (ex->zz[0][r] + ex->zz[1][r]) * a.dt + (ex->zw[0][r] + ex->zw[1][r]);
+        // (the next writes to ex->zz / zw come a whole step later, behind several pair barriers)
+    }
+    double nn = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < FHT; ++nt) nn = fma(X[nt][0], X[nt][0], fma(X[nt][1], X[nt][1], nn));
+    nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+    nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+    if (c == 0) ex->nn[half][r] = nn;
+    pair_sync(pair);
+    if (live && c == 0 && half == 0) {
+        const double res = log(a.ga + a.gb * (ex->nn[0][r] + ex->nn[1][r])) - u;
         a.u[path] = u;
         a.r2[path] = res * res;
         a.ubar[path] = -2.0 * res * a.inv_total;
@@ -656,6 +817,7 @@ struct b200ude_bsde_handle {
     void *dW = nullptr;       // Brownian increments of the iteration (fused sweeps)
     FusedArgs fa;             // slab tables (the pointers are filled per call)
     int sm_count = 148;
+    bool fwd_pairs = true;    // forward sweep with two warps per path tile (k_fused_forward2)
     void *hu[3] = {}, *cu_[3] = {};   // u0 net (single column): activations / cotangents
     void *scal = nullptr;             // [0] loss, [1] sum ubar, [2] u0(x0)
     int *t_dev = nullptr;
@@ -731,6 +893,8 @@ int32_t net_backward(b200ude_bsde_handle *h, const Net &n, const R *in, R *const
 
 inline size_t fused_smem(int warps) { return ((size_t)FRING * FSLAB + (size_t)warps * 8 * FLD) * sizeof(double) + 8 * FRING + sizeof(SlabShared); }
 
+inline size_t fused_smem2() { return ((size_t)FP_DEPTH * FSLAB + (size_t)(FPW / 2) * 2 * 8 * FLD) * sizeof(double) + 8 * FRING + ((sizeof(SlabShared) + 7) / 8) * 8 + (FPW / 2) * sizeof(PairExch); }
+
 // the fused fp64 path of one iteration: operand slabs, forward sweep (+ residual), loss sums, cotangent sweep
 int32_t fused_sweeps(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_total, cudaStream_t st)
 {
@@ -755,7 +919,8 @@ int32_t fused_sweeps(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_t
     const int tiles = (M + 7) / 8;
     const size_t smem = fused_smem(FWPC);
     if (h->time_kernels) cudaEventRecord(h->kev[0], st);
-    k_fused_forward<<<(tiles + FWF - 1) / FWF, 32 * FWF, fused_smem(FWF), st>>>(a);
+    if (h->fwd_pairs) k_fused_forward2<<<(tiles + FPW / 2 - 1) / (FPW / 2), 32 * FPW, fused_smem2(), st>>>(a);
+    else k_fused_forward<<<(tiles + FWF - 1) / FWF, 32 * FWF, fused_smem(FWF), st>>>(a);
     if (h->time_kernels) cudaEventRecord(h->kev[1], st);
     k_sum2<double><<<1, 256, 0, st>>>((const double *)h->r2, (const double *)h->ubar, M, inv_total, (double *)h->scal, (double *)h->scal + 1);
     if (h->time_kernels) cudaEventRecord(h->kev[2], st);
@@ -973,11 +1138,14 @@ int32_t b200ude_bsde_create(const b200ude_bsde_desc *d, b200ude_bsde_handle **ou
                 fa.b_last[i] = (unsigned char)(k0 + FSR >= h->nz.widths[l + 1]);
             }
         h->sm_count = prop.multiProcessorCount;
+        const char *penv = getenv("B200UDE_BSDE_PAIRS");
+        h->fwd_pairs = !(penv && penv[0] == '0');
         const int smem = (int)fused_smem(FWF);
         if (cudaMalloc(&h->packed, (size_t)(fa.n_f + fa.n_b) * FSLAB * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->mask, (size_t)d->n_steps * 3 * d->max_paths * 4 * sizeof(uint32_t)) == cudaSuccess &&
             cudaMalloc(&h->dW, (size_t)d->n_steps * d->dim * d->max_paths * sizeof(double)) == cudaSuccess &&
             cudaFuncSetAttribute(k_fused_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+            cudaFuncSetAttribute(k_fused_forward2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem2()) == cudaSuccess &&
             cudaFuncSetAttribute(k_fused_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess)
             h->fused = true;
         else
