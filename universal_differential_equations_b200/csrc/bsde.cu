@@ -323,8 +323,10 @@ struct SlabRing {
     __device__ __forceinline__ void release(int lane)
     {
         __syncwarp();
-        if (lane == 0) {   // (__syncwarp above orders the other lanes' reads of the slab before this)
+        if (lane == 0) {   // release (this warp's reads of the slab, gathered by __syncwarp) ... acquire (everybody's) around the counter
+            __threadfence_block();
             if (atomicAdd(&sh->done[cb], 1) == nwarps - 1) {
+                __threadfence_block();
                 sh->done[cb] = 0;
                 issue(idx + depth, cb);
             }
