@@ -403,7 +403,7 @@ def main_hjb(a):
         return
     fl = hjb_flops(d, hls, n_steps) * m
     ms_iter = total_ms / a.steps
-    # dominant kernel: the fused forward sweep (csrc/bsde.cu::k_fused_forward); its time from CUDA events on the handle's stream,
+    # dominant kernel: the fused forward sweep (csrc/bsde.cu::k_fused_forward2); its time from CUDA events on the handle's stream,
     # averaged over eager (non-graph) iterations of the same workload
     sweeps = []
     for i in range(5):
@@ -436,7 +436,7 @@ def main_hjb(a):
         "library_launches": (sum(1 for k in names if "::k_" not in k) if names else 0) * a.steps,
         "kernels_per_step": sorted(set(names)) if names else None, "kernels_source": names_src,
         "clocks": clk.summary(),
-        "roofline": {"kernel": "k_fused_forward (fused DMMA forward sweep: 4 layers x 20 steps + Euler-Maruyama, csrc/bsde.cu)", "bound": "tensor",
+        "roofline": {"kernel": "k_fused_forward2 (fused DMMA forward sweep: 4 layers x 20 steps + Euler-Maruyama, two warps per 8-path tile, csrc/bsde.cu)", "bound": "tensor",
                      "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak, "traffic": None,
                      "peak_source": "fp64 tensor pipe: DMMA.8x8x4 issue-rate microbenchmark (tools/microbench/dmma.cu, profiles/r02_dmma_microbench.txt); "
                                     f"torch.matmul fp64 4096^3 in this run: {peak:.1f} TFLOP/s",

@@ -156,6 +156,20 @@ def test_f64_adam_history_vs_oracle():
     s.close()
 
 
+def test_f64_repeat_is_bitwise_identical():
+    """Same parameters, seed and batch -> the same bits (fixed-order sums; the slab ring and the two-warp tiles change timing, not order)."""
+    ude = _ude()
+    d, hls, M, N = 100, 110, 333, 7
+    prob, alg = _problem(ude, d, hls)
+    s = ude.BSDESolver(prob, alg, N, M, dtype=torch.float64)
+    s.set_params(bo.init_params(d, hls, seed=9))
+    l1, g1, u1 = s.loss_gradient(M, seed=4)
+    s.loss_gradient(M, seed=5)
+    l2, g2, u2 = s.loss_gradient(M, seed=4)
+    assert l1 == l2 and u1 == u2 and torch.equal(g1, g2)
+    s.close()
+
+
 def test_path_shards_add_up():
     """Multi-GPU sharding rule (path_offset / total_paths): two half batches give the whole batch's loss and gradient."""
     ude = _ude()
