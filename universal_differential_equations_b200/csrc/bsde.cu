@@ -755,6 +755,108 @@ __global__ void k_pack_slabs(const double *__restrict__ theta, double *dst, cons
     dst[(size_t)sl * FSLAB + i] = v;
 }
 
+// ---- fused weight-gradient products (fp64) ---------------------------------------------------------------------------------------
+// [dW | db] of layer l = sum over all (step, path) rows k of cot_l[k][j] * act_l[k][i] -- a 112 x 112 x (steps x paths) product whose long
+// dimension is the tape.  One launch for the four layers: blockIdx.y = layer, blockIdx.x = a contiguous range of 16-row chunks of the
+// tape; warp w of a CTA owns unit tile w of the layer's outputs (8 values of j) against all 14 input tiles (28 accumulator registers
+// x 2), so a k-step is 1 + 14 fragment loads for 14 DMMAs.  Both tapes stream through a four-stage ring of shared memory, every stage
+// filled by two TMA bulk copies (the tapes' rows are contiguous: a chunk is one block of memory) and released by its last reader.
+// Rows of a tape beyond a layer's width are the next path's data: they only reach output elements that are never stored.  Partial
+// sums per CTA, then a fixed-order reduction into the gradient in theta's layout.
+constexpr int WGW = FT;          // warps per CTA
+constexpr int WGR = 16;          // tape rows per chunk
+constexpr int WGD = 4;           // ring depth
+constexpr int WGLD = 120;        // row stride bound of a staged tape (>= the largest leading dimension in use: 116)
+constexpr int WGSTAGE = 2 * (WGR * WGLD + 16);   // doubles per stage: cot chunk + act chunk (+ slack for the over-read of the last row)
+struct WgradArgs {
+    const double *cot[4], *act[4];
+    int ldc[4], lda[4], nout[4], nact[4];
+    long K;                // rows of the tapes (steps x paths)
+    double *partial;       // [4][gridDim.x][FW * FW]
+};
+__global__ void __launch_bounds__(32 * WGW, 1) k_wgrad(const WgradArgs a)
+{
+    extern __shared__ __align__(16) double fsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+    const int l = blockIdx.y, ldc = a.ldc[l], lda = a.lda[l];
+    const double *cot = a.cot[l], *act = a.act[l];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + (size_t)WGD * WGSTAGE);
+    int *done = reinterpret_cast<int *>(bars + WGD);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    for (int i = threadIdx.x; i < WGD * WGSTAGE; i += blockDim.x) fsm[i] = 0.0;   // stale rows must be finite (they meet zero operands)
+    const long chunks = (a.K + WGR - 1) / WGR;
+    const long c_lo = chunks * blockIdx.x / gridDim.x, c_hi = chunks * (blockIdx.x + 1) / gridDim.x;
+    auto issue = [&](long ch, int b) {   // one thread: chunk ch of both tapes -> stage b
+        if (ch >= c_hi) return;
+        const long k0 = ch * WGR;
+        const int rows = (int)(a.K - k0 < WGR ? a.K - k0 : WGR);
+        const uint32_t br = bar0 + 8u * b, bytes_c = (uint32_t)(rows * ldc * 8), bytes_a = (uint32_t)(rows * lda * 8);
+        const uint32_t dc = (uint32_t)__cvta_generic_to_shared(fsm + (size_t)b * WGSTAGE), da = dc + (WGR * WGLD + 16) * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(br), "r"(bytes_c + bytes_a) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dc), "l"(cot + k0 * ldc), "r"(bytes_c), "r"(br) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(da), "l"(act + k0 * lda), "r"(bytes_a), "r"(br) : "memory");
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WGD; ++i) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * i)); done[i] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // (also: the zero fill is complete before any copy lands)
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill (generic proxy) before the bulk copies (async proxy)
+        for (int i = 0; i < WGD; ++i) issue(c_lo + i, i);
+    }
+    double acc[FT][2];
+#pragma unroll
+    for (int nt = 0; nt < FT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+    int b = 0, ph = 0;
+    for (long ch = c_lo; ch < c_hi; ++ch) {
+        mbar_wait(bar0 + 8u * b, (uint32_t)ph);
+        const double *sc = fsm + (size_t)b * WGSTAGE, *sa = sc + WGR * WGLD + 16;
+        const long k0 = ch * WGR;
+        const int rows = (int)(a.K - k0 < WGR ? a.K - k0 : WGR);
+        const double *ap = sc + c * ldc + 8 * warp + r, *bp = sa + c * lda + r;
+#pragma unroll
+        for (int ks = 0; ks < WGR / 4; ++ks) {
+            const double av = 4 * ks + c < rows ? ap[ks * 4 * ldc] : 0.0;   // rows past the tape's end contribute nothing
+            double bv[FT];
+#pragma unroll
+            for (int nt = 0; nt < FT; ++nt) bv[nt] = bp[ks * 4 * lda + 8 * nt];
+#pragma unroll
+            for (int nt = 0; nt < FT; ++nt) dmma(acc[nt], av, bv[nt]);
+        }
+        __syncwarp();
+        if (lane == 0) {   // release ... acquire around the reader counter; the last reader refills the stage
+            __threadfence_block();
+            if (atomicAdd(&done[b], 1) == WGW - 1) {
+                __threadfence_block();
+                done[b] = 0;
+                issue(ch + WGD, b);
+            }
+        }
+        b = b == WGD - 1 ? 0 : b + 1;
+        if (b == 0) ph ^= 1;
+    }
+    double *P = a.partial + ((size_t)l * gridDim.x + blockIdx.x) * (FW * FW);
+#pragma unroll
+    for (int nt = 0; nt < FT; ++nt) {
+        const int j = 8 * warp + r, i = 8 * nt + 2 * c;
+        P[(size_t)i * FW + j] = acc[nt][0];
+        P[(size_t)(i + 1) * FW + j] = acc[nt][1];
+    }
+}
+// grad[w_off_l + i * nout + j] = sum over the CTAs' partial sums, in a fixed order
+__global__ void k_wgrad_reduce(const double *__restrict__ partial, int splits, double *grad, const PackArgs q)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y;
+    if (e >= FW * FW) return;
+    const int i = e / FW, j = e % FW;
+    if (j >= q.nout[l] || i >= q.nin[l] + 1) return;
+    const double *p = partial + (size_t)l * splits * (FW * FW) + e;
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += p[(size_t)k * (FW * FW)];
+    grad[q.w_off[l] + (size_t)i * q.nout[l] + j] = s;
+}
+
 inline cublasStatus_t gemm(cublasHandle_t h, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k, const float *al, const float *A, int lda,
                            const float *B, int ldb, const float *be, float *C, int ldc)
 {
@@ -799,7 +901,8 @@ Net make_net(const int *widths, int n_layers, size_t base)
 struct b200ude_bsde_handle {
     b200ude_bsde_desc desc;
     int d = 0, hls = 0, P = 0;
-    int ldh = 0;   // leading dimension of the hidden-activation tapes: hls + 1 (the ones row) rounded up to even (16-byte columns in fp64)
+    int ldh = 0;   // leading dimension of the hidden-activation tapes: >= hls + 1 (the ones row), = 4 mod 16 (even: 16-byte columns in fp64;
+                   // conflict-free 8-byte fragment reads when a tape chunk is staged in shared memory with this row stride)
     bool f64 = true;
     size_t cap = 0;
     Net nu, nz;
@@ -820,6 +923,8 @@ struct b200ude_bsde_handle {
     FusedArgs fa;             // slab tables (the pointers are filled per call)
     int sm_count = 148;
     bool fwd_pairs = true;    // forward sweep with two warps per path tile (k_fused_forward2)
+    void *wg_partial = nullptr;   // per-CTA partial sums of the fused weight-gradient products (null: library GEMMs)
+    int wg_splits = 0;
     void *hu[3] = {}, *cu_[3] = {};   // u0 net (single column): activations / cotangents
     void *scal = nullptr;             // [0] loss, [1] sum ubar, [2] u0(x0)
     int *t_dev = nullptr;
@@ -896,6 +1001,8 @@ int32_t net_backward(b200ude_bsde_handle *h, const Net &n, const R *in, R *const
 inline size_t fused_smem(int warps) { return ((size_t)FRING * FSLAB + (size_t)warps * 8 * FLD) * sizeof(double) + 8 * FRING + sizeof(SlabShared); }
 
 inline size_t fused_smem2() { return ((size_t)FP_DEPTH * FSLAB + (size_t)(FPW / 2) * 2 * 8 * FLD) * sizeof(double) + 8 * FRING + ((sizeof(SlabShared) + 7) / 8) * 8 + (FPW / 2) * sizeof(PairExch); }
+
+inline size_t wgrad_smem() { return (size_t)WGD * WGSTAGE * sizeof(double) + 8 * WGD + 4 * WGD + 16; }
 
 // the fused fp64 path of one iteration: operand slabs, forward sweep (+ residual), loss sums, cotangent sweep
 int32_t fused_sweeps(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_total, cudaStream_t st)
@@ -987,13 +1094,32 @@ int32_t loss_gradient(b200ude_bsde_handle *h, int M, uint32_t path0, double inv_
             }
         }
     }
-    // [dW | db] of every layer in one GEMM over all steps: cot [out x (N M)] times augmented activation^T [(N M) x (in + 1)]
+    // [dW | db] of every layer over all steps at once: cot [out x (N M)] times augmented activation^T [(N M) x (in + 1)]
     R *g = (R *)h->grad;
     const int K = N * M;
-    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, d + 2, K, &one, C[0], hl, IN, d + 2, &zero, g + nz.w_off[0], hl));
-    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[1], hl, H[0], ldh, &zero, g + nz.w_off[1], hl));
-    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[2], hl, H[1], ldh, &zero, g + nz.w_off[2], hl));
-    BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, d, hl + 1, K, &one, Zb, d, H[2], ldh, &zero, g + nz.w_off[3], d));
+    bool wg_fused = false;
+    if constexpr (sizeof(R) == 8) wg_fused = fused && h->wg_partial != nullptr;
+    if (wg_fused) {
+        if constexpr (sizeof(R) == 8) {
+            WgradArgs w;
+            const double *cots[4] = {C[0], C[1], C[2], Zb}, *acts[4] = {IN, H[0], H[1], H[2]};
+            for (int l = 0; l < 4; ++l) {
+                w.cot[l] = cots[l]; w.act[l] = acts[l];
+                w.ldc[l] = l < 3 ? hl : d; w.lda[l] = l == 0 ? d + 2 : ldh;
+                w.nout[l] = nz.widths[l + 1]; w.nact[l] = nz.widths[l] + 1;
+            }
+            w.K = K; w.partial = (double *)h->wg_partial;
+            PackArgs q;
+            for (int l = 0; l < 4; ++l) { q.w_off[l] = nz.w_off[l]; q.nin[l] = nz.widths[l]; q.nout[l] = nz.widths[l + 1]; }
+            k_wgrad<<<dim3(h->wg_splits, 4), 32 * WGW, wgrad_smem(), st>>>(w);
+            k_wgrad_reduce<<<dim3(blocks((size_t)FW * FW), 4), 256, 0, st>>>((const double *)h->wg_partial, h->wg_splits, g, q);
+        }
+    } else {
+        BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, d + 2, K, &one, C[0], hl, IN, d + 2, &zero, g + nz.w_off[0], hl));
+        BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[1], hl, H[0], ldh, &zero, g + nz.w_off[1], hl));
+        BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, hl, hl + 1, K, &one, C[2], hl, H[1], ldh, &zero, g + nz.w_off[2], hl));
+        BS_BLAS(h, gemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, d, hl + 1, K, &one, Zb, d, H[2], ldh, &zero, g + nz.w_off[3], d));
+    }
     if (h->time_kernels) cudaEventRecord(h->kev[4], st);
     rc = net_backward<R>(h, h->nu, (const R *)h->x0, outs_u, cots_u, 1, st);   // cotangent of u0(x0) = sum of ubar (already in scal[1])
     if (rc) return rc;
@@ -1110,7 +1236,7 @@ int32_t b200ude_bsde_create(const b200ude_bsde_desc *d, b200ude_bsde_handle **ou
     b200ude_bsde_handle *h = new (std::nothrow) b200ude_bsde_handle();
     if (!h) return bfail(nullptr, B200UDE_ENOMEM, "bsde_create: out of host memory");
     h->desc = *d;
-    h->d = d->dim; h->hls = d->hidden; h->ldh = (d->hidden + 2) & ~1; h->f64 = d->dtype == B200UDE_F64; h->cap = d->max_paths;
+    h->d = d->dim; h->hls = d->hidden; h->ldh = ((d->hidden + 1 - 4 + 15) / 16) * 16 + 4; /* >= hidden + 1 (the ones row), = 4 mod 16 */ h->f64 = d->dtype == B200UDE_F64; h->cap = d->max_paths;
     const int wu[4] = {d->dim, d->hidden, d->hidden, 1}, wz[5] = {d->dim + 1, d->hidden, d->hidden, d->hidden, d->dim};
     h->nu = make_net(wu, 3, 0);
     h->nz = make_net(wz, 4, h->nu.P);
@@ -1142,6 +1268,16 @@ int32_t b200ude_bsde_create(const b200ude_bsde_desc *d, b200ude_bsde_handle **ou
         h->sm_count = prop.multiProcessorCount;
         const char *penv = getenv("B200UDE_BSDE_PAIRS");
         h->fwd_pairs = !(penv && penv[0] == '0');
+        const char *wenv = getenv("B200UDE_BSDE_WGRAD");
+        if (!(wenv && wenv[0] == '0') && d->dim % 2 == 0 && d->hidden % 2 == 0) {   // TMA chunks of the tapes: even leading dimensions
+            h->wg_splits = prop.multiProcessorCount / 4 > 0 ? prop.multiProcessorCount / 4 : 1;
+            if (cudaMalloc(&h->wg_partial, (size_t)4 * h->wg_splits * FW * FW * sizeof(double)) != cudaSuccess ||
+                cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem()) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(h->wg_partial);
+                h->wg_partial = nullptr;
+            }
+        }
         const int smem = (int)fused_smem(FWF);
         if (cudaMalloc(&h->packed, (size_t)(fa.n_f + fa.n_b) * FSLAB * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->mask, (size_t)d->n_steps * 3 * d->max_paths * 4 * sizeof(uint32_t)) == cudaSuccess &&
@@ -1176,7 +1312,7 @@ void b200ude_bsde_destroy(b200ude_bsde_handle *h)
 {
     if (!h) return;
     void *bufs[] = {h->theta, h->grad, h->adam_m, h->adam_v, h->x0, h->IN, h->u, h->H[0], h->H[1], h->H[2], h->Z, h->Zb, h->C[0], h->C[1], h->C[2],
-                    h->r2, h->ubar, h->ones, h->hu[0], h->hu[1], h->cu_[0], h->cu_[1], h->scal, h->t_dev, h->seed_dev, h->workspace, h->packed, h->mask, h->dW};
+                    h->r2, h->ubar, h->ones, h->hu[0], h->hu[1], h->cu_[0], h->cu_[1], h->scal, h->t_dev, h->seed_dev, h->workspace, h->packed, h->mask, h->dW, h->wg_partial};
     for (void *b : bufs) cudaFree(b);
     for (cudaEvent_t e : h->kev)
         if (e) cudaEventDestroy(e);
