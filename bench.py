@@ -441,8 +441,8 @@ def main_hjb(a):
                      "peak_source": "fp64 tensor pipe: DMMA.8x8x4 issue-rate microbenchmark (tools/microbench/dmma.cu, profiles/r02_dmma_microbench.txt); "
                                     f"torch.matmul fp64 4096^3 in this run: {peak:.1f} TFLOP/s",
                      "algorithmic_flop_per_path_step": 2.0 * mac_f, "kernel_ms": fwd_ms,
-                     "note": "share of the iteration: forward sweep / cotangent sweep / batched weight-gradient GEMMs (cuBLAS) in kernel_ms"},
-        "kernel_ms": {"forward_sweep": fwd_ms, "cotangent_sweep": bwd_ms, "weight_gradient_gemms": wg_ms, "iteration": ms_iter},
+                     "note": "share of the iteration: forward sweep / cotangent sweep / fused weight-gradient products in kernel_ms"},
+        "kernel_ms": {"forward_sweep": fwd_ms, "cotangent_sweep": bwd_ms, "weight_gradient_products": wg_ms, "iteration": ms_iter},
         "iteration_gemm_tflops": fl / (ms_iter * 1e-3) / 1e12,
         "cpu_baseline": cpu,
     }))
