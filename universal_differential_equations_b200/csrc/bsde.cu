@@ -7,17 +7,21 @@
 // NNPDENS [EXT NeuralNetDiffEq 1.1.0] integrates  dX = mu dt + sigma dW,  du = -f(X, u, z, p, t) dt + z . dW,  z = sigmaT_grad_u([X; t]),
 // u(0) = u0(x0), for `trajectories` paths and minimises mean (g(X_T) - u_T)^2 over both networks with ADAM; the answer is u0(x0).
 // Here, for the script's family  mu = 0, sigma = s I, f = -lambda |z|^2, g(X) = log(a + b |X|^2)  (Hamilton-Jacobi-Bellman):
-//   * all paths of an iteration advance together; the networks are [width x paths] column-major activations, so every layer is
-//     ONE library GEMM (cuBLAS: theta's vec(W) is already the column-major out x in matrix -- no repacking); everything between
-//     the GEMMs is hand-written: counter-based Brownian increments (Philox4x32-10 + Box-Muller, regenerated in the backward sweep
-//     instead of stored), the fused Euler-Maruyama update (one warp per path), bias + relu, the loss and its cotangents, ADAM;
+//   * all paths of an iteration advance together; the networks work on [width x paths] column-major activations (a path = a column), so
+//     theta's vec(W) is already the operand of every layer product -- no repacking of the reference's parameter vector;
+//   * fp64 (BASELINE's config 5), widths <= 112: hand-written DMMA kernels -- a fused forward sweep (all layers and all steps in one
+//     launch, two warps per 8-path tile, weights streamed through a TMA slab ring, relu / Euler-Maruyama / residual on the fragments),
+//     a fused cotangent sweep and a fused weight-gradient kernel (see "fused fp64 sweeps" below); Brownian increments from a
+//     counter-based generator (Philox4x32-10 + Box-Muller) in a separate parallel pass;
+//   * fp32, and wider networks: one library GEMM per layer (cuBLAS) with hand-written kernels between them (fused Euler-Maruyama
+//     with the increments regenerated in place, relu / masks, the loss and its cotangents);
 //   * the backward sweep is the exact reverse-mode derivative of the discretised solve (what Tracker computes through the SDE
 //     solver in the reference).  Nothing is recomputed: with 180 GB of HBM every step's activations and cotangents stay resident
 //     ((4 d + 6 hls) x paths x n_steps elements, 1.5 GB for the benchmark's 10 000 fp64 paths);
 //   * every activation matrix carries a constant row of ones below it, and theta stores a layer as vec(W) followed by b, i.e.
-//     the column-major out x (in + 1) matrix [W | b]: the forward GEMM over the augmented activations adds the bias for free,
-//     and ONE GEMM per layer over all steps at once (k = n_steps x paths) writes [dW | db] straight into the gradient in
-//     theta's layout -- no bias kernels, no per-step weight-gradient GEMMs, no split-K reductions per step;
+//     the column-major out x (in + 1) matrix [W | b]: the forward product over the augmented activations adds the bias for free,
+//     and ONE product per layer over all steps at once (k = n_steps x paths) writes [dW | db] straight into the gradient in
+//     theta's layout -- no bias kernels, no per-step weight-gradient products;
 //   * relu'(0) = 1 as Flux 0.9 / Tracker differentiate max(zero(x), x): the sign bit of a zero activation records the side;
 //   * fixed-step Euler-Maruyama (the script's LambaEM is EM with step-size control; for this family X is exact under EM and only
 //     the u-quadrature depends on dt);
