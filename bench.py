@@ -331,6 +331,7 @@ def main_hjb(a):
     def dist_step(i):
         # path shards: disjoint Philox path counters, mean over ALL paths; one all-reduce of [grad; loss]; identical ADAM update everywhere
         out = torch.empty(2, device=dev, dtype=torch.float64)
+        torch.cuda.current_stream().synchronize()      # the handle works on its own stream: torch's queued work on g_all / out first
         ude._lib.check_bsde(s._h, s._L.b200ude_bsde_loss_gradient(s._h, m, 1 + i, rank * m, world * m, out.data_ptr(), g_all.data_ptr(), None))
         g_all[s.P] = out[0]
         dist.all_reduce(g_all)

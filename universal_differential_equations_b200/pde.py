@@ -132,6 +132,7 @@ class BSDESolver:
     def set_params(self, theta):
         if isinstance(theta, torch.Tensor):
             t = theta.detach().to(self.device, self.dtype).contiguous()
+            self._fence()
             _lib.check_bsde(self._h, self._L.b200ude_bsde_set_params(self._h, t.data_ptr(), t.numel(), _lib.DEVICE))
         else:
             a = np.ascontiguousarray(theta, self.np_dtype)
@@ -142,10 +143,17 @@ class BSDESolver:
         _lib.check_bsde(self._h, self._L.b200ude_bsde_get_params(self._h, a.ctypes.data, a.size, _lib.HOST))
         return a.astype(np.float64 if self.io_dtype == torch.float64 else np.float32, copy=False)
 
+    def _fence(self):
+        """The b200ude_bsde_* calls run on the handle's own (non-blocking) stream and are synchronous to the host on return; work torch has
+        queued on ITS stream for tensors handed to them (a gradient coming out of an all-reduce, recycled allocator blocks) must be
+        finished first."""
+        torch.cuda.current_stream(self.device).synchronize()
+
     def loss_gradient(self, n_paths, seed, path_offset=0, total_paths=0):
         """(loss, grad [P] device tensor, u0(x0)) at the handle's theta."""
         out = torch.empty(2, device=self.device, dtype=self.dtype)
         grad = torch.empty(self.P, device=self.device, dtype=self.dtype)
+        self._fence()
         _lib.check_bsde(self._h, self._L.b200ude_bsde_loss_gradient(self._h, n_paths, seed, path_offset, total_paths, out.data_ptr(), grad.data_ptr(),
                                                                     out.data_ptr() + out.element_size()))
         o = out.cpu()
@@ -166,12 +174,14 @@ class BSDESolver:
     def adam_step(self, opt: ADAM, grad: torch.Tensor):
         """One ADAM update with a device gradient (e.g. after an all-reduce over path shards)."""
         g = grad.to(self.device, self.dtype).contiguous()
+        self._fence()
         a = self._adam(opt)
         _lib.check_bsde(self._h, self._L.b200ude_bsde_adam_step(self._h, C.byref(a), g.data_ptr()))
 
     def train_adam(self, opt: ADAM, n_paths, iters, seed0=1):
         """`iters` iterations on the device; returns (loss history, u0(x0) history) as device tensors."""
         hist = torch.empty(2, iters, device=self.device, dtype=self.dtype)
+        self._fence()
         a = self._adam(opt)
         _lib.check_bsde(self._h, self._L.b200ude_bsde_train_adam(self._h, C.byref(a), n_paths, iters, seed0, hist[0].data_ptr(), hist[1].data_ptr()))
         return hist[0].to(self.io_dtype), hist[1].to(self.io_dtype)
