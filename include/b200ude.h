@@ -252,7 +252,9 @@ int32_t b200ude_selftest_tanh(int32_t device, const void *x, void *y, size_t n, 
  * (out x in, column-major) then b -- Flux.params order.  relu'(0) = 1 (Flux 0.9 / Tracker differentiating max(zero(x), x)).
  * Time stepping: Euler-Maruyama with the fixed step T / n_steps (LambaEM is EM with step-size control).  Brownian increments:
  * sqrt(dt) * Box-Muller(Philox4x32-10) with counter (path, component / 4, step, 0) and key = seed; iteration i of
- * b200ude_bsde_train_adam uses seed0 + i.  dtype selects float or double for every buffer of the calls. */
+ * b200ude_bsde_train_adam uses seed0 + i.  dtype selects float or double for every buffer of the calls.
+ * Streams: these calls take no stream; they run on the handle's own stream and return when the work is complete.  Device arrays
+ * handed in (theta, a gradient for b200ude_bsde_adam_step) must be ready -- finish or synchronise the producing stream first. */
 typedef struct b200ude_bsde_handle b200ude_bsde_handle;
 typedef struct b200ude_bsde_desc {
     uint32_t struct_size; /* = sizeof(b200ude_bsde_desc) */
