@@ -812,6 +812,8 @@ __global__ void __launch_bounds__(32 * WGW, 1) k_wgrad(const WgradArgs a)
     double acc[FT][2];
 #pragma unroll
     for (int nt = 0; nt < FT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+    const int nti = (a.nact[l] + 7) / 8;             // input tiles the layer really has
+    const bool wactive = 8 * warp < a.nout[l];
     int b = 0, ph = 0;
     for (long ch = c_lo; ch < c_hi; ++ch) {
         mbar_wait(bar0 + 8u * b, (uint32_t)ph);
@@ -819,14 +821,18 @@ __global__ void __launch_bounds__(32 * WGW, 1) k_wgrad(const WgradArgs a)
         const long k0 = ch * WGR;
         const int rows = (int)(a.K - k0 < WGR ? a.K - k0 : WGR);
         const double *ap = sc + c * ldc + 8 * warp + r, *bp = sa + c * lda + r;
+        if (wactive) {   // (a warp whose unit tile lies beyond the layer's outputs only takes part in the ring protocol)
 #pragma unroll
-        for (int ks = 0; ks < WGR / 4; ++ks) {
-            const double av = 4 * ks + c < rows ? ap[ks * 4 * ldc] : 0.0;   // rows past the tape's end contribute nothing
-            double bv[FT];
+            for (int ks = 0; ks < WGR / 4; ++ks) {
+                const double av = 4 * ks + c < rows ? ap[ks * 4 * ldc] : 0.0;   // rows past the tape's end contribute nothing
+                double bv[FT];
 #pragma unroll
-            for (int nt = 0; nt < FT; ++nt) bv[nt] = bp[ks * 4 * lda + 8 * nt];
+                for (int nt = 0; nt < FT; ++nt)
+                    if (nt < nti) bv[nt] = bp[ks * 4 * lda + 8 * nt];
 #pragma unroll
-            for (int nt = 0; nt < FT; ++nt) dmma(acc[nt], av, bv[nt]);
+                for (int nt = 0; nt < FT; ++nt)
+                    if (nt < nti) dmma(acc[nt], av, bv[nt]);
+            }
         }
         __syncwarp();
         if (lane == 0) {   // release ... acquire around the reader counter; the last reader refills the stage
