@@ -111,3 +111,33 @@ def test_path_shards_over_two_ranks_add_up_gloo():
     want = np.concatenate([g["grad"], [float(g["loss"])]])
     for r in range(2):
         np.testing.assert_allclose(res[r], want, rtol=1e-11, atol=1e-14)
+
+
+def test_python_mirror_validates_and_never_falls_back():
+    """pde.py: wrong chain shapes / problem forms are ValueErrors before any native call; without a device the solve raises the library's
+    ENODEVICE -- the mirror has no CPU path (and does not import the oracle)."""
+    import math
+    import pytest
+    import torch
+    import universal_differential_equations_b200 as ude
+    from universal_differential_equations_b200 import pde, _lib
+    d, hls = 6, 8
+    prob = ude.TerminalPDEProblem(ude.HJBTerminal(), ude.HJBNonlinearity(1.0), ude.ZeroDrift(), ude.ConstantDiffusion(math.sqrt(2.0)), np.zeros(d), (0.0, 1.0))
+    u0 = ude.Chain(ude.Dense(d, hls, ude.relu), ude.Dense(hls, hls, ude.relu), ude.Dense(hls, 1))
+    sg = ude.Chain(ude.Dense(d + 1, hls, ude.relu), ude.Dense(hls, hls, ude.relu), ude.Dense(hls, hls, ude.relu), ude.Dense(hls, d))
+    with pytest.raises(ValueError):
+        ude.BSDESolver(prob, ude.NNPDENS(u0, u0), 4, 8)                                   # second chain has the wrong shape
+    with pytest.raises(ValueError):
+        ude.BSDESolver(prob, ude.NNPDENS(ude.Chain(ude.Dense(d, hls, ude.tanh), ude.Dense(hls, hls, ude.relu), ude.Dense(hls, 1)), sg), 4, 8)
+    bad = ude.TerminalPDEProblem(ude.HJBTerminal(), ude.HJBNonlinearity(1.0), ude.ZeroDrift(), ude.ConstantDiffusion(1.0), np.zeros(d), (0.5, 1.0))
+    with pytest.raises(ValueError):
+        ude.BSDESolver(bad, ude.NNPDENS(u0, sg), 4, 8)                                   # tspan must start at 0
+    assert pde.initial_params_pde(ude.NNPDENS(u0, sg)).size == sum(bo.num_params(d, hls))
+    import ast
+    mods = [n.module or "" for n in ast.walk(ast.parse(open(pde.__file__).read())) if isinstance(n, ast.ImportFrom)] + \
+           [a.name for n in ast.walk(ast.parse(open(pde.__file__).read())) if isinstance(n, ast.Import) for a in n.names]
+    assert not any("oracle" in m for m in mods), mods
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.B200UDEError) as e:
+            ude.solve(prob, ude.NNPDENS(u0, sg, opt=ude.ADAM(0.03)), maxiters=2, trajectories=8, alg=ude.LambaEM())
+        assert e.value.code == _lib.ENODEVICE
