@@ -12,6 +12,7 @@ from .sciml import (  # noqa: F401
     concrete_solve, identity, initial_params, rbf, remake, sciml_train, sciml_train_l2, solve, tanh,
 )
 from . import pde  # noqa: F401
+from . import jld2  # noqa: F401
 from .pde import (  # noqa: F401
     BSDESolver, ConstantDiffusion, HJBNonlinearity, HJBTerminal, LambaEM, NNPDENS, TerminalPDEProblem, ZeroDrift, initial_params_pde, relu,
 )
