@@ -82,3 +82,23 @@ def test_reader_lists_structs_without_decoding_them():
     with pytest.raises(KeyError):
         f.read("nope")
     assert set(jld2.load(os.path.join(REF, "Hudson_Bay_recovery.jld2"))) >= {"X", "t", "losses", "model_parameter"}
+
+
+@needs_ref
+def test_parameter_containers_are_followed_to_their_arrays(golden):
+    """`trained_parameters` (a ComponentVector) and `initial_parameters` (Lux's NamedTuple of layers) are Julia structs whose array fields
+    are references to other objects of the file: read_tree follows them and returns the very arrays the golden vectors hold."""
+    from universal_differential_equations_b200 import jld2
+    f = jld2.JLD2File(os.path.join(REF, "Scenario_1_recovery_0.005.jld2"))
+    (theta,) = f.read_tree("trained_parameters")
+    np.testing.assert_array_equal(theta, golden["scenario_1"]["theta_trained"])
+    layers = f.read_tree("initial_parameters")
+    assert [a.shape for a in layers] == [(5, 2), (5, 1), (5, 5), (5, 1), (5, 5), (5, 1), (2, 5), (2, 1)]
+    for k, w in zip(("W1_init", "W2_init", "W3_init", "W4_init"), layers[0::2]):
+        np.testing.assert_array_equal(w, golden["scenario_1"][k])
+    assert all(not b.any() for b in layers[1::2])                                  # Lux's zero biases
+    f2 = jld2.JLD2File(os.path.join(REF, "Scenario_2_recovery_0.005.jld2"))
+    np.testing.assert_array_equal(f2.read_tree("trained_parameters")[0], golden["scenario_2"]["theta_trained"])
+    np.testing.assert_array_equal(f2.read_tree("initial_parameters")[0], golden["scenario_2"]["theta_init"])
+    f3 = jld2.JLD2File(os.path.join(REF, "Scenario_3_recovery_0.005.jld2"))
+    np.testing.assert_array_equal(f3.read_tree("trained_parameters")[0], golden["scenario_3"]["theta_trained"])

@@ -137,8 +137,11 @@ class JLD2File:
         return list(self.links)
 
     def _describe(self, name):
+        return self._describe_at(self.links[name])
+
+    def _describe_at(self, addr):
         dims = dtype = layout = None
-        for mtype, d in self._messages(self.links[name]):
+        for mtype, d in self._messages(addr):
             if mtype == 1:                              # dataspace
                 ver, rank = d[0], d[1]
                 off = 8 if ver == 1 else 4
@@ -167,7 +170,10 @@ class JLD2File:
         dimensions slowest first, i.e. reversed)."""
         if name not in self.links:
             raise KeyError(name)
-        dims, dtype, layout = self._describe(name)
+        return self._read_at(self.links[name], name)
+
+    def _read_at(self, addr, name="<object>"):
+        dims, dtype, layout = self._describe_at(addr)
         if dims is None or dtype is None or layout is None:
             raise TypeError(f"{name}: not a plain numeric dataset (Julia struct / committed datatype)")
         count = int(np.prod(dims)) if dims else 1
@@ -179,6 +185,29 @@ class JLD2File:
         else:
             raw = np.frombuffer(layout[1], dtype, count)
         return np.array(raw).reshape(tuple(reversed(dims)), order="F")
+
+
+    def _object_at(self, addr):
+        pos = self.base + addr
+        return 0 < addr < len(self.blob) - self.base - 8 and self.blob[pos:pos + 4] == b"OHDR"
+
+    def read_tree(self, name, _addr=None, _depth=0):
+        """The numeric arrays reachable from a Julia struct stored under `name` (a `ComponentVector`'s data, the weights and biases of a
+        NamedTuple of layers, ...), depth first in field order.  JLD2 stores a struct as a fixed-size record whose array-valued fields are
+        8-byte references to other objects of the file; this follows every field that is such a reference without decoding the committed
+        compound type, so scalars that happen to look like an object address would be followed too -- meant for parameter containers."""
+        addr = self.links[name] if _addr is None else _addr
+        dims, dtype, layout = self._describe_at(addr)
+        if dims is not None and dtype is not None and layout is not None:
+            return [self._read_at(addr, name)]
+        out = []
+        if layout is not None and _depth < 8:
+            raw = layout[1] if layout[0] == "compact" else self.blob[self.base + layout[1]:self.base + layout[1] + layout[2]]
+            for k in range(0, len(raw) - 7, 8):
+                ref = struct.unpack_from("<Q", raw, k)[0]
+                if self._object_at(ref):
+                    out += self.read_tree(name, ref, _depth + 1)
+        return out
 
 
 def load(path, *names):
