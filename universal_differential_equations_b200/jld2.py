@@ -6,7 +6,8 @@ JLD2 0.1.x is an HDF5 container behind a 512-byte text header: superblock versio
 "OCHK" blocks), hard links in link messages.  This module walks the root group's links and decodes the datasets whose element type is an
 IEEE float or an integer with contiguous or compact layout -- the arrays a training run needs (data X, time points t, loss histories).
 Julia structs (the `ODESolution`, `ComponentVector`, Lux chains ... that the same files hold as committed compound types with object
-references) are listed by `keys()` but not decoded.  `save` writes Float32 / Float64 arrays with exactly the messages JLD2 itself emits
+references) are listed by `keys()`; `read_tree` follows a parameter container's references to its arrays, nothing else of a struct is
+decoded.  `save` writes Float32 / Float64 arrays with exactly the messages JLD2 itself emits
 for them (fill value, version-2 dataspace, IEEE datatype, compact or contiguous layout, lookup3 checksums): the dataset object headers
 it produces for the reference's own X / t / losses arrays are byte-identical to the ones in the reference's files (tests/test_jld2_reader.py).
 Pure Python + numpy, host side only; no HDF5 library is needed or used.
