@@ -170,6 +170,24 @@ def test_f64_repeat_is_bitwise_identical():
     s.close()
 
 
+def test_f64_training_curve_at_the_script_configuration_vs_oracle():
+    """300 ADAM(0.03) iterations at lambaem.jl's own sizes (d = 100, hls = 110, m = 100, 20 steps), Brownian seeds 1, 2, ...: the loss and
+    u0(x0) histories of the on-device loop against the oracle's committed curve (tests/golden/hjb_script_curve.npz,
+    tools/make_golden_bsde_curve.py).  Measured agreement 1.4e-14 relative over the whole curve; the tolerance leaves five orders."""
+    import os
+    ude = _ude()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hjb_script_curve.npz"))
+    d, hls, M, N, iters = int(g["d"]), int(g["hls"]), int(g["M"]), int(g["N"]), int(g["iters"])
+    prob, alg = _problem(ude, d, hls)
+    s = ude.BSDESolver(prob, alg, N, M, dtype=torch.float64)
+    s.set_params(bo.init_params(d, hls, seed=int(g["init_seed"])))
+    losses, u0s = s.train_adam(ude.ADAM(float(g["eta"])), M, iters, seed0=int(g["seed0"]))
+    np.testing.assert_allclose(losses.cpu().numpy(), g["losses"], rtol=1e-9)
+    np.testing.assert_allclose(u0s.cpu().numpy(), g["u0s"], rtol=1e-9, atol=1e-12)
+    assert abs(np.linalg.norm(s.get_params()) - float(g["theta_final_norm"])) <= 1e-9 * float(g["theta_final_norm"])
+    s.close()
+
+
 def test_path_shards_add_up():
     """Multi-GPU sharding rule (path_offset / total_paths): two half batches give the whole batch's loss and gradient."""
     ude = _ude()
