@@ -226,7 +226,7 @@ def cpu_pass(cfg, theta, u0, y, threads):
     from oracle import oracle as O
     m, w = cfg.oracle_model(O)
     t0 = time.perf_counter()
-    O.ensemble_loss_grad(m, theta.astype(np.float32), u0, y, w, cfg.dt, cfg.n_steps, save_every=cfg.every, n_threads=threads, want_gu0=True)
+    O.ensemble_loss_grad(m, theta.astype(np.float32), u0, y, w, cfg.dt, cfg.n_steps, save_every=cfg.every, n_threads=threads, want_gu0=False)   # as the GPU arm's timed step: loss + grad_theta
     return time.perf_counter() - t0
 
 
